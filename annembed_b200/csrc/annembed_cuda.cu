@@ -1,0 +1,1074 @@
+// annembed_cuda.cu -- kernels and C ABI of the B200-native cross-entropy embedding optimizer.
+// See include/annembed_cuda.h for the boundary and DESIGN.md for the data layout and rooflines.
+// Reference citations are relative to /root/reference/src.
+#include "../../include/annembed_cuda.h"
+
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen'ed in comm_init, never linked
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sgd_core.cuh"
+
+using namespace annembed;
+
+// =====================================================================================================
+// small host utilities
+// =====================================================================================================
+static thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        if (count == 0) { return cudaSuccess; }
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool load(std::string &err)
+    {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define LOADSYM(name) name = (decltype(name))dlsym(handle, "nccl" #name); if (!name) { err = "missing symbol nccl" #name; return false; }
+        LOADSYM(GetUniqueId) LOADSYM(CommInitRank) LOADSYM(CommDestroy) LOADSYM(AllGather) LOADSYM(AllReduce) LOADSYM(GetErrorString)
+#undef LOADSYM
+        return true;
+    }
+};
+static NcclApi g_nccl;
+
+struct annembed_cuda_ctx {
+    annembed_cuda_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int n_sm = 148;
+
+    // graph (replicated on every rank)
+    uint64_t n = 0, E = 0;
+    uint32_t kmax = 0;
+    DevBuf<uint64_t> row_ptr;
+    DevBuf<uint32_t> col;
+    DevBuf<float> dist, rho;
+    DevBuf<float> scale, proba;
+    bool have_graph = false, have_weights = false, have_build = false, have_embedding = false, have_alias = false;
+
+    // optimizer context (≙ EntropyOptim, embedder.rs:936-951)
+    DevBuf<float> emb_scale, inv_s2;
+    DevBuf<uint64_t> in_ptr_all;   // n+1, transposed index of the whole graph
+    DevBuf<uint4> in_rec;          // in-edge records of the owned slice
+    uint64_t in_base = 0;
+    DevBuf<uint2> neg_alias;
+    DevBuf<float> y[2], y0;
+    int cur = 0;
+    int DP = 2;
+
+    // shard
+    int rank = 0, nranks = 1;
+    uint32_t lo = 0, hi = 0, n_pad = 0;
+    ncclComm_t comm = nullptr;
+
+    // scratch
+    DevBuf<double> partials;
+    DevBuf<unsigned long long> counter;
+    DevBuf<unsigned long long> errword;
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+    annembed_cuda_stats st{};
+};
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return ANNEMBED_ERR_CUDA;                                                                \
+        }                                                                                            \
+    } while (0)
+
+#define REQUIRE(cond, code, msg)                                                                     \
+    do { if (!(cond)) { ctx->err = (msg); return (code); } } while (0)
+
+static inline unsigned int nblocks(uint64_t n, unsigned int bs) { return (unsigned int)((n + bs - 1) / bs); }
+static int pad_dim(uint32_t d) { return d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32; }
+
+// =====================================================================================================
+// kernels: graph validation, K0, K1, K1b, perplexity
+// =====================================================================================================
+enum { GERR_EMPTY = 1, GERR_COL = 2, GERR_SELF = 3, GERR_UNSORTED = 4, GERR_ROWPTR = 5 };
+
+__global__ void k_validate_graph(uint64_t n, uint64_t E, const uint64_t *__restrict__ row_ptr,
+                                 const uint32_t *__restrict__ col, const float *__restrict__ dist,
+                                 unsigned long long *err, unsigned int *kmax)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    unsigned int code = 0;
+    if (r1 < r0 || r1 > E) code = GERR_ROWPTR;
+    else if (r1 == r0) code = GERR_EMPTY;
+    else {
+        float prev = dist[r0];
+        if (!(prev >= 0.0f)) code = GERR_UNSORTED;          // NaN or negative distance
+        for (uint64_t m = r0; m < r1 && !code; m++) {
+            const uint32_t c = col[m];
+            const float d = dist[m];
+            if (c >= n) code = GERR_COL;
+            else if (c == i) code = GERR_SELF;
+            else if (!(d >= prev)) code = GERR_UNSORTED;
+            prev = d;
+        }
+        atomicMax(kmax, (unsigned int)(r1 - r0));
+    }
+    if (code) atomicMin(err, ((unsigned long long)i << 4) | code);
+}
+
+// K0: first-neighbour distance of every node, compacted (kdumap.rs:149-152 reads it k+1 times per node)
+__global__ void k_first_dist(uint64_t n, const uint64_t *__restrict__ row_ptr, const float *__restrict__ dist,
+                             float *__restrict__ rho)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rho[i] = dist[row_ptr[i]];
+}
+
+// K1: kdumap.rs:132-235.  One thread per node, sums in the reference's left-to-right order.
+// exp/pow are evaluated in fp64 and rounded once, i.e. correctly rounded fp32 functions.
+__global__ void __launch_bounds__(256)
+k_edge_weights(uint64_t n, const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+               const float *__restrict__ dist, const float *__restrict__ rho, float scale_rho, float beta,
+               float *__restrict__ scale_out, float *__restrict__ p_out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    const uint64_t k = r1 - r0;
+    const float rho_x = rho[i];
+    float sum = 0.0f;
+    for (uint64_t m = r0; m < r1; m++) sum = __fadd_rn(sum, rho[col[m]]);              // :149-152
+    sum = __fadd_rn(sum, rho_x);                                                        // :154
+    const float mean_rho = __fdiv_rn(sum, (float)(k + 1));                              // :155
+    const float scale = __fmul_rn(scale_rho, mean_rho);                                 // :159
+    scale_out[i] = scale;
+    bool all_equal = true;
+    float last_dist = 0.0f;
+    for (uint64_t m = r1; m > r0; m--) {                                                // :163-170
+        const float d = dist[m - 1];
+        if (d > 0.0f) { last_dist = d; all_equal = false; break; }
+    }
+    if (!all_equal && last_dist > rho_x) {
+        float wsum = 0.0f;
+        for (uint64_t m = r0; m < r1; m++) {
+            const float a = __fdiv_rn(fmaxf(__fsub_rn(dist[m], rho_x), 0.0f), scale);   // :172-174
+            const float pw = (beta == 1.0f) ? a : (float)pow((double)a, (double)beta);
+            float w = (float)exp(-(double)pw);
+            w = fmaxf(w, 1.0e-4f);                                                      // PROBA_MIN, NaN -> floor
+            p_out[m] = w;
+            wsum = __fadd_rn(wsum, w);                                                  // :215
+        }
+        for (uint64_t m = r0; m < r1; m++) p_out[m] = __fdiv_rn(p_out[m], wsum);        // :216-218
+    } else {
+        const float u = __fdiv_rn(1.0f, (float)k);                                      // :224-230
+        for (uint64_t m = r0; m < r1; m++) p_out[m] = u;
+    }
+}
+
+// nodeparam.rs:88-91
+__global__ void k_perplexity(uint64_t n, const uint64_t *__restrict__ row_ptr, const float *__restrict__ p,
+                             float *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float h = 0.0f;
+    for (uint64_t m = row_ptr[i]; m < row_ptr[i + 1]; m++) h += -p[m] * logf(p[m]);
+    out[i] = expf(h);
+}
+
+// K1b: embedder.rs:760-783 + tools/dichotomy.rs:4-65 (dead code in the reference; kept as an option)
+__device__ __forceinline__ float umap_f(const float *__restrict__ d, uint64_t r0, uint64_t r1, float rho, float beta)
+{
+    float s = 0.0f;
+    for (uint64_t m = r0; m < r1; m++) s = __fadd_rn(s, expf(-(d[m] - rho) * beta));
+    return s;
+}
+__global__ void k_edge_weights_umap(uint64_t n, const uint64_t *__restrict__ row_ptr, const float *__restrict__ dist,
+                                    float target, float *__restrict__ scale_out, float *__restrict__ w_out,
+                                    uint8_t *__restrict__ status)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    const float rho = dist[r0];
+    const float FMAX = 3.402823466e+38f;
+    float lower = 0.0f, upper = FMAX, middle = 1.0f;
+    const float fl = umap_f(dist, r0, r1, rho, lower), fu = umap_f(dist, r0, r1, rho, upper);
+    uint8_t st = 0;
+    if (fmaxf(fl, fu) < target || fminf(fu, fl) > target || fu > fl) st = 2;            // dichotomy.rs:21-33 panics
+    if (!st) {
+        int it = 0;
+        while (fabsf(target - umap_f(dist, r0, r1, rho, middle)) > 1.0e-5f) {          // :41
+            if (umap_f(dist, r0, r1, rho, middle) > target) lower = middle; else upper = middle;   // decreasing f
+            middle = (lower + upper) * 0.5f;
+            if (++it > 100) { st = 1; break; }                                          // :59-61
+        }
+    }
+    scale_out[i] = 1.0f / middle;
+    for (uint64_t m = r0; m < r1; m++) w_out[m] = expf(-(dist[m] - rho) * middle);
+    if (status) status[i] = st;
+}
+
+// =====================================================================================================
+// kernels: K2 and the transposed index
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_partial_sum_f64(uint64_t n, const T *__restrict__ x, double *__restrict__ partials)
+{
+    double s = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        s += (double)x[i];
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const double tot = BR(tmp).Sum(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+// fixed-order final sum -> deterministic
+__global__ void __launch_bounds__(256) k_final_sum_f64(unsigned int m, const double *__restrict__ partials, double *__restrict__ out)
+{
+    double s = 0.0;
+    for (unsigned int i = threadIdx.x; i < m; i += 256) s += partials[i];
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const double tot = BR(tmp).Sum(s);
+    if (threadIdx.x == 0) out[0] = tot;
+}
+
+// K2: embedder.rs:1356-1373.  mean from a deterministic fp64 reduction (the reference's sequential fp32 sum
+// drifts by ~1e-4 relative at 1e7 nodes)
+__global__ void k_embedded_scales(uint64_t n, const float *__restrict__ scale, const double *__restrict__ sum,
+                                  float *__restrict__ emb_scale, float *__restrict__ inv_s2)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float mean = (float)(sum[0] / (double)n);
+    const float s = 0.2f * fmaxf(fminf(__fdiv_rn(scale[i], mean), 4.0f), 0.25f);
+    emb_scale[i] = s;
+    inv_s2[i] = __fdiv_rn(1.0f, __fmul_rn(s, s));
+}
+
+__global__ void k_iota(uint64_t n, uint32_t *x)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = (uint32_t)i;
+}
+
+// in_ptr_all[v] = first position q with sorted_dst[q] >= v
+__global__ void k_in_ptr(uint64_t E, uint64_t n, const uint32_t *__restrict__ sorted_dst, uint64_t *__restrict__ in_ptr)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > E) return;
+    const uint64_t prev = (q == 0) ? 0 : (uint64_t)sorted_dst[q - 1] + 1;
+    const uint64_t curr = (q == E) ? n + 1 : (uint64_t)sorted_dst[q] + 1;   // exclusive upper of v to fill
+    for (uint64_t v = prev; v < curr; v++) in_ptr[v] = q;
+}
+
+__global__ void k_in_rec(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_t *__restrict__ sorted_eid,
+                         const uint64_t *__restrict__ row_ptr, const float *__restrict__ p,
+                         const float *__restrict__ inv_s2, uint4 *__restrict__ rec)
+{
+    const uint64_t q = q_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= q_hi) return;
+    const uint32_t e = sorted_eid[q];
+    uint64_t a = 0, b = n;                       // largest i with row_ptr[i] <= e
+    while (b - a > 1) { const uint64_t mid = (a + b) >> 1; if (row_ptr[mid] <= e) a = mid; else b = mid; }
+    rec[q - q_lo] = make_uint4((uint32_t)a, e, __float_as_uint(p[e]), __float_as_uint(inv_s2[a]));
+}
+
+__global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint32_t *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)(ptr[i + 1] - ptr[i]);
+}
+
+__global__ void k_pad_rows(uint64_t n, int d, int DP, const float *__restrict__ in, float *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (uint64_t)DP) return;
+    const uint64_t i = t / DP; const int c = (int)(t % DP);
+    out[t] = c < d ? in[i * d + c] : 0.0f;
+}
+__global__ void k_unpad_rows(uint64_t n, int d, int DP, const float *__restrict__ in, float *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (uint64_t)d) return;
+    const uint64_t i = t / d; const int c = (int)(t % d);
+    out[t] = in[i * DP + c];
+}
+
+// =====================================================================================================
+// kernels: K3, K4, K5, draws
+// =====================================================================================================
+// K3: strict list order on one thread (test mode: correctness, not speed)
+template <int DP>
+__global__ void k_step_fixed(float *Y, uint64_t n, const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                             const float *__restrict__ p, const float *__restrict__ inv_s2, SgdConst K, uint64_t n_samples,
+                             const uint64_t *__restrict__ edge_idx, const uint32_t *__restrict__ negs)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (uint64_t s = 0; s < n_samples; s++) {
+        const uint64_t e = edge_idx[s];
+        uint64_t a = 0, b = n;
+        while (b - a > 1) { const uint64_t mid = (a + b) >> 1; if (row_ptr[mid] <= e) a = mid; else b = mid; }
+        fixed_sample<DP>(Y, (uint32_t)a, col[e], p[e], inv_s2[a], K, negs + 5 * s);
+    }
+}
+
+// K4: one mini-epoch over the owned node range
+template <int DP, bool HUB>
+__global__ void __launch_bounds__(256) k_epoch(EpochArgs a, unsigned long long *sample_counter)
+{
+    const uint32_t node = a.lo + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int applied = 0;
+    if (node < a.hi) applied = epoch_node<DP, HUB>(a, node);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) applied += __shfl_xor_sync(0xffffffffu, applied, o);
+    if ((threadIdx.x & 31) == 0 && applied) atomicAdd(sample_counter, (unsigned long long)applied);
+}
+
+// K5: embedder.rs:1127-1163 + cauchy_edge_weight :1322-1345, fp64 like the reference
+template <int DP>
+__global__ void __launch_bounds__(256)
+k_cross_entropy(uint32_t lo, uint32_t hi, const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                const float *__restrict__ p, const float *__restrict__ emb_scale, const float *__restrict__ Y, double b,
+                double *__restrict__ partials)
+{
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
+        float yi[DP];
+        load_row<DP>(Y, (uint32_t)i, yi);
+        const double s = (double)emb_scale[i];
+        const double s2 = s * s;
+        for (uint64_t m = row_ptr[i]; m < row_ptr[i + 1]; m++) {
+            float yj[DP];
+            load_row<DP>(Y, col[m], yj);
+            float ds = 0.0f;
+#pragma unroll
+            for (int c = 0; c < DP; c++) { const float t = __fsub_rn(yi[c], yj[c]); ds = __fadd_rn(ds, __fmul_rn(t, t)); }
+            double x = (double)ds / s2;
+            x = (b == 1.0) ? x : pow(x, b);
+            float wf = (float)(1.0 / (1.0 + x));
+            if (!(wf < 1.0f)) wf = 1.0f - 1.1920929e-7f;                                 // :1338-1341
+            const double w = (double)wf, pe = (double)p[m];
+            if (w > 0.0) acc += -pe * log(w);
+            if (w < 1.0) acc += -(1.0 - pe) * log(1.0 - w);
+        }
+    }
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const double tot = BR(tmp).Sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
+template <bool HUB>
+__global__ void k_debug_draws(EpochArgs a, uint32_t *__restrict__ counts, uint32_t *__restrict__ negs_out)
+{
+    const uint64_t node = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= a.n) return;
+    const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
+    for (uint64_t m = r0; m < r1; m++) {
+        const uint32_t e = (uint32_t)m;
+        const Philox4 A = philox4x32_10(e, 0u, a.epoch, 0u, a.k0, a.k1);
+        const int c = firing_count(a.p[m], a.kappa, A.x);
+        counts[m] = (uint32_t)c;
+        if (negs_out) {
+            uint32_t negs[ANNEMBED_NB_NEG] = {ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE};
+            if (c > 0) draw_negatives<HUB>(a, e, 0u, A, (uint32_t)node, a.col[m], r0, r1, negs);
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++) negs_out[5 * m + q] = negs[q];
+        }
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+static int sync_stream(annembed_cuda_ctx *ctx)
+{
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return ANNEMBED_OK;
+}
+
+static int h2d(annembed_cuda_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->st.h2d_bytes += bytes;
+    return ANNEMBED_OK;
+}
+static int d2h(annembed_cuda_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->st.d2h_bytes += bytes;
+    return ANNEMBED_OK;
+}
+
+static int sum_f64(annembed_cuda_ctx *ctx, const float *x, uint64_t n, double *d_out /* device, partials[4095] */)
+{
+    const unsigned int nb = std::min<unsigned int>(2048u, std::max(1u, nblocks(n, 256)));
+    k_partial_sum_f64<float><<<nb, 256, 0, ctx->stream>>>(n, x, ctx->partials.p);
+    k_final_sum_f64<<<1, 256, 0, ctx->stream>>>(nb, ctx->partials.p, d_out);
+    ctx->st.kernel_launches += 2;
+    CU(cudaGetLastError());
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_default_params(annembed_cuda_params *p)
+{
+    if (!p) return ANNEMBED_ERR_INVALID_ARG;
+    memset(p, 0, sizeof(*p));
+    p->asked_dim = 2; p->dmap_init = 1; p->beta = 1.0; p->b = 1.0; p->scale_rho = 1.0; p->grad_step = 2.0;   // embedparams.rs:107-132
+    p->nb_sampling_by_edge = 10; p->nb_grad_batch = 20; p->grad_factor = 4; p->hierarchy_layer = 0; p->hubness_weighting = 0;
+    p->mini_epochs_per_batch = 0; p->seed = 0x5eedULL; p->flags = 0;
+    return ANNEMBED_OK;
+}
+
+extern "C" const char *annembed_cuda_last_error(const annembed_cuda_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int annembed_cuda_create(annembed_cuda_ctx **out, const annembed_cuda_params *params, int device)
+{
+    if (!out || !params) { g_create_error = "null argument"; return ANNEMBED_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (params->asked_dim == 0 || params->nb_grad_batch == 0 || params->nb_sampling_by_edge == 0 ||
+        !(params->b > 0.0) || !(params->beta > 0.0) || !(params->scale_rho > 0.0)) {
+        g_create_error = "invalid EmbedderParams (asked_dim, nb_grad_batch, nb_sampling_by_edge, b, beta, scale_rho must be > 0)";
+        return ANNEMBED_ERR_INVALID_ARG;
+    }
+    if (params->asked_dim > 32) { g_create_error = "asked_dim > 32 not supported on device"; return ANNEMBED_ERR_UNSUPPORTED; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return ANNEMBED_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device ordinal"; return ANNEMBED_ERR_INVALID_ARG; }
+    annembed_cuda_ctx *ctx = new annembed_cuda_ctx();
+    ctx->prm = *params;
+    if (ctx->prm.mini_epochs_per_batch == 0) ctx->prm.mini_epochs_per_batch = ctx->prm.nb_sampling_by_edge;
+    ctx->device = device;
+    ctx->DP = pad_dim(params->asked_dim);
+    auto fail = [&](const char *what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete ctx;
+        return ANNEMBED_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if ((e = ctx->partials.alloc(4096)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = ctx->counter.alloc(1)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = ctx->errword.alloc(2)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess) return fail("cudaEventCreate", e);
+    *out = ctx;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_destroy(annembed_cuda_ctx *ctx)
+{
+    if (!ctx) return ANNEMBED_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    for (auto ev : ctx->ev) cudaEventDestroy(ev);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_comm_unique_id(uint8_t unique_id[128])
+{
+    if (!unique_id) return ANNEMBED_ERR_INVALID_ARG;
+    if (!g_nccl.load(g_create_error)) return ANNEMBED_ERR_COMM;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return ANNEMBED_ERR_COMM; }
+    memcpy(unique_id, &id, 128);
+    return ANNEMBED_OK;
+}
+
+static void set_shard(annembed_cuda_ctx *ctx)
+{
+    const uint64_t n = ctx->n;
+    ctx->n_pad = (uint32_t)((n + ctx->nranks - 1) / ctx->nranks);
+    ctx->lo = (uint32_t)std::min<uint64_t>(n, (uint64_t)ctx->rank * ctx->n_pad);
+    ctx->hi = (uint32_t)std::min<uint64_t>(n, (uint64_t)(ctx->rank + 1) * ctx->n_pad);
+}
+
+extern "C" int annembed_cuda_comm_init(annembed_cuda_ctx *ctx, int rank, int nranks, const uint8_t unique_id[128])
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, ANNEMBED_ERR_INVALID_ARG, "bad rank / nranks");
+    REQUIRE(!ctx->have_graph, ANNEMBED_ERR_STATE, "comm_init must precede set_graph_csr");
+    CU(cudaSetDevice(ctx->device));
+    ctx->rank = rank; ctx->nranks = nranks;
+    if (nranks == 1) return ANNEMBED_OK;
+    REQUIRE(unique_id != nullptr, ANNEMBED_ERR_INVALID_ARG, "unique_id is null");
+    if (!g_nccl.load(ctx->err)) return ANNEMBED_ERR_COMM;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); ctx->comm = nullptr; return ANNEMBED_ERR_COMM; }
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, const uint64_t *row_ptr,
+                                           const uint32_t *col, const float *dist)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(row_ptr && col && dist, ANNEMBED_ERR_INVALID_ARG, "null graph pointer");
+    REQUIRE(n >= 1, ANNEMBED_ERR_INVALID_ARG, "graph has no node");
+    REQUIRE(n < 0xFFFFFFFFull, ANNEMBED_ERR_UNSUPPORTED, "n >= 2^32-1 not supported");
+    REQUIRE(row_ptr[0] == 0, ANNEMBED_ERR_INVALID_ARG, "row_ptr[0] != 0");
+    const uint64_t E = row_ptr[n];
+    REQUIRE(E < 0xFFFFFFFFull, ANNEMBED_ERR_UNSUPPORTED, "E >= 2^32-1 not supported");
+    REQUIRE(E >= 1, ANNEMBED_ERR_EMPTY_ROW, "graph has no edge (node 0 has no neighbour)");
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_graph = ctx->have_weights = ctx->have_build = ctx->have_embedding = false;
+    ctx->n = n; ctx->E = E;
+    set_shard(ctx);
+    CU(ctx->row_ptr.alloc(n + 1)); CU(ctx->col.alloc(E)); CU(ctx->dist.alloc(E)); CU(ctx->rho.alloc(n));
+    CU(ctx->scale.alloc(n)); CU(ctx->proba.alloc(E));
+    int rc;
+    if ((rc = h2d(ctx, ctx->row_ptr.p, row_ptr, (n + 1) * sizeof(uint64_t)))) return rc;
+    if ((rc = h2d(ctx, ctx->col.p, col, E * sizeof(uint32_t)))) return rc;
+    if ((rc = h2d(ctx, ctx->dist.p, dist, E * sizeof(float)))) return rc;
+    // validate on the device
+    unsigned long long init[2] = {~0ull, 0ull};
+    CU(cudaMemcpyAsync(ctx->errword.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    k_validate_graph<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, E, ctx->row_ptr.p, ctx->col.p, ctx->dist.p, ctx->errword.p,
+                                                               (unsigned int *)(ctx->errword.p + 1));
+    ctx->st.kernel_launches++;
+    unsigned long long res[2];
+    CU(cudaMemcpyAsync(res, ctx->errword.p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = sync_stream(ctx))) return rc;
+    if (res[0] != ~0ull) {
+        const unsigned long long node = res[0] >> 4;
+        const unsigned int code = (unsigned int)(res[0] & 15);
+        char buf[160];
+        switch (code) {
+        case GERR_EMPTY: snprintf(buf, sizeof buf, "node rank %llu has no neighbour (kdumap.rs:75-85)", node); ctx->err = buf; return ANNEMBED_ERR_EMPTY_ROW;
+        case GERR_UNSORTED: snprintf(buf, sizeof buf, "row %llu: distances not ascending / not finite (kgraph.rs:508-509)", node); ctx->err = buf; return ANNEMBED_ERR_UNSORTED_ROW;
+        case GERR_COL: snprintf(buf, sizeof buf, "row %llu: neighbour index >= n", node); break;
+        case GERR_SELF: snprintf(buf, sizeof buf, "row %llu: self edge (embedder.rs:1201)", node); break;
+        default: snprintf(buf, sizeof buf, "row %llu: row_ptr not monotone", node); break;
+        }
+        ctx->err = buf;
+        return ANNEMBED_ERR_INVALID_ARG;
+    }
+    ctx->kmax = (uint32_t)(res[1] & 0xFFFFFFFFu);
+    if (n < (uint64_t)ctx->kmax + 3) {
+        ctx->err = "graph too small: no node acceptable as negative sample (embedder.rs:1241-1252 would not terminate)";
+        return ANNEMBED_ERR_NO_NEGATIVE;
+    }
+    k_first_dist<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr.p, ctx->dist.p, ctx->rho.p);
+    ctx->st.kernel_launches++;
+    if ((rc = sync_stream(ctx))) return rc;
+    ctx->have_graph = true;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_edge_weights(annembed_cuda_ctx *ctx, float *scale_out, float *proba_out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "edge_weights: graph not set");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    k_edge_weights<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->row_ptr.p, ctx->col.p, ctx->dist.p, ctx->rho.p,
+                                                                  (float)ctx->prm.scale_rho, (float)ctx->prm.beta,
+                                                                  ctx->scale.p, ctx->proba.p);
+    ctx->st.kernel_launches++;
+    CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+    int rc;
+    if ((rc = sync_stream(ctx))) return rc;
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ctx->st.edge_weights_ms = ms;
+    ctx->have_weights = true; ctx->have_build = false;
+    if (scale_out && (rc = d2h(ctx, scale_out, ctx->scale.p, ctx->n * sizeof(float)))) return rc;
+    if (proba_out && (rc = d2h(ctx, proba_out, ctx->proba.p, ctx->E * sizeof(float)))) return rc;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_edge_weights_umap(annembed_cuda_ctx *ctx, float norm, float *scale_out, float *weight_out,
+                                               uint8_t *status_out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "edge_weights_umap: graph not set");
+    REQUIRE(scale_out && weight_out, ANNEMBED_ERR_INVALID_ARG, "null output");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<float> s, w; DevBuf<uint8_t> st;
+    CU(s.alloc(ctx->n)); CU(w.alloc(ctx->E)); CU(st.alloc(ctx->n));
+    k_edge_weights_umap<<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->row_ptr.p, ctx->dist.p, norm, s.p, w.p, st.p);
+    ctx->st.kernel_launches++;
+    int rc;
+    if ((rc = sync_stream(ctx))) return rc;
+    if ((rc = d2h(ctx, scale_out, s.p, ctx->n * sizeof(float)))) return rc;
+    if ((rc = d2h(ctx, weight_out, w.p, ctx->E * sizeof(float)))) return rc;
+    if (status_out && (rc = d2h(ctx, status_out, st.p, ctx->n))) return rc;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_set_edge_weights(annembed_cuda_ctx *ctx, const float *scale, const float *proba)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_edge_weights: graph not set");
+    REQUIRE(scale && proba, ANNEMBED_ERR_INVALID_ARG, "null weights");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = h2d(ctx, ctx->scale.p, scale, ctx->n * sizeof(float)))) return rc;
+    if ((rc = h2d(ctx, ctx->proba.p, proba, ctx->E * sizeof(float)))) return rc;
+    ctx->have_weights = true; ctx->have_build = false;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_get_perplexity(annembed_cuda_ctx *ctx, float *out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_weights, ANNEMBED_ERR_STATE, "get_perplexity: edge weights not computed");
+    REQUIRE(out, ANNEMBED_ERR_INVALID_ARG, "null output");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<float> t; CU(t.alloc(ctx->n));
+    k_perplexity<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->row_ptr.p, ctx->proba.p, t.p);
+    ctx->st.kernel_launches++;
+    int rc;
+    if ((rc = sync_stream(ctx))) return rc;
+    return d2h(ctx, out, t.p, ctx->n * sizeof(float));
+}
+
+// Vose alias table on the host (setup, O(n)); ≙ WeightedAliasIndex::new in NodeSampler::new (embedder.rs:916-919)
+extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float *w)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_neg_weights: graph not set");
+    CU(cudaSetDevice(ctx->device));
+    if (!w) { ctx->have_alias = false; ctx->neg_alias.release(); return ANNEMBED_OK; }
+    const uint64_t n = ctx->n;
+    double tot = 0.0;
+    for (uint64_t i = 0; i < n; i++) {
+        REQUIRE(w[i] >= 0.0f && std::isfinite(w[i]), ANNEMBED_ERR_INVALID_ARG, "negative / non-finite sampling weight");
+        tot += w[i];
+    }
+    REQUIRE(tot > 0.0, ANNEMBED_ERR_INVALID_ARG, "all sampling weights are zero");
+    std::vector<double> q(n);
+    std::vector<uint32_t> small, large;
+    small.reserve(n); large.reserve(n);
+    std::vector<uint2> tab(n);
+    for (uint64_t i = 0; i < n; i++) {
+        q[i] = (double)w[i] * (double)n / tot;
+        (q[i] < 1.0 ? small : large).push_back((uint32_t)i);
+    }
+    auto put = [&](uint32_t i, float prob, uint32_t alias) { uint32_t bits; memcpy(&bits, &prob, 4); tab[i] = make_uint2(bits, alias); };
+    while (!small.empty() && !large.empty()) {
+        const uint32_t s = small.back(); small.pop_back();
+        const uint32_t l = large.back(); large.pop_back();
+        put(s, (float)q[s], l);
+        q[l] = (q[l] + q[s]) - 1.0;
+        (q[l] < 1.0 ? small : large).push_back(l);
+    }
+    for (uint32_t l : large) put(l, 1.0f, l);
+    for (uint32_t s : small) put(s, 1.0f, s);
+    CU(ctx->neg_alias.alloc(n));
+    int rc;
+    if ((rc = h2d(ctx, ctx->neg_alias.p, tab.data(), n * sizeof(uint2)))) return rc;
+    ctx->have_alias = true;
+    return ANNEMBED_OK;
+}
+
+// device context build: K2 + transposed index (≙ EntropyOptim::new, embedder.rs:964-1025)
+static int ensure_build(annembed_cuda_ctx *ctx)
+{
+    if (ctx->have_build) return ANNEMBED_OK;
+    REQUIRE(ctx->have_weights, ANNEMBED_ERR_STATE, "edge weights not computed (embedder.rs:802-808: initial_space not constructed)");
+    const uint64_t n = ctx->n, E = ctx->E;
+    CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); CU(ctx->in_ptr_all.alloc(n + 2));
+    int rc;
+    // K2
+    if ((rc = sum_f64(ctx, ctx->scale.p, n, ctx->partials.p + 4095))) return rc;
+    k_embedded_scales<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->scale.p, ctx->partials.p + 4095, ctx->emb_scale.p, ctx->inv_s2.p);
+    ctx->st.kernel_launches++;
+    // transposed index: stable radix sort of (dst, edge id)
+    {
+        DevBuf<uint32_t> eid, dst_sorted, eid_sorted;
+        DevBuf<unsigned char> tmp;
+        CU(eid.alloc(E)); CU(dst_sorted.alloc(E)); CU(eid_sorted.alloc(E));
+        k_iota<<<nblocks(E, 256), 256, 0, ctx->stream>>>(E, eid.p);
+        int bits = 1; while (bits < 32 && (1ull << bits) < n) bits++;
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
+        CU(tmp.alloc(tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
+        k_in_ptr<<<nblocks(E + 1, 256), 256, 0, ctx->stream>>>(E, n, dst_sorted.p, ctx->in_ptr_all.p);
+        ctx->st.kernel_launches += 3;
+        uint64_t qr[2];
+        CU(cudaMemcpyAsync(&qr[0], ctx->in_ptr_all.p + ctx->lo, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&qr[1], ctx->in_ptr_all.p + ctx->hi, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = sync_stream(ctx))) return rc;
+        ctx->in_base = qr[0];
+        const uint64_t cnt = qr[1] - qr[0];
+        CU(ctx->in_rec.alloc(std::max<uint64_t>(cnt, 1)));
+        if (cnt) {
+            k_in_rec<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, ctx->row_ptr.p, ctx->proba.p,
+                                                                 ctx->inv_s2.p, ctx->in_rec.p);
+            ctx->st.kernel_launches++;
+        }
+        if ((rc = sync_stream(ctx))) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+    if ((rc = sync_stream(ctx))) return rc;
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ctx->st.build_ms = ms;
+    ctx->have_build = true;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_get_hubness_counts(annembed_cuda_ctx *ctx, uint32_t *counts)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(counts, ANNEMBED_ERR_INVALID_ARG, "null output");
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "get_hubness_counts: graph not set");
+    CU(cudaSetDevice(ctx->device));
+    // in-degree = histogram of col; independent of the weights: sort-free path through atomics is not needed,
+    // the transposed index gives it when built, else build a throw-away one.
+    if (!ctx->have_build) {
+        const bool hw = ctx->have_weights;
+        if (!hw) { CU(cudaMemsetAsync(ctx->scale.p, 0, ctx->n * sizeof(float), ctx->stream)); CU(cudaMemsetAsync(ctx->proba.p, 0, ctx->E * sizeof(float), ctx->stream)); ctx->have_weights = true; }
+        int rc = ensure_build(ctx);
+        if (!hw) { ctx->have_weights = false; ctx->have_build = false; }
+        if (rc) return rc;
+    }
+    DevBuf<uint32_t> t; CU(t.alloc(ctx->n));
+    k_degree_u32<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->in_ptr_all.p, t.p);
+    ctx->st.kernel_launches++;
+    int rc;
+    if ((rc = sync_stream(ctx))) return rc;
+    return d2h(ctx, counts, t.p, ctx->n * sizeof(uint32_t));
+}
+
+extern "C" int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *y)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_embedding: graph not set");
+    REQUIRE(y, ANNEMBED_ERR_INVALID_ARG, "null embedding");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->n, rows = (uint64_t)ctx->n_pad * ctx->nranks;
+    const int d = (int)ctx->prm.asked_dim, DP = ctx->DP;
+    if (ctx->y[0].n != rows * DP) {
+        CU(ctx->y[0].alloc(rows * DP)); CU(ctx->y[1].alloc(rows * DP)); CU(ctx->y0.alloc(rows * DP));
+        CU(cudaMemsetAsync(ctx->y[0].p, 0, rows * DP * sizeof(float), ctx->stream));
+        CU(cudaMemsetAsync(ctx->y[1].p, 0, rows * DP * sizeof(float), ctx->stream));
+        CU(cudaMemsetAsync(ctx->y0.p, 0, rows * DP * sizeof(float), ctx->stream));
+    }
+    int rc;
+    if (d == DP) {
+        if ((rc = h2d(ctx, ctx->y0.p, y, n * d * sizeof(float)))) return rc;
+    } else {
+        DevBuf<float> stage; CU(stage.alloc(n * d));
+        if ((rc = h2d(ctx, stage.p, y, n * d * sizeof(float)))) return rc;
+        k_pad_rows<<<nblocks(n * DP, 256), 256, 0, ctx->stream>>>(n, d, DP, stage.p, ctx->y0.p);
+        ctx->st.kernel_launches++;
+        if ((rc = sync_stream(ctx))) return rc;
+    }
+    ctx->have_embedding = true;
+    return annembed_cuda_reset_embedding(ctx);
+}
+
+extern "C" int annembed_cuda_reset_embedding(annembed_cuda_ctx *ctx)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_embedding, ANNEMBED_ERR_STATE, "reset_embedding: embedding not set");
+    CU(cudaSetDevice(ctx->device));
+    ctx->cur = 0;
+    CU(cudaMemcpyAsync(ctx->y[0].p, ctx->y0.p, ctx->y0.n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return sync_stream(ctx);
+}
+
+extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(out, ANNEMBED_ERR_INVALID_ARG, "null output");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_build(ctx))) return rc;
+    return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
+}
+
+static SgdConst make_const(const annembed_cuda_ctx *ctx, double grad_step)
+{
+    SgdConst K;
+    K.gamma = (float)grad_step;
+    K.b = (float)ctx->prm.b;
+    K.two_b = (float)(2.0 * ctx->prm.b);
+    K.b_is_one = ctx->prm.b == 1.0;
+    return K;
+}
+
+extern "C" int annembed_cuda_step_fixed(annembed_cuda_ctx *ctx, uint64_t n_samples, const uint64_t *edge_idx,
+                                        const uint32_t *neg_idx, double grad_step)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_embedding, ANNEMBED_ERR_STATE, "step_fixed: embedding not set");
+    REQUIRE(ctx->nranks == 1, ANNEMBED_ERR_UNSUPPORTED, "step_fixed is single-GPU (test mode)");
+    if (n_samples == 0) return ANNEMBED_OK;
+    REQUIRE(edge_idx && neg_idx, ANNEMBED_ERR_INVALID_ARG, "null sample list");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_build(ctx))) return rc;
+    for (uint64_t s = 0; s < n_samples; s++) {
+        REQUIRE(edge_idx[s] < ctx->E, ANNEMBED_ERR_INVALID_ARG, "edge index out of range");
+        for (int q = 0; q < 5; q++) REQUIRE(neg_idx[5 * s + q] < ctx->n, ANNEMBED_ERR_INVALID_ARG, "negative index out of range");
+    }
+    DevBuf<uint64_t> de; DevBuf<uint32_t> dn;
+    CU(de.alloc(n_samples)); CU(dn.alloc(n_samples * 5));
+    if ((rc = h2d(ctx, de.p, edge_idx, n_samples * sizeof(uint64_t)))) return rc;
+    if ((rc = h2d(ctx, dn.p, neg_idx, n_samples * 5 * sizeof(uint32_t)))) return rc;
+    const SgdConst K = make_const(ctx, grad_step);
+    float *Y = ctx->y[ctx->cur].p;
+#define LAUNCH_FIXED(DPV) k_step_fixed<DPV><<<1, 32, 0, ctx->stream>>>(Y, ctx->n, ctx->row_ptr.p, ctx->col.p, ctx->proba.p, ctx->inv_s2.p, K, n_samples, de.p, dn.p)
+    switch (ctx->DP) {
+    case 2: LAUNCH_FIXED(2); break;
+    case 4: LAUNCH_FIXED(4); break;
+    case 8: LAUNCH_FIXED(8); break;
+    case 16: LAUNCH_FIXED(16); break;
+    default: LAUNCH_FIXED(32); break;
+    }
+#undef LAUNCH_FIXED
+    ctx->st.kernel_launches++;
+    return sync_stream(ctx);
+}
+
+static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double grad_step)
+{
+    EpochArgs a;
+    a.y_snap = ctx->y[ctx->cur].p;
+    a.y_next = ctx->y[ctx->cur ^ 1].p;
+    a.row_ptr = ctx->row_ptr.p; a.col = ctx->col.p; a.p = ctx->proba.p; a.inv_s2 = ctx->inv_s2.p;
+    a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
+    a.neg_alias = ctx->neg_alias.p;
+    a.n = (uint32_t)ctx->n; a.lo = ctx->lo; a.hi = ctx->hi;
+    a.epoch = epoch;
+    a.k0 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu); a.k1 = (uint32_t)(ctx->prm.seed >> 32);
+    // expected firings of edge e per mini-epoch: nb_sampling_by_edge * E * (p_e / n) / M   (embedder.rs:858,987)
+    a.kappa = (float)((double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)ctx->n) / (double)ctx->prm.mini_epochs_per_batch);
+    a.K = make_const(ctx, grad_step);
+    return a;
+}
+
+template <bool HUB>
+static void launch_epoch(annembed_cuda_ctx *ctx, const EpochArgs &a)
+{
+    const unsigned int nb = nblocks(a.hi - a.lo, 256);
+    if (nb == 0) return;
+    switch (ctx->DP) {
+    case 2: k_epoch<2, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
+    case 4: k_epoch<4, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
+    case 8: k_epoch<8, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
+    case 16: k_epoch<16, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
+    default: k_epoch<32, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
+    }
+}
+
+static int use_hubness(annembed_cuda_ctx *ctx, bool *hub)
+{
+    *hub = ctx->prm.hubness_weighting != 0;
+    if (*hub) REQUIRE(ctx->have_alias, ANNEMBED_ERR_STATE, "hubness_weighting set but set_neg_weights was not called");
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t first_batch, uint32_t n_batches)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "optimize: graph not set");
+    REQUIRE(ctx->have_embedding, ANNEMBED_ERR_STATE, "optimize: initial embedding not set");
+    REQUIRE(first_batch >= 1, ANNEMBED_ERR_INVALID_ARG, "batches are numbered from 1 (embedder.rs:873)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    bool hub;
+    if ((rc = use_hubness(ctx, &hub))) return rc;
+    if ((rc = ensure_build(ctx))) return rc;
+    const uint32_t nb = ctx->prm.nb_grad_batch, M = ctx->prm.mini_epochs_per_batch;
+    const uint32_t last = std::min<uint64_t>((uint64_t)first_batch + n_batches, (uint64_t)nb + 1);   // exclusive
+    const size_t n_launch = first_batch < last ? (size_t)(last - first_batch) * M : 0;
+    while (ctx->ev.size() < 2 * n_launch + 2 * n_launch * (ctx->nranks > 1)) {
+        cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
+    }
+    CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    size_t li = 0;
+    const size_t xoff = 2 * n_launch;
+    for (uint32_t iter = first_batch; iter < last; iter++) {
+        const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
+        for (uint32_t m = 0; m < M; m++, li++) {
+            const EpochArgs a = make_epoch_args(ctx, (iter - 1) * M + m, grad_step);
+            CU(cudaEventRecord(ctx->ev[2 * li], ctx->stream));
+            if (hub) launch_epoch<true>(ctx, a); else launch_epoch<false>(ctx, a);
+            CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
+            if (ctx->nranks > 1) {
+                // replicate the updated rows: in-place all-gather of the owned slice of y_next
+                float *buf = ctx->y[ctx->cur ^ 1].p;
+                const size_t cnt = (size_t)ctx->n_pad * ctx->DP;
+                CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
+                ncclResult_t r = g_nccl.AllGather(buf + (size_t)ctx->rank * cnt, buf, cnt, ncclFloat, ctx->comm, ctx->stream);
+                if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+                CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream));
+            }
+            ctx->cur ^= 1;
+        }
+    }
+    CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, ctx->counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = sync_stream(ctx))) return rc;
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    double kms = 0, xms = 0;
+    for (size_t i = 0; i < n_launch; i++) {
+        float t = 0; CU(cudaEventElapsedTime(&t, ctx->ev[2 * i], ctx->ev[2 * i + 1])); kms += t;
+        if (ctx->nranks > 1) { CU(cudaEventElapsedTime(&t, ctx->ev[xoff + 2 * i], ctx->ev[xoff + 2 * i + 1])); xms += t; }
+    }
+    ctx->st.optimize_ms = ms; ctx->st.epoch_kernel_ms = kms; ctx->st.exchange_ms = xms;
+    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_launch;
+    ctx->st.positive_samples = cnt; ctx->st.edge_updates = 6 * cnt;
+    ctx->st.model_bytes = (double)cnt * (12.0 + 36.0 * (double)ctx->prm.asked_dim);
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_cross_entropy(annembed_cuda_ctx *ctx, double *out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(out, ANNEMBED_ERR_INVALID_ARG, "null output");
+    REQUIRE(ctx->have_embedding, ANNEMBED_ERR_STATE, "cross_entropy: embedding not set");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_build(ctx))) return rc;
+    CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    const unsigned int nb = std::min<unsigned int>(2048u, std::max(1u, nblocks(ctx->hi - ctx->lo, 256)));
+    const float *Y = ctx->y[ctx->cur].p;
+#define LAUNCH_CE(DPV) k_cross_entropy<DPV><<<nb, 256, 0, ctx->stream>>>(ctx->lo, ctx->hi, ctx->row_ptr.p, ctx->col.p, ctx->proba.p, ctx->emb_scale.p, Y, ctx->prm.b, ctx->partials.p)
+    switch (ctx->DP) {
+    case 2: LAUNCH_CE(2); break;
+    case 4: LAUNCH_CE(4); break;
+    case 8: LAUNCH_CE(8); break;
+    case 16: LAUNCH_CE(16); break;
+    default: LAUNCH_CE(32); break;
+    }
+#undef LAUNCH_CE
+    k_final_sum_f64<<<1, 256, 0, ctx->stream>>>(nb, ctx->partials.p, ctx->partials.p + 4095);
+    ctx->st.kernel_launches += 2;
+    if (ctx->nranks > 1) {
+        ncclResult_t r = g_nccl.AllReduce(ctx->partials.p + 4095, ctx->partials.p + 4095, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+    }
+    CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+    double v = 0;
+    CU(cudaMemcpyAsync(&v, ctx->partials.p + 4095, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = sync_stream(ctx))) return rc;
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ctx->st.cross_entropy_ms = ms;
+    ctx->st.d2h_bytes += sizeof(double);
+    *out = v;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_optimize(annembed_cuda_ctx *ctx, double *ce_initial, double *ce_final)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    int rc;
+    if (ce_initial && (rc = annembed_cuda_cross_entropy(ctx, ce_initial))) return rc;      // embedder.rs:846
+    if ((rc = annembed_cuda_optimize_batches(ctx, 1, ctx->prm.nb_grad_batch))) return rc;  // :873-879
+    if (ce_final && (rc = annembed_cuda_cross_entropy(ctx, ce_final))) return rc;          // :885
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_get_embedding(annembed_cuda_ctx *ctx, float *y_out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(y_out, ANNEMBED_ERR_INVALID_ARG, "null output");
+    REQUIRE(ctx->have_embedding, ANNEMBED_ERR_STATE, "get_embedding: embedding not set (embedder.rs:384 panics before embed)");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->n;
+    const int d = (int)ctx->prm.asked_dim, DP = ctx->DP;
+    if (d == DP) return d2h(ctx, y_out, ctx->y[ctx->cur].p, n * d * sizeof(float));
+    DevBuf<float> stage; CU(stage.alloc(n * d));
+    k_unpad_rows<<<nblocks(n * d, 256), 256, 0, ctx->stream>>>(n, d, DP, ctx->y[ctx->cur].p, stage.p);
+    ctx->st.kernel_launches++;
+    int rc;
+    if ((rc = sync_stream(ctx))) return rc;
+    return d2h(ctx, y_out, stage.p, n * d * sizeof(float));
+}
+
+extern "C" int annembed_cuda_get_stats(annembed_cuda_ctx *ctx, annembed_cuda_stats *stats)
+{
+    if (!ctx || !stats) return ANNEMBED_ERR_INVALID_ARG;
+    *stats = ctx->st;
+    return ANNEMBED_OK;
+}
+extern "C" int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    memset(&ctx->st, 0, sizeof(ctx->st));
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_debug_draws(annembed_cuda_ctx *ctx, uint32_t epoch, uint32_t *counts_out, uint32_t *neg_out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(counts_out, ANNEMBED_ERR_INVALID_ARG, "null output");
+    REQUIRE(ctx->have_graph && ctx->have_weights, ANNEMBED_ERR_STATE, "debug_draws: graph / weights not set");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    bool hub;
+    if ((rc = use_hubness(ctx, &hub))) return rc;
+    DevBuf<uint32_t> dc, dn;
+    CU(dc.alloc(ctx->E));
+    if (neg_out) CU(dn.alloc(ctx->E * 5));
+    EpochArgs a = make_epoch_args(ctx, epoch, 0.0);
+    if (hub) k_debug_draws<true><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);
+    else k_debug_draws<false><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);
+    ctx->st.kernel_launches++;
+    if ((rc = sync_stream(ctx))) return rc;
+    if ((rc = d2h(ctx, counts_out, dc.p, ctx->E * sizeof(uint32_t)))) return rc;
+    if (neg_out && (rc = d2h(ctx, neg_out, dn.p, ctx->E * 5 * sizeof(uint32_t)))) return rc;
+    return ANNEMBED_OK;
+}

@@ -1,0 +1,305 @@
+// Per-sample arithmetic of the cross-entropy optimizer and the per-node mini-epoch body.
+//
+// Follows /root/reference/src/embedder.rs:1167-1302 (ce_optim_edge_shannon): one positive edge is an
+// attraction that moves both ends, followed by 5 accepted negatives that repel the origin node only.
+// The reference computes coefficients in f64 from f32 coordinates; here everything is fp32
+// (tolerance 1e-4 for one step, tests/test_step_fixed.py).
+//
+// The functions are __host__ __device__ so that tests/hostsim can compile the SAME source for the host
+// and replay a mini-epoch on the CPU when no GPU is around (test tooling; the product never does that).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "philox.cuh"
+
+namespace annembed {
+
+#define ANNEMBED_NB_NEG 5          // embedder.rs:1241 asked_nb_neg
+#define ANNEMBED_MAX_REDRAW 24     // bounded replacement for the reference's unbounded rejection loop (:1244)
+#define ANNEMBED_NO_NODE 0xFFFFFFFFu
+
+struct SgdConst {
+    float gamma;     // grad_step of this batch (embedder.rs:875)
+    float b;         // Cauchy exponent
+    float two_b;
+    int   b_is_one;
+};
+
+__host__ __device__ __forceinline__ float fast_div(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+__host__ __device__ __forceinline__ float as_float(uint32_t u)
+{
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t as_uint(float f)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+
+// ---- rows of the layout: DP floats per node (asked_dim padded with zeros), vector loads ----------
+template <int DP>
+__host__ __device__ __forceinline__ void load_row(const float *__restrict__ Y, uint32_t idx, float (&v)[DP])
+{
+    const float *r = Y + (size_t)idx * DP;
+    if constexpr (DP == 1) {
+        v[0] = r[0];
+    } else if constexpr (DP == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(r);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < DP; c += 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(r + c);
+            v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+        }
+    }
+}
+template <int DP>
+__host__ __device__ __forceinline__ void store_row(float *__restrict__ Y, uint32_t idx, const float (&v)[DP])
+{
+    float *r = Y + (size_t)idx * DP;
+    if constexpr (DP == 1) {
+        r[0] = v[0];
+    } else if constexpr (DP == 2) {
+        *reinterpret_cast<float2 *>(r) = make_float2(v[0], v[1]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < DP; c += 4)
+            *reinterpret_cast<float4 *>(r + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+}
+
+template <int DP>
+__host__ __device__ __forceinline__ float sqdist(const float (&a)[DP], const float (&b)[DP])
+{
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < DP; c++) { const float t = a[c] - b[c]; s += t * t; }   // embedder.rs:1206-1211 order
+    return s;
+}
+
+// common coefficient, embedder.rs:1216-1222 / :1276-1282
+__host__ __device__ __forceinline__ float cauchy_coeff(float u, float inv_s2, const SgdConst &K)
+{
+    if (K.b_is_one) return fast_div(K.two_b * inv_s2, 1.0f + u);
+    const float pw = powf(u, K.b);
+    return K.two_b * (1.0f / (1.0f + pw)) * powf(u, K.b - 1.0f) * inv_s2;
+}
+
+// Positive edge (i -> j, proba p): embedder.rs:1202-1238.  yi/yj are local copies, g the sample's gradient.
+template <int DP>
+__host__ __device__ __forceinline__ void attract(float (&yi)[DP], float (&yj)[DP], float (&g)[DP], float p,
+                                                 float inv_s2, const SgdConst &K)
+{
+    const float u = sqdist<DP>(yi, yj) * inv_s2;
+    if (u > 0.0f) {
+        const float rep = fast_div(1.0f, fmaxf(u * u, 1.0e4f));                  // alfa = 1/PROBA_MIN :1225-1226
+        const float a = fmaxf(K.gamma * cauchy_coeff(u, inv_s2, K) * (-p + (1.0f - p) * rep), -0.49f); // :1228-1229
+#pragma unroll
+        for (int c = 0; c < DP; c++) g[c] = (yj[c] - yi[c]) * a;                  // :1230
+    }
+#pragma unroll
+    for (int c = 0; c < DP; c++) { yi[c] -= g[c]; yj[c] += g[c]; }                // :1237-1238
+}
+
+// Negative node k: embedder.rs:1263-1297.  Only yi moves; g keeps its previous value when the
+// two points coincide (the reference does the same).
+template <int DP>
+__host__ __device__ __forceinline__ void repulse(float (&yi)[DP], const float (&yk)[DP], float (&g)[DP],
+                                                 float inv_s2, const SgdConst &K)
+{
+    const float dk = sqdist<DP>(yi, yk);
+    if (dk > 0.0f) {
+        const float u = dk * inv_s2;
+        const float rep = fast_div(1.0f, fmaxf(u * u, 0.0625f));                  // alfa = 1/16 :1286-1288
+        const float a = fminf(K.gamma * cauchy_coeff(u, inv_s2, K) * rep, 2.0f);
+#pragma unroll
+        for (int c = 0; c < DP; c++) g[c] = (yk[c] - yi[c]) * a;
+    }
+#pragma unroll
+    for (int c = 0; c < DP; c++) yi[c] -= g[c];
+}
+
+// One complete reference sample applied in place on a layout (serial semantics, K3).
+template <int DP>
+__host__ __device__ __forceinline__ void fixed_sample(float *Y, uint32_t i, uint32_t j, float p, float inv_s2,
+                                                      const SgdConst &K, const uint32_t *negs)
+{
+    float yi[DP], yj[DP], g[DP], yk[DP];
+    load_row<DP>(Y, i, yi);
+    load_row<DP>(Y, j, yj);
+#pragma unroll
+    for (int c = 0; c < DP; c++) g[c] = 0.0f;
+    attract<DP>(yi, yj, g, p, inv_s2, K);
+    store_row<DP>(Y, j, yj);                                                      // :1239
+    for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+        load_row<DP>(Y, negs[q], yk);
+        repulse<DP>(yi, yk, g, inv_s2, K);
+    }
+    store_row<DP>(Y, i, yi);                                                      // :1301
+}
+
+// ---- the counter-based sampler ------------------------------------------------------------------
+// Sub-stream layout of counter word 3 for (edge, epoch):
+//   3s, 3s+1, 3s+2          firing s (word x of sub-stream 0 decides the firing count)
+//   0x80000000|s<<8|q<<5|t  redraw attempt t of negative q of firing s (rejection, embedder.rs:1246-1252)
+struct EpochArgs {
+    const float *__restrict__ y_snap;   // layout at the start of the mini-epoch (replicated, n x DP)
+    float *__restrict__ y_next;         // layout after it; only rows [lo,hi) are written here
+    const uint64_t *__restrict__ row_ptr;
+    const uint32_t *__restrict__ col;
+    const float *__restrict__ p;
+    const float *__restrict__ inv_s2;   // 1 / embedded_scale^2 per node
+    const uint64_t *__restrict__ in_ptr; // transposed index of the owned nodes: in_ptr[node-lo] .. in_ptr[node-lo+1]
+    const uint4 *__restrict__ in_rec;   // {src node, edge id, bits(p_e), bits(inv_s2[src])}, entry q at in_rec[q - in_base]
+    uint64_t in_base;
+    const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
+    uint32_t n, lo, hi;
+    uint32_t epoch, k0, k1;
+    float kappa;                        // expected firings of edge e in this mini-epoch = kappa * p_e
+    SgdConst K;
+};
+
+// firing count of an edge: floor(kappa*p + u), u ~ U[0,1) from word x of sub-stream 0.
+// E[count] = kappa*p = nb_sampling_by_edge * E * (p_e/N) / mini_epochs, the reference's expectation
+// (alias draw over all edges with weights p_e, embedder.rs:987,1182; each row sums to 1).
+__host__ __device__ __forceinline__ int firing_count(float p, float kappa, uint32_t word)
+{
+    return (int)fmaf(p, kappa, u01_24(word));
+}
+
+template <bool HUB>
+__host__ __device__ __forceinline__ uint32_t map_negative(const EpochArgs &a, uint32_t w_idx, uint32_t w_acc)
+{
+    uint32_t k = below32(w_idx, a.n);                                             // uniform, embedder.rs:1121
+    if constexpr (HUB) {
+        const uint2 t = a.neg_alias[k];
+        if (!(u01_24(w_acc) < as_float(t.x))) k = t.y;                            // alias method, :919,929
+    }
+    return k;
+}
+
+__host__ __device__ __forceinline__ bool negative_rejected(const EpochArgs &a, uint32_t k, uint32_t node, uint32_t j,
+                                                           uint64_t r0, uint64_t r1)
+{
+    if (k == node || k == j) return true;                                         // :1246-1247
+    for (uint64_t m = r0; m < r1; m++)                                            // nodeparam.rs:83-85
+        if (a.col[m] == k) return true;
+    return false;
+}
+
+// the 5 accepted negatives of firing s of edge e (A = sub-stream 3s, already drawn by the caller)
+template <bool HUB>
+__host__ __device__ __forceinline__ void draw_negatives(const EpochArgs &a, uint32_t e, uint32_t s, const Philox4 &A,
+                                                        uint32_t node, uint32_t j, uint64_t r0, uint64_t r1,
+                                                        uint32_t (&negs)[ANNEMBED_NB_NEG])
+{
+    const Philox4 B = philox4x32_10(e, 0u, a.epoch, 3u * s + 1u, a.k0, a.k1);
+    uint32_t wi[ANNEMBED_NB_NEG] = {A.y, A.z, A.w, B.x, B.y};
+    uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
+    if constexpr (HUB) {
+        const Philox4 C = philox4x32_10(e, 0u, a.epoch, 3u * s + 2u, a.k0, a.k1);
+        wa[0] = B.z; wa[1] = B.w; wa[2] = C.x; wa[3] = C.y; wa[4] = C.z;
+    }
+#pragma unroll
+    for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+        uint32_t k = map_negative<HUB>(a, wi[q], wa[q]);
+        bool rej = negative_rejected(a, k, node, j, r0, r1);
+        for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
+            const Philox4 R = philox4x32_10(e, 0u, a.epoch, 0x80000000u | (s << 8) | ((uint32_t)q << 5) | t, a.k0, a.k1);
+            k = map_negative<HUB>(a, R.x, R.y);
+            rej = negative_rejected(a, k, node, j, r0, r1);
+        }
+        negs[q] = rej ? ANNEMBED_NO_NODE : k;
+    }
+}
+
+// ---- one node, one mini-epoch (owner computes; no atomics on the layout) -------------------------
+// Sequential over the node's own firings (Gauss-Seidel inside the node) against the snapshot of every
+// other node (Jacobi across nodes).  Both ends of a positive edge move in the reference (:1237-1239):
+// the origin's owner applies -g here (phase A), the destination's owner replays the same counter-based
+// draw and applies +g (phase B).  When an edge fires c>1 times in a mini-epoch both owners simulate the
+// pair's c sequential attractions on local copies, which is what the serial reference would do to the pair.
+template <int DP, bool HUB>
+__host__ __device__ __forceinline__ unsigned int epoch_node(const EpochArgs &a, uint32_t node)
+{
+    float y[DP], g[DP];
+    load_row<DP>(a.y_snap, node, y);
+    const float inv_s2 = a.inv_s2[node];
+    const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
+    unsigned int applied = 0;
+    // phase A: out-edges (node is the origin i)
+    for (uint64_t m = r0; m < r1; m++) {
+        const uint32_t e = (uint32_t)m;
+        Philox4 A = philox4x32_10(e, 0u, a.epoch, 0u, a.k0, a.k1);
+        const float pe = a.p[m];
+        const int c = firing_count(pe, a.kappa, A.x);
+        if (c == 0) continue;
+        const uint32_t j = a.col[m];
+        float yj[DP];
+        load_row<DP>(a.y_snap, j, yj);
+        for (int s = 0; s < c; s++) {
+            if (s > 0) A = philox4x32_10(e, 0u, a.epoch, 3u * (uint32_t)s, a.k0, a.k1);
+            uint32_t negs[ANNEMBED_NB_NEG];
+            draw_negatives<HUB>(a, e, (uint32_t)s, A, node, j, r0, r1, negs);
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
+            if constexpr (DP <= 4) {
+                // issue the five gathers before the dependent arithmetic
+                float yk[ANNEMBED_NB_NEG][DP];
+#pragma unroll
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+                    load_row<DP>(a.y_snap, negs[q] == ANNEMBED_NO_NODE ? node : negs[q], yk[q]);
+                attract<DP>(y, yj, g, pe, inv_s2, a.K);
+#pragma unroll
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+                    if (negs[q] != ANNEMBED_NO_NODE) repulse<DP>(y, yk[q], g, inv_s2, a.K);
+            } else {
+                attract<DP>(y, yj, g, pe, inv_s2, a.K);
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+                    if (negs[q] == ANNEMBED_NO_NODE) continue;
+                    float yk[DP];
+                    load_row<DP>(a.y_snap, negs[q], yk);
+                    repulse<DP>(y, yk, g, inv_s2, a.K);
+                }
+            }
+        }
+        applied += (unsigned int)c;
+    }
+    // phase B: in-edges (node is the destination j of src -> node)
+    const uint64_t q0 = a.in_ptr[node - a.lo], q1 = a.in_ptr[node - a.lo + 1];
+    for (uint64_t q = q0; q < q1; q++) {
+        const uint4 rec = a.in_rec[q - a.in_base];
+        const Philox4 A = philox4x32_10(rec.y, 0u, a.epoch, 0u, a.k0, a.k1);
+        const float pe = as_float(rec.z);
+        const int c = firing_count(pe, a.kappa, A.x);
+        if (c == 0) continue;
+        float ys[DP];
+        load_row<DP>(a.y_snap, rec.x, ys);
+        const float inv_s2_src = as_float(rec.w);
+        for (int s = 0; s < c; s++) {
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
+            attract<DP>(ys, y, g, pe, inv_s2_src, a.K);
+        }
+    }
+    store_row<DP>(a.y_next, node, y);
+    return applied;
+}
+
+} // namespace annembed

@@ -1,0 +1,279 @@
+"""Embedder -- host-side mirror of /root/reference/src/embedder.rs `Embedder` for the hot path only.
+
+Same method names, argument meaning and error behaviour as the Rust struct (embedder.rs:84-453), with the pair
+`to_proba_edges` + `entropy_optimize` (embedder.rs:351-356) replaced by calls into the C ABI
+(include/annembed_cuda.h).  What is NOT here (out of scope): the diffusion-map initial layout
+(an explicit `initial_embedding` is required when dmap_init is true), hierarchical `from_hkgraph`, quality estimate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AnnembedCudaError, Params, Stats, ptr
+from .embedparams import EmbedderParams
+from .kgraph import KGraph
+
+
+def _c_params(p: EmbedderParams) -> Params:
+    return Params(asked_dim=p.asked_dim, dmap_init=int(p.dmap_init), beta=p.beta, b=p.b, scale_rho=p.scale_rho,
+                  grad_step=p.grad_step, nb_sampling_by_edge=p.nb_sampling_by_edge, nb_grad_batch=p.nb_grad_batch,
+                  grad_factor=p.grad_factor, hierarchy_layer=p.hierarchy_layer,
+                  hubness_weighting=int(p.hubness_weighting), mini_epochs_per_batch=p.mini_epochs_per_batch,
+                  seed=p.seed, flags=p.flags, reserved=0)
+
+
+class CudaContext:
+    """Thin RAII wrapper of annembed_cuda_ctx; every method maps 1:1 to a C-ABI call and raises on status != 0."""
+
+    def __init__(self, params: EmbedderParams, device: int = 0):
+        self.lib = _lib.load()
+        self.params = params
+        self.h = C.c_void_p()
+        cp = _c_params(params)
+        st = self.lib.annembed_cuda_create(C.byref(self.h), C.byref(cp), device)
+        if st != 0:
+            msg = self.lib.annembed_cuda_last_error(None)
+            self.h = C.c_void_p()
+            raise AnnembedCudaError(st, msg.decode() if msg else "")
+        self.n = 0
+        self.E = 0
+
+    def _ck(self, st: int):
+        if st != 0:
+            msg = self.lib.annembed_cuda_last_error(self.h)
+            raise AnnembedCudaError(st, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.annembed_cuda_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- multi GPU
+    def unique_id(self) -> np.ndarray:
+        out = np.zeros(128, np.uint8)
+        st = self.lib.annembed_cuda_comm_unique_id(ptr(out, C.c_uint8))
+        if st != 0:
+            raise AnnembedCudaError(st, (self.lib.annembed_cuda_last_error(None) or b"").decode())
+        return out
+
+    def comm_init(self, rank: int, nranks: int, unique_id: np.ndarray | None):
+        uid = None if unique_id is None else np.ascontiguousarray(unique_id, np.uint8)
+        self._ck(self.lib.annembed_cuda_comm_init(self.h, rank, nranks, ptr(uid, C.c_uint8)))
+
+    # --- graph / weights
+    def set_graph_csr(self, row_ptr, col, dist):
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
+        col = np.ascontiguousarray(col, np.uint32)
+        dist = np.ascontiguousarray(dist, np.float32)
+        n = len(row_ptr) - 1
+        if n < 0 or len(col) != len(dist):
+            raise ValueError("inconsistent CSR arrays")
+        self._ck(self.lib.annembed_cuda_set_graph_csr(self.h, n, ptr(row_ptr, C.c_uint64), ptr(col, C.c_uint32),
+                                                      ptr(dist, C.c_float)))
+        self.n, self.E = n, len(col)
+
+    def edge_weights(self, want_outputs: bool = True):
+        if not want_outputs:
+            self._ck(self.lib.annembed_cuda_edge_weights(self.h, None, None))
+            return None, None
+        scale = np.empty(self.n, np.float32)
+        p = np.empty(self.E, np.float32)
+        self._ck(self.lib.annembed_cuda_edge_weights(self.h, ptr(scale, C.c_float), ptr(p, C.c_float)))
+        return scale, p
+
+    def edge_weights_umap(self, norm: float):
+        scale = np.empty(self.n, np.float32)
+        w = np.empty(self.E, np.float32)
+        status = np.empty(self.n, np.uint8)
+        self._ck(self.lib.annembed_cuda_edge_weights_umap(self.h, norm, ptr(scale, C.c_float), ptr(w, C.c_float),
+                                                          ptr(status, C.c_uint8)))
+        return scale, w, status
+
+    def set_edge_weights(self, scale, proba):
+        scale = np.ascontiguousarray(scale, np.float32)
+        proba = np.ascontiguousarray(proba, np.float32)
+        assert len(scale) == self.n and len(proba) == self.E
+        self._ck(self.lib.annembed_cuda_set_edge_weights(self.h, ptr(scale, C.c_float), ptr(proba, C.c_float)))
+
+    def get_perplexity(self):
+        out = np.empty(self.n, np.float32)
+        self._ck(self.lib.annembed_cuda_get_perplexity(self.h, ptr(out, C.c_float)))
+        return out
+
+    def set_neg_weights(self, w):
+        if w is not None:
+            w = np.ascontiguousarray(w, np.float32)
+            assert len(w) == self.n
+        self._ck(self.lib.annembed_cuda_set_neg_weights(self.h, ptr(w, C.c_float)))
+
+    def get_hubness_counts(self):
+        out = np.empty(self.n, np.uint32)
+        self._ck(self.lib.annembed_cuda_get_hubness_counts(self.h, ptr(out, C.c_uint32)))
+        return out
+
+    # --- layout
+    def set_embedding(self, y):
+        y = np.ascontiguousarray(y, np.float32)
+        if y.shape != (self.n, self.params.asked_dim):
+            raise ValueError(f"initial embedding must be ({self.n}, {self.params.asked_dim}), got {y.shape}")
+        self._ck(self.lib.annembed_cuda_set_embedding(self.h, ptr(y, C.c_float)))
+
+    def reset_embedding(self):
+        self._ck(self.lib.annembed_cuda_reset_embedding(self.h))
+
+    def get_embedded_scales(self):
+        out = np.empty(self.n, np.float32)
+        self._ck(self.lib.annembed_cuda_get_embedded_scales(self.h, ptr(out, C.c_float)))
+        return out
+
+    def step_fixed(self, edge_idx, neg_idx, grad_step: float):
+        edge_idx = np.ascontiguousarray(edge_idx, np.uint64)
+        neg_idx = np.ascontiguousarray(neg_idx, np.uint32).reshape(-1)
+        assert len(neg_idx) == 5 * len(edge_idx)
+        self._ck(self.lib.annembed_cuda_step_fixed(self.h, len(edge_idx), ptr(edge_idx, C.c_uint64),
+                                                   ptr(neg_idx, C.c_uint32), grad_step))
+
+    def optimize(self, want_ce: bool = True):
+        if want_ce:
+            a, b = C.c_double(), C.c_double()
+            self._ck(self.lib.annembed_cuda_optimize(self.h, C.byref(a), C.byref(b)))
+            return a.value, b.value
+        self._ck(self.lib.annembed_cuda_optimize(self.h, None, None))
+        return None, None
+
+    def optimize_batches(self, first_batch: int, n_batches: int):
+        self._ck(self.lib.annembed_cuda_optimize_batches(self.h, first_batch, n_batches))
+
+    def cross_entropy(self) -> float:
+        v = C.c_double()
+        self._ck(self.lib.annembed_cuda_cross_entropy(self.h, C.byref(v)))
+        return v.value
+
+    def get_embedding(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n, self.params.asked_dim), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.n * self.params.asked_dim
+        self._ck(self.lib.annembed_cuda_get_embedding(self.h, ptr(out, C.c_float)))
+        return out
+
+    def get_stats(self) -> dict:
+        s = Stats()
+        self._ck(self.lib.annembed_cuda_get_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._ck(self.lib.annembed_cuda_reset_stats(self.h))
+
+    def debug_draws(self, epoch: int, want_negs: bool = True):
+        counts = np.empty(self.E, np.uint32)
+        negs = np.empty((self.E, 5), np.uint32) if want_negs else None
+        self._ck(self.lib.annembed_cuda_debug_draws(self.h, epoch, ptr(counts, C.c_uint32), ptr(negs, C.c_uint32)))
+        return counts, negs
+
+
+class EmbedError(RuntimeError):
+    """≙ `Err(1)` of Embedder::embed (embedder.rs:183,366-369)."""
+
+
+class Embedder:
+    """≙ `Embedder<'a, F>` (embedder.rs:84-100) restricted to the one-step path (`Embedder::new`, :107)."""
+
+    def __init__(self, kgraph: KGraph, parameters: EmbedderParams, initial_embedding: np.ndarray | None = None,
+                 device: int = 0, comm: tuple | None = None):
+        self.kgraph = kgraph                     # borrowed, like &'a KGraph<F>
+        self.parameters = parameters             # copied by value in the reference (EmbedderParams: Copy)
+        self.initial_embedding = None if initial_embedding is None else np.ascontiguousarray(initial_embedding, np.float32)
+        self.embedding = None
+        self.hubness_counts = None
+        self.cross_entropy = (None, None)
+        self.device = device
+        self.comm = comm                          # (rank, nranks, unique_id) or None
+        self.stats = {}
+
+    # --- parameter getters, embedder.rs:135-153
+    def get_asked_dimension(self) -> int: return self.parameters.asked_dim
+    def get_scale_rho(self) -> float: return self.parameters.scale_rho
+    def get_b(self) -> float: return self.parameters.b
+    def get_grad_step(self) -> float: return self.parameters.grad_step
+    def get_nb_grad_batch(self) -> int: return self.parameters.nb_grad_batch
+    def get_kgraph(self) -> KGraph: return self.kgraph
+    def get_hubness(self): return self.hubness_counts
+    def get_nb_nodes(self) -> int: return self.kgraph.get_nb_nodes()
+
+    def _get_random_init(self, size: float) -> np.ndarray:
+        """≙ get_random_init (embedder.rs:456-470): uniform in [-size/2, size/2]^d (seeded here)."""
+        rng = np.random.Generator(np.random.PCG64(self.parameters.seed))
+        n, d = self.get_nb_nodes(), self.parameters.asked_dim
+        return rng.uniform(-size / 2, size / 2, size=(n, d)).astype(np.float32)
+
+    def embed(self) -> int:
+        """≙ embed -> one_step_embed (embedder.rs:183,298-371).  Returns 1 (`Ok(1)`); raises EmbedError (`Err(1)`)."""
+        p = self.parameters
+        if self.initial_embedding is None:
+            if p.dmap_init:
+                raise EmbedError("dmap_init=true needs an explicit initial_embedding: the diffusion-map layout "
+                                 "(embedder.rs:308-345) is outside this library's hot path")
+            self.initial_embedding = self._get_random_init(1.0)       # embedder.rs:348
+        ctx = None
+        try:
+            ctx = CudaContext(p, self.device)
+            if self.comm is not None:
+                ctx.comm_init(*self.comm)
+            row_ptr, col, dist = self.kgraph.get_neighbours()
+            ctx.set_graph_csr(row_ptr, col, dist)
+            ctx.edge_weights(want_outputs=False)                       # to_proba_edges, embedder.rs:351
+            if p.hubness_weighting:                                    # embedder.rs:810-837
+                counts = ctx.get_hubness_counts()
+                self.hubness_counts = counts
+                n = float(len(counts))
+                ctx.set_neg_weights(np.clip(counts.astype(np.float32), 1.0, n))
+            ctx.set_embedding(self.initial_embedding)
+            self.cross_entropy = ctx.optimize(want_ce=True)            # entropy_optimize, embedder.rs:356
+            self.embedding = ctx.get_embedding()
+            self.stats = ctx.get_stats()
+        except AnnembedCudaError as e:
+            raise EmbedError(str(e)) from e
+        finally:
+            if ctx is not None:
+                ctx.close()
+        return 1
+
+    # --- results, embedder.rs:378-453
+    def get_embedded(self):
+        return self.embedding
+
+    def get_embedded_reindexed(self) -> np.ndarray:
+        """≙ embedder.rs:384-405: row i of the embedding goes to row DataId(i); DataIds must be 0..n."""
+        if self.embedding is None:
+            raise RuntimeError("get_embedded_reindexed called before embed (the reference panics, embedder.rs:385)")
+        return self._reindex(self.embedding)
+
+    def get_embedded_by_dataid(self, data_id: int) -> np.ndarray:
+        return self.embedding[self.kgraph.get_idx_from_dataid(data_id)]
+
+    def get_embedded_by_nodeid(self, node: int) -> np.ndarray:
+        return self.embedding[node]
+
+    def get_initial_embedding(self):
+        return self.initial_embedding
+
+    def get_initial_embedding_reindexed(self) -> np.ndarray:
+        return self._reindex(self.initial_embedding)
+
+    def _reindex(self, a: np.ndarray) -> np.ndarray:
+        ids = self.kgraph.data_id.astype(np.int64)
+        n = len(ids)
+        if ids.min(initial=0) < 0 or ids.max(initial=-1) >= n or len(np.unique(ids)) != n:
+            raise IndexError("DataIds must fill 0..n to reindex (embedder.rs:397-403 indexes out of bounds otherwise)")
+        out = np.zeros_like(a)
+        out[ids] = a
+        return out

@@ -1,0 +1,161 @@
+/*
+ * annembed_cuda.h -- C ABI of the B200-native (sm_100a) cross-entropy embedding optimizer.
+ *
+ * Drop-in boundary for ONE hot path of jean-pierreBoth/annembed: what sits behind
+ *   Embedder::new(&kgraph, EmbedderParams) / embed() / get_embedded_reindexed()
+ * i.e. to_proba_edges (src/tools/kdumap.rs:26-235) + entropy_optimize (src/embedder.rs:794-904).
+ * The reference is pure Rust with no FFI of its own for this path; these are the entry points a
+ * `cuda` cargo feature would bind with `extern "C"` (INTEGRATION.md shows the Rust side).
+ * Citations below are relative to /root/reference/src.
+ *
+ * Conventions
+ *  - every function returns an int status (ANNEMBED_OK == 0); nothing aborts or throws across the ABI
+ *    (the reference exits the process on an empty neighbourhood, kdumap.rs:75-85; here it is a status);
+ *  - all pointer arguments are HOST pointers owned by the caller and are copied before return;
+ *  - the opaque context owns every device allocation, its stream and (optionally) its NCCL communicator;
+ *  - a context is not thread-safe; distinct contexts are independent; calls block until done;
+ *  - there is no CPU fallback: without a CUDA device annembed_cuda_create fails with ANNEMBED_ERR_CUDA.
+ *  - one context drives one GPU; multi-GPU = one context per process/GPU + annembed_cuda_comm_init.
+ */
+#ifndef ANNEMBED_CUDA_H
+#define ANNEMBED_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANNEMBED_CUDA_ABI_VERSION 1
+
+enum annembed_status {
+    ANNEMBED_OK = 0,
+    ANNEMBED_ERR_INVALID_ARG = 1,   /* null pointer, bad size, col >= n, self edge (embedder.rs:1201 asserts) */
+    ANNEMBED_ERR_CUDA = 2,          /* CUDA runtime error / no device */
+    ANNEMBED_ERR_EMPTY_ROW = 3,     /* node without neighbour: kdumap.rs:75-85 (process::exit(1) there) */
+    ANNEMBED_ERR_UNSORTED_ROW = 4,  /* row distances not ascending: kgraph.rs:508-509 invariant */
+    ANNEMBED_ERR_STATE = 5,         /* call order: graph / weights / embedding not set (embedder.rs:802-808) */
+    ANNEMBED_ERR_UNSUPPORTED = 6,   /* asked_dim > 32, E >= 2^32, n >= 2^32 */
+    ANNEMBED_ERR_COMM = 7,          /* NCCL not loadable / communicator failure */
+    ANNEMBED_ERR_NO_NEGATIVE = 8    /* n too small for 5 accepted negatives (embedder.rs:1241-1252 would spin) */
+};
+
+/* Mirror of EmbedderParams (embedparams.rs:76-103; defaults :107-132) + device-side knobs.
+ * dmap_init / grad_factor / hierarchy_layer are carried for fidelity; the initial layout is an input
+ * (annembed_cuda_set_embedding), so they do not change what this library computes. */
+typedef struct annembed_cuda_params {
+    uint32_t asked_dim;            /* embedparams.rs:78  default 2   (1..32 supported on device) */
+    uint32_t dmap_init;            /* :80  default 1 */
+    double   beta;                 /* :82  default 1.   exponent inside the exponential, kdumap.rs:172-174 */
+    double   b;                    /* :85  default 1.   Cauchy exponent, embedder.rs:1216-1222 */
+    double   scale_rho;            /* :88  default 1. */
+    double   grad_step;            /* :90  default 2. */
+    uint32_t nb_sampling_by_edge;  /* :92  default 10 */
+    uint32_t nb_grad_batch;        /* :94  default 20 */
+    uint32_t grad_factor;          /* :98  default 4 */
+    uint32_t hierarchy_layer;      /* :100 default 0 */
+    uint32_t hubness_weighting;    /* :102 default 0: negatives uniform; 1: alias over set_neg_weights */
+    /* ---- device-side additions (no reference counterpart: its RNG is unseeded, embedder.rs:1182) ---- */
+    uint32_t mini_epochs_per_batch;/* bulk-synchronous sub-steps per reference batch; 0 -> nb_sampling_by_edge */
+    uint64_t seed;                 /* Philox4x32-10 key */
+    uint32_t flags;                /* ANNEMBED_FLAG_* */
+    uint32_t reserved;
+} annembed_cuda_params;
+
+#define ANNEMBED_FLAG_NONE 0u
+
+typedef struct annembed_cuda_stats {
+    double   edge_weights_ms;      /* K0+K1 device time, last call */
+    double   build_ms;             /* device context build (scales, transposed index), last call */
+    double   optimize_ms;          /* device time of the last optimize loop (events on the library stream) */
+    double   epoch_kernel_ms;      /* sum of epoch-kernel (K4) durations inside optimize_ms */
+    double   exchange_ms;          /* all-gather time inside optimize_ms (0 on one GPU) */
+    double   cross_entropy_ms;     /* K5 time, last call */
+    uint64_t epoch_launches;       /* K4 launches in the last optimize */
+    uint64_t kernel_launches;      /* all kernels of this library launched since create / reset_stats */
+    uint64_t positive_samples;     /* positive-edge samples applied by this rank in the last optimize */
+    uint64_t edge_updates;         /* = 6 * positive_samples (1 attraction + 5 repulsions, embedder.rs:1241) */
+    uint64_t h2d_bytes;            /* since create / reset_stats */
+    uint64_t d2h_bytes;
+    double   model_bytes;          /* positive_samples * (12 + 36 d): SURVEY.md 8(d) algorithmic bytes */
+} annembed_cuda_stats;
+
+typedef struct annembed_cuda_ctx annembed_cuda_ctx;
+
+/* Fill `p` with EmbedderParams::default() (embedparams.rs:107-132) and the device-side defaults. */
+int annembed_cuda_default_params(annembed_cuda_params *p);
+
+/* ≙ Embedder::new (embedder.rs:107): copies params; `device` is the CUDA ordinal. */
+int annembed_cuda_create(annembed_cuda_ctx **ctx, const annembed_cuda_params *params, int device);
+int annembed_cuda_destroy(annembed_cuda_ctx *ctx);
+/* NUL-terminated message of the last failing call on ctx (ctx == NULL: last create failure). */
+const char *annembed_cuda_last_error(const annembed_cuda_ctx *ctx);
+
+/* ---- multi-GPU (one context per rank). No reference counterpart (single process, rayon). ----
+ * Node range [rank*ceil(n/nranks), ...) is owned by `rank`; the n x d layout is replicated and
+ * all-gathered once per mini-epoch.  unique_id is the 128-byte ncclUniqueId made by rank 0. */
+int annembed_cuda_comm_unique_id(uint8_t unique_id[128]);
+int annembed_cuda_comm_init(annembed_cuda_ctx *ctx, int rank, int nranks, const uint8_t unique_id[128]);
+
+/* ≙ the KGraph hand-off, kgraph.rs:108-120 + get_neighbours :157.  Rows sorted ascending by distance
+ * (kgraph.rs:508-509), no self edges, every row non-empty.  row_ptr has n+1 entries. */
+int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, const uint64_t *row_ptr,
+                                const uint32_t *col, const float *dist);
+
+/* K1 ≙ to_proba_edges (kdumap.rs:26-116) / get_scale_from_proba_normalisation (:132-235).
+ * Outputs are optional (NULL to keep results on the device only). */
+int annembed_cuda_edge_weights(annembed_cuda_ctx *ctx, float *scale_out /*[n]*/, float *proba_out /*[E]*/);
+/* K1b ≙ get_scale_from_umap (embedder.rs:760-783) + dichotomy_solver (tools/dichotomy.rs:4-65); dead code in
+ * the reference.  Per row: bisection for beta' with sum_m exp(-(d_m-d_0) beta') = norm.  Outputs 1/beta' and
+ * the un-normalised weights; does not replace the weights used by optimize. status_out[i]: 0 ok, 1 not converged. */
+int annembed_cuda_edge_weights_umap(annembed_cuda_ctx *ctx, float norm, float *scale_out /*[n]*/,
+                                    float *weight_out /*[E]*/, uint8_t *status_out /*[n], nullable*/);
+/* Inject weights computed elsewhere (isolates the optimizer in tests). */
+int annembed_cuda_set_edge_weights(annembed_cuda_ctx *ctx, const float *scale /*[n]*/, const float *proba /*[E]*/);
+/* ≙ NodeParam::get_perplexity (nodeparam.rs:88-91) for every node. */
+int annembed_cuda_get_perplexity(annembed_cuda_ctx *ctx, float *out /*[n]*/);
+
+/* ≙ NodeSampler::new (embedder.rs:909-931): weights already clamp(in_degree,1,n) (embedder.rs:826-833).
+ * NULL -> uniform negatives (embedder.rs:1121). */
+int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float *w /*[n], nullable*/);
+/* In-degree counts of the loaded graph ≙ Hubness::get_counts (fromhnsw/hubness.rs:39-79). */
+int annembed_cuda_get_hubness_counts(annembed_cuda_ctx *ctx, uint32_t *counts /*[n]*/);
+
+/* The initial layout, n x asked_dim row-major (≙ initial_embedding argument of entropy_optimize,
+ * embedder.rs:794-798).  A device-resident copy is kept for annembed_cuda_reset_embedding. */
+int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *y);
+int annembed_cuda_reset_embedding(annembed_cuda_ctx *ctx);
+/* K2 ≙ estimate_embedded_scales_from_initial_scales (embedder.rs:1356-1373). */
+int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *out /*[n]*/);
+
+/* K3 ≙ serial gradient_iteration (embedder.rs:1304-1308) over an explicit sample list, applied strictly in
+ * list order: sample s = (flat edge index edge_idx[s], 5 accepted negatives neg_idx[5s..5s+5)). */
+int annembed_cuda_step_fixed(annembed_cuda_ctx *ctx, uint64_t n_samples, const uint64_t *edge_idx,
+                             const uint32_t *neg_idx, double grad_step);
+
+/* K4(+K5) ≙ entropy_optimize (embedder.rs:794-904): CE, nb_grad_batch batches with the reference's
+ * schedule grad_step*(1-iter/nb) (:873-876), CE.  ce_* nullable (skips that K5 pass). */
+int annembed_cuda_optimize(annembed_cuda_ctx *ctx, double *ce_initial, double *ce_final);
+/* Bounded slice of the schedule: batches iter = first_batch .. first_batch+n_batches-1 of 1..=nb_grad_batch. */
+int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t first_batch, uint32_t n_batches);
+
+/* K5 ≙ ce_compute_threaded (embedder.rs:1127-1163) with cauchy_edge_weight (:1322-1345). */
+int annembed_cuda_cross_entropy(annembed_cuda_ctx *ctx, double *out);
+
+/* ≙ the copy-out at embedder.rs:888-899: n x asked_dim, node-index order.  The caller re-indexes to
+ * DataId order exactly as get_embedded_reindexed does (embedder.rs:384-405). */
+int annembed_cuda_get_embedding(annembed_cuda_ctx *ctx, float *y_out);
+
+int annembed_cuda_get_stats(annembed_cuda_ctx *ctx, annembed_cuda_stats *stats);
+int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx);
+
+/* Test hook: what the counter-based sampler draws for `epoch` (global mini-epoch index) without applying it.
+ * counts_out[e] = number of firings of edge e; neg_out[5e..5e+5) = accepted negatives of its first firing
+ * (0xFFFFFFFF where the edge does not fire).  Same stream the epoch kernel consumes. */
+int annembed_cuda_debug_draws(annembed_cuda_ctx *ctx, uint32_t epoch, uint32_t *counts_out /*[E]*/,
+                              uint32_t *neg_out /*[5E], nullable*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANNEMBED_CUDA_H */

@@ -1,0 +1,46 @@
+"""Quality statistics of an embedding -- restatement of embedder.rs:478-753 (A.8 of SURVEY.md).
+
+TEST INFRASTRUCTURE ONLY.  Differences from the reference, stated in SURVEY.md 8(c):
+the radius R_i (distance to the nbng-th nearest embedded neighbour) is EXACT here (scipy cKDTree)
+whereas the reference gets it from an HNSW built on the embedded points (embedder.rs:527-554,
+hnsw_rs not vendored); quantiles are exact instead of CKMS(0.01).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle
+
+
+def quality_stats(row_ptr, col, y, nbng):
+    from scipy.spatial import cKDTree
+
+    row_ptr = np.asarray(row_ptr, np.uint64)
+    y = np.ascontiguousarray(y, np.float32)
+    n = len(row_ptr) - 1
+    # embedder.rs:478-522
+    t = oracle.transformed_kgraph(row_ptr, col, y).astype(np.float64)
+    # embedder.rs:527-554 + kgraph.rs:167-183: per node, length of the longest of its nbng embedded kNN edges
+    tree = cKDTree(y.astype(np.float64))
+    dd, _ = tree.query(y.astype(np.float64), k=nbng + 1, workers=-1)
+    radius = dd[:, nbng]
+    deg = np.diff(row_ptr.astype(np.int64))
+    rad_e = np.repeat(radius, deg)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = t / rad_e
+    match_e = (t <= rad_e).astype(np.int64)
+    nodes_match = np.add.reduceat(match_e, row_ptr[:-1].astype(np.int64))
+    nb_without_match = int((nodes_match == 0).sum())           # :676-678
+    mean_nbmatch = float(nodes_match.sum() / max(1, n - nb_without_match))  # :679-680
+    qs = (0.05, 0.25, 0.5, 0.75, 0.85, 0.95)
+    finite = np.isfinite(ratio)
+    return {
+        "nb_without_match": nb_without_match,
+        "mean_nbmatch": mean_nbmatch,
+        "knn_preservation": float(nodes_match.sum() / deg.sum()),  # SURVEY A.8 proposed definition
+        "radius_quantiles": [float(np.quantile(radius, q)) for q in qs],
+        "ratio_quantiles": [float(np.quantile(ratio[finite], q)) for q in qs],
+        "median_ratio": float(np.quantile(ratio[finite], 0.5)),
+        "mean_ratio": float(ratio[finite].mean()),                 # :721-726
+        "first_dist": t[row_ptr[:-1].astype(np.int64)],           # -> first_dist.csv :729-735
+    }

@@ -1,0 +1,154 @@
+// hostsim.cu -- TEST TOOLING ONLY.  Compiles the product's __host__ __device__ mini-epoch body
+// (annembed_b200/csrc/sgd_core.cuh) for the HOST so the bulk-synchronous owner-computes semantics of the
+// epoch kernel can be replayed on a CPU-only box (design studies, draw-for-draw checks against the GPU).
+// It is never loaded by the product package and is not a fallback: nothing in annembed_b200/ references it.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <numeric>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../../annembed_b200/csrc/sgd_core.cuh"
+
+using namespace annembed;
+
+extern "C" void hostsim_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+struct HostCtx {
+    std::vector<uint64_t> in_ptr;
+    std::vector<uint4> in_rec;
+    std::vector<float> inv_s2;
+};
+
+static void build(HostCtx &h, uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *p, const float *emb_scale)
+{
+    const uint64_t E = row_ptr[n];
+    h.inv_s2.resize(n);
+    for (uint64_t i = 0; i < n; i++) h.inv_s2[i] = 1.0f / (emb_scale[i] * emb_scale[i]);
+    h.in_ptr.assign(n + 1, 0);
+    for (uint64_t e = 0; e < E; e++) h.in_ptr[col[e] + 1]++;
+    for (uint64_t i = 0; i < n; i++) h.in_ptr[i + 1] += h.in_ptr[i];
+    h.in_rec.resize(E);
+    std::vector<uint64_t> fill(h.in_ptr.begin(), h.in_ptr.end() - 1);
+    for (uint64_t i = 0; i < n; i++)
+        for (uint64_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) {   // ascending edge id inside each destination
+            uint4 r; r.x = (uint32_t)i; r.y = (uint32_t)e; r.z = as_uint(p[e]); r.w = as_uint(h.inv_s2[i]);
+            h.in_rec[fill[col[e]]++] = r;
+        }
+}
+
+template <int DP, bool HUB>
+static uint64_t run_epoch(const EpochArgs &a)
+{
+    uint64_t tot = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : tot)
+    for (int64_t i = (int64_t)a.lo; i < (int64_t)a.hi; i++) tot += epoch_node<DP, HUB>(a, (uint32_t)i);
+    return tot;
+}
+
+template <bool HUB>
+static uint64_t run_epoch_dp(int DP, const EpochArgs &a)
+{
+    switch (DP) {
+    case 2: return run_epoch<2, HUB>(a);
+    case 4: return run_epoch<4, HUB>(a);
+    case 8: return run_epoch<8, HUB>(a);
+    case 16: return run_epoch<16, HUB>(a);
+    default: return run_epoch<32, HUB>(a);
+    }
+}
+
+// y: n x d in/out.  neg_alias: nullable n x {prob bits, alias}.  Returns positive samples applied.
+extern "C" int64_t hostsim_optimize(uint64_t n, uint32_t d, const uint64_t *row_ptr, const uint32_t *col, const float *p,
+                                    const float *emb_scale, float *y, double b, double grad_step0, uint32_t nbs,
+                                    uint32_t nb_batch, uint32_t M, uint64_t seed, const uint32_t *neg_alias,
+                                    uint32_t first_batch, uint32_t n_batches)
+{
+    const int DP = d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;
+    HostCtx h;
+    build(h, n, row_ptr, col, p, emb_scale);
+    std::vector<float> Y[2];
+    Y[0].assign(n * DP, 0.0f); Y[1].assign(n * DP, 0.0f);
+    for (uint64_t i = 0; i < n; i++) for (uint32_t c = 0; c < d; c++) Y[0][i * DP + c] = y[i * d + c];
+    int cur = 0;
+    const uint64_t E = row_ptr[n];
+    int64_t total = 0;
+    for (uint32_t iter = first_batch; iter < first_batch + n_batches && iter <= nb_batch; iter++) {
+        const double gs = grad_step0 * (1.0 - (double)iter / (double)nb_batch);
+        for (uint32_t m = 0; m < M; m++) {
+            EpochArgs a;
+            a.y_snap = Y[cur].data(); a.y_next = Y[cur ^ 1].data();
+            a.row_ptr = row_ptr; a.col = col; a.p = p; a.inv_s2 = h.inv_s2.data();
+            a.in_ptr = h.in_ptr.data(); a.in_rec = h.in_rec.data(); a.in_base = 0;
+            a.neg_alias = (const uint2 *)neg_alias;
+            a.n = (uint32_t)n; a.lo = 0; a.hi = (uint32_t)n;
+            a.epoch = (iter - 1) * M + m; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+            a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
+            a.K.gamma = (float)gs; a.K.b = (float)b; a.K.two_b = (float)(2.0 * b); a.K.b_is_one = b == 1.0;
+            total += (int64_t)(neg_alias ? run_epoch_dp<true>(DP, a) : run_epoch_dp<false>(DP, a));
+            cur ^= 1;
+        }
+    }
+    for (uint64_t i = 0; i < n; i++) for (uint32_t c = 0; c < d; c++) y[i * d + c] = Y[cur][i * DP + c];
+    return total;
+}
+
+// the draws of one mini-epoch (same contract as annembed_cuda_debug_draws)
+extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *p, uint32_t nbs,
+                              uint32_t M, uint64_t seed, uint32_t epoch, const uint32_t *neg_alias, uint32_t *counts,
+                              uint32_t *negs_out)
+{
+    const uint64_t E = row_ptr[n];
+    EpochArgs a;
+    memset(&a, 0, sizeof a);
+    a.row_ptr = row_ptr; a.col = col; a.p = p; a.neg_alias = (const uint2 *)neg_alias;
+    a.n = (uint32_t)n; a.epoch = epoch; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
+    for (uint64_t node = 0; node < n; node++) {
+        const uint64_t r0 = row_ptr[node], r1 = row_ptr[node + 1];
+        for (uint64_t m = r0; m < r1; m++) {
+            const Philox4 A = philox4x32_10((uint32_t)m, 0u, epoch, 0u, a.k0, a.k1);
+            const int c = firing_count(p[m], a.kappa, A.x);
+            counts[m] = (uint32_t)c;
+            if (negs_out) {
+                uint32_t negs[5] = {ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE};
+                if (c > 0) {
+                    if (neg_alias) draw_negatives<true>(a, (uint32_t)m, 0u, A, (uint32_t)node, col[m], r0, r1, negs);
+                    else draw_negatives<false>(a, (uint32_t)m, 0u, A, (uint32_t)node, col[m], r0, r1, negs);
+                }
+                for (int q = 0; q < 5; q++) negs_out[5 * m + q] = negs[q];
+            }
+        }
+    }
+}
+
+// one fixed-list step with the product's fp32 arithmetic (host build of K3's body)
+extern "C" void hostsim_step_fixed(uint64_t n, uint32_t d, const uint64_t *row_ptr, const uint32_t *col, const float *p,
+                                   const float *emb_scale, float *y, double b, double grad_step, uint64_t n_samples,
+                                   const uint64_t *edge_idx, const uint32_t *negs)
+{
+    const int DP = d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;
+    std::vector<float> Y(n * DP, 0.0f);
+    for (uint64_t i = 0; i < n; i++) for (uint32_t c = 0; c < d; c++) Y[i * DP + c] = y[i * d + c];
+    SgdConst K; K.gamma = (float)grad_step; K.b = (float)b; K.two_b = (float)(2.0 * b); K.b_is_one = b == 1.0;
+    for (uint64_t s = 0; s < n_samples; s++) {
+        const uint64_t e = edge_idx[s];
+        uint64_t lo = 0, hi = n;
+        while (hi - lo > 1) { uint64_t mid = (lo + hi) / 2; if (row_ptr[mid] <= e) lo = mid; else hi = mid; }
+        const float inv_s2 = 1.0f / (emb_scale[lo] * emb_scale[lo]);
+        switch (DP) {
+        case 2: fixed_sample<2>(Y.data(), (uint32_t)lo, col[e], p[e], inv_s2, K, negs + 5 * s); break;
+        case 4: fixed_sample<4>(Y.data(), (uint32_t)lo, col[e], p[e], inv_s2, K, negs + 5 * s); break;
+        case 8: fixed_sample<8>(Y.data(), (uint32_t)lo, col[e], p[e], inv_s2, K, negs + 5 * s); break;
+        case 16: fixed_sample<16>(Y.data(), (uint32_t)lo, col[e], p[e], inv_s2, K, negs + 5 * s); break;
+        default: fixed_sample<32>(Y.data(), (uint32_t)lo, col[e], p[e], inv_s2, K, negs + 5 * s); break;
+        }
+    }
+    for (uint64_t i = 0; i < n; i++) for (uint32_t c = 0; c < d; c++) y[i * d + c] = Y[i * DP + c];
+}
