@@ -484,7 +484,6 @@ extern "C" int annembed_cuda_create(annembed_cuda_ctx **out, const annembed_cuda
     if (device < 0 || device >= ndev) { g_create_error = "bad device ordinal"; return ANNEMBED_ERR_INVALID_ARG; }
     annembed_cuda_ctx *ctx = new annembed_cuda_ctx();
     ctx->prm = *params;
-    if (ctx->prm.mini_epochs_per_batch == 0) ctx->prm.mini_epochs_per_batch = ctx->prm.nb_sampling_by_edge;
     ctx->device = device;
     ctx->DP = pad_dim(params->asked_dim);
     auto fail = [&](const char *what, cudaError_t ce) {
@@ -835,6 +834,16 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
     return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
 }
 
+// Mini-epochs per reference batch.  Default: about 3 own firings per node per mini-epoch
+// (nb_sampling_by_edge * mean degree / 3), where the bulk-synchronous layout statistics meet the serial
+// reference's within 1 % (tests/studies/semantics_study.py).
+static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
+{
+    if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;
+    const double per_node = (double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)std::max<uint64_t>(ctx->n, 1));
+    return (uint32_t)std::max<double>((double)ctx->prm.nb_sampling_by_edge, std::ceil(per_node / 3.0));
+}
+
 static SgdConst make_const(const annembed_cuda_ctx *ctx, double grad_step)
 {
     SgdConst K;
@@ -891,7 +900,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.epoch = epoch;
     a.k0 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu); a.k1 = (uint32_t)(ctx->prm.seed >> 32);
     // expected firings of edge e per mini-epoch: nb_sampling_by_edge * E * (p_e / n) / M   (embedder.rs:858,987)
-    a.kappa = (float)((double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)ctx->n) / (double)ctx->prm.mini_epochs_per_batch);
+    a.kappa = (float)((double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)ctx->n) / (double)eff_mini_epochs(ctx));
     a.K = make_const(ctx, grad_step);
     return a;
 }
@@ -928,7 +937,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     bool hub;
     if ((rc = use_hubness(ctx, &hub))) return rc;
     if ((rc = ensure_build(ctx))) return rc;
-    const uint32_t nb = ctx->prm.nb_grad_batch, M = ctx->prm.mini_epochs_per_batch;
+    const uint32_t nb = ctx->prm.nb_grad_batch, M = eff_mini_epochs(ctx);
     const uint32_t last = std::min<uint64_t>((uint64_t)first_batch + n_batches, (uint64_t)nb + 1);   // exclusive
     const size_t n_launch = first_batch < last ? (size_t)(last - first_batch) * M : 0;
     while (ctx->ev.size() < 2 * n_launch + 2 * n_launch * (ctx->nranks > 1)) {
@@ -1042,6 +1051,7 @@ extern "C" int annembed_cuda_get_stats(annembed_cuda_ctx *ctx, annembed_cuda_sta
 {
     if (!ctx || !stats) return ANNEMBED_ERR_INVALID_ARG;
     *stats = ctx->st;
+    stats->mini_epochs_per_batch = ctx->have_graph ? eff_mini_epochs(ctx) : ctx->prm.mini_epochs_per_batch;
     return ANNEMBED_OK;
 }
 extern "C" int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx)

@@ -1,0 +1,40 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed only carries the 128-byte NCCL id.
+
+The data path has ONE exchange step, inside the C library: an in-place ncclAllGather of the rows each rank owns
+after every mini-epoch (csrc/annembed_cuda.cu).  Nodes are partitioned in contiguous ranges of ceil(n/R).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, nranks: int) -> tuple[int, int]:
+    """Owned node range of `rank` -- must match set_shard() in csrc/annembed_cuda.cu."""
+    n_pad = (n + nranks - 1) // nranks
+    return min(n, rank * n_pad), min(n, (rank + 1) * n_pad)
+
+
+def env_rank_world() -> tuple[int, int, int]:
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+
+def broadcast_unique_id(make_id, rank: int, nranks: int) -> np.ndarray | None:
+    """Rank 0 calls make_id() (-> 128 uint8) and every rank receives it through torch.distributed
+    (any backend: gloo on CPU, nccl on GPUs).  Returns None when nranks == 1."""
+    if nranks == 1:
+        return None
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed must be initialised before broadcast_unique_id")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid = np.ascontiguousarray(make_id(), np.uint8)
+        assert uid.shape == (128,)
+        t.copy_(torch.from_numpy(uid))
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy().copy()

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- edge updates/s of the cross-entropy embedding optimizer on the 11M x 28 Higgs-shape graph
+(BASELINE.json configs[2]: kNN=6, embed dim 2, 40 batches x 10 samples/edge, scale_rho 0.75, grad_step 1;
+parameters of /root/reference/examples/higgs.rs:204-211,234).
+
+A step = one full pass of the hot path: edge weights (K1) + context build + all gradient batches (K4) +
+initial/final cross entropy (K5), i.e. what `Embedder::embed()` spends in to_proba_edges + entropy_optimize.
+`value`  : graph and initial layout already resident in HBM (reset_embedding -> edge_weights -> optimize).
+`e2e`    : the public host API (annembed_b200.Embedder.embed(): create, H2D of graph + layout from pinned host
+           memory, K1, K4, K5, D2H of the layout, destroy) -- the headline against the CPU arm.
+`--impl reference`: the CPU restatement of the reference (oracle/, all host threads) on a bounded sample of the
+same workload (the Rust reference itself cannot be built in this image: no cargo/rustc).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "edge_updates_per_s"
+UNIT = "edge updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=11_000_000)
+    ap.add_argument("--knn", type=int, default=6)
+    ap.add_argument("--dim", type=int, default=2)
+    ap.add_argument("--batches", type=int, default=40)
+    ap.add_argument("--mini-epochs", type=int, default=0)
+    ap.add_argument("--hubness", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per bounded oracle sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"synthetic {a.nodes}x28 Higgs-shape mixture, cluster-blocked exact kNN k={a.knn}, shuffled node ids, "
+            f"0.5% duplicate rows; embed dim {a.dim}; {a.batches} batches x 10 samples/edge; scale_rho 0.75, grad_step 1")
+
+
+def make_inputs(a, device):
+    import workloads
+    t = time.time()
+    row_ptr, col, dist = workloads.blocked_knn_graph(a.nodes, 28, a.knn, seed=0, device=device)
+    y0 = workloads.random_init(a.nodes, a.dim, seed=0)
+    # keep the host copies in pinned memory (the e2e arm copies from them every step)
+    def pin(arr):
+        t_ = torch.from_numpy(arr)
+        if torch.cuda.is_available():
+            t_ = t_.pin_memory()
+        return t_.numpy(), t_
+    keep = []
+    out = []
+    for arr in (row_ptr.view(np.int64), col.view(np.int32), dist, y0):
+        v, t_ = pin(np.ascontiguousarray(arr))
+        keep.append(t_)
+        out.append(v)
+    row_ptr, col, dist, y0 = out[0].view(np.uint64), out[1].view(np.uint32), out[2], out[3]
+    return row_ptr, col, dist, y0, keep, time.time() - t
+
+
+def params_for(a):
+    import annembed_b200 as A
+    return A.EmbedderParams(asked_dim=a.dim, dmap_init=False, beta=1.0, b=1.0, scale_rho=0.75, grad_step=1.0,
+                            nb_sampling_by_edge=10, nb_grad_batch=a.batches, hubness_weighting=bool(a.hubness),
+                            mini_epochs_per_batch=a.mini_epochs, seed=0xB200)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_median": float(np.median(pw)) if pw else None, "reasons": reasons, "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            v = json.load(f)
+        return float(v["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per K4 launch from the committed ncu --set full capture, if any (profiles/k4_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k4_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def cpu_arm(a, row_ptr, col, dist, y0, seconds, label):
+    """The reference's CPU path restated (oracle/), all host threads, bounded sample of one batch."""
+    from oracle import oracle
+    t0 = time.time()
+    scale, p = oracle.edge_weights(row_ptr, col, dist, 0.75, 1.0)
+    es = oracle.embedded_scales(scale)
+    t_w = time.time() - t0
+    cores = oracle.num_threads()
+    E = len(col)
+    # calibrate on a tiny slice, then size the sample for ~`seconds` of work (first batch: full gradient step)
+    _, done, secs = oracle.optimize(row_ptr, col, p, es, y0[:, :a.dim], 1.0, 1.0, 10, a.batches, seed=1, first_batch=1,
+                                    n_batches=1, sample_fraction=max(2e-4, 2e5 / (10.0 * E)), timing=True)
+    rate = done / max(secs, 1e-6)
+    frac = min(1.0, rate * seconds / (10.0 * E))
+    _, done, secs = oracle.optimize(row_ptr, col, p, es, y0[:, :a.dim], 1.0, 1.0, 10, a.batches, seed=2, first_batch=1,
+                                    n_batches=1, sample_fraction=frac, timing=True)
+    return {"value": 6.0 * done / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{label}: {done} positive samples = {frac:.4f} of one batch (of {a.batches}) of the same graph, "
+                      f"sampling loop only ({secs:.1f} s); K1 weights + scales took {t_w:.1f} s on the host and are not included",
+            "positive_samples": int(done), "seconds": secs}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    row_ptr, col, dist, y0, keep, t_in = make_inputs(a, dev)
+    for _ in range(max(0, a.warmup)):
+        cpu_arm(a, row_ptr, col, dist, y0, min(2.0, a.cpu_seconds), "warm-up")
+    vals = []
+    t0 = time.time()
+    for s in range(a.steps):
+        vals.append(cpu_arm(a, row_ptr, col, dist, y0, a.cpu_seconds, f"step {s}"))
+    tot_s = sum(v["seconds"] for v in vals)
+    tot_upd = sum(6.0 * v["positive_samples"] for v in vals)
+    value = tot_upd / tot_s
+    cb = dict(vals[-1]); cb["value"] = value
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * tot_s / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 coordinates, f64 coefficients", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "CPU restatement of the reference (oracle/annembed_oracle.c, OpenMP "
+                   "Hogwild); the Rust reference cannot be built here (no cargo/rustc). Each step is a bounded sample."},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    import annembed_b200 as A
+    from annembed_b200.dist import broadcast_unique_id, env_rank_world
+
+    rank, world, local = env_rank_world()
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    row_ptr, col, distances, y0, keep, t_in = make_inputs(a, f"cuda:{local}")
+    params = params_for(a)
+    ctx = A.CudaContext(params, device=local)
+    uid = broadcast_unique_id(ctx.unique_id, rank, world)
+    ctx.comm_init(rank, world, uid)
+    ctx.set_graph_csr(row_ptr, col, distances)
+    if a.hubness:
+        ctx.edge_weights(want_outputs=False)
+        cnt = ctx.get_hubness_counts()
+        ctx.set_neg_weights(np.clip(cnt.astype(np.float32), 1.0, float(len(cnt))))
+    ctx.set_embedding(y0)
+
+    def step():
+        ctx.reset_embedding()
+        ctx.edge_weights(want_outputs=False)        # K0/K1
+        return ctx.optimize(want_ce=True)            # build + K5 + K4 x batches + K5
+
+    for _ in range(a.warmup):
+        step()
+    ctx.reset_stats()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    agg = {"positive_samples": 0, "epoch_kernel_ms": 0.0, "epoch_launches": 0, "optimize_ms": 0.0, "exchange_ms": 0.0,
+           "edge_weights_ms": 0.0, "build_ms": 0.0, "cross_entropy_ms": 0.0, "model_bytes": 0.0}
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ce = step()
+        st = ctx.get_stats()
+        for k in agg:
+            agg[k] += st[k]
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    st = ctx.get_stats()
+    launches = st["kernel_launches"]
+    mini = st["mini_epochs_per_batch"]
+
+    # ---- end to end through the public host API (pinned host buffers -> embed() -> host result)
+    e2e = None
+    if not a.no_e2e:
+        g = A.KGraph(row_ptr, col, distances, max_nbng=a.knn)
+        comm = (rank, world, None)
+        e2e_t, e2e_samples, h2d, d2h = 0.0, 0, 0, 0
+        for it in range(1 + a.steps):                 # first one is a warm-up
+            uid = broadcast_unique_id(ctx.unique_id, rank, world)
+            emb = A.Embedder(g, params, initial_embedding=y0, device=local, comm=(rank, world, uid))
+            barrier()
+            t1 = time.perf_counter()
+            emb.embed()
+            out = emb.get_embedded()
+            barrier()
+            if it > 0:
+                e2e_t += time.perf_counter() - t1
+                e2e_samples += emb.stats["positive_samples"]
+                h2d, d2h = emb.stats["h2d_bytes"], emb.stats["d2h_bytes"]
+        e2e = (e2e_t, e2e_samples, h2d, d2h)
+
+    # ---- reduce over ranks: time = max, work = sum
+    def allreduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    R = dist.ReduceOp if world > 1 else None
+    elapsed_max = allreduce(elapsed, R.MAX if R else None)
+    samples = allreduce(float(agg["positive_samples"]), R.SUM if R else None)
+    launches_all = allreduce(float(launches), R.SUM if R else None)
+    k4_ms_max = allreduce(agg["epoch_kernel_ms"], R.MAX if R else None)
+    if e2e is not None:
+        e2e_tmax = allreduce(e2e[0], R.MAX if R else None)
+        e2e_s = allreduce(float(e2e[1]), R.SUM if R else None)
+
+    if rank == 0:
+        value = 6.0 * samples / elapsed_max
+        peak, peak_src = hbm_peak()
+        # roofline of the dominant kernel (K4): algorithmic bytes per launch / average launch duration (CUDA events
+        # on the library's stream around every launch), this rank's shard
+        per_launch_bytes = agg["model_bytes"] / max(1, agg["epoch_launches"])
+        per_launch_s = 1e-3 * agg["epoch_kernel_ms"] / max(1, agg["epoch_launches"])
+        achieved = per_launch_bytes / per_launch_s / 1e9
+        traffic = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * elapsed_max / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "mini_epochs_per_batch": int(mini),
+                       "l2": "inputs larger than L2 (graph + transposed index > 2 GB per pass); no flush needed",
+                       "parallelism": f"node-sharded x{world}, replicated layout, all-gather per mini-epoch" if world > 1 else "single GPU",
+                       "positive_samples_per_step": samples / a.steps, "input_build_s": t_in,
+                       "cross_entropy_last_step": list(ce)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "peak_source": peak_src, "kernel": "k_epoch (K4)",
+                         "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": 1e3 * per_launch_s,
+                         "model": "positive samples x (12 + 36 d) bytes (SURVEY.md 8d)"},
+            "breakdown_ms_per_step": {k: agg[k] / a.steps for k in ("edge_weights_ms", "build_ms", "optimize_ms", "epoch_kernel_ms",
+                                                                      "exchange_ms", "cross_entropy_ms")},
+            "gpu_launches": int(launches_all),
+            "clocks": clk,
+        }
+        if e2e is not None:
+            line["e2e"] = {"value": 6.0 * e2e_s / e2e_tmax, "unit": UNIT, "h2d_bytes_per_step": int(e2e[2]),
+                           "d2h_bytes_per_step": int(e2e[3]), "ms_per_step": 1e3 * e2e_tmax / a.steps,
+                           "api": "annembed_b200.Embedder(kgraph, params, initial_embedding).embed() + get_embedded()"}
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_arm(a, row_ptr, col, distances, y0, a.cpu_seconds, "rank 0")
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

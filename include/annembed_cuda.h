@@ -56,7 +56,8 @@ typedef struct annembed_cuda_params {
     uint32_t hierarchy_layer;      /* :100 default 0 */
     uint32_t hubness_weighting;    /* :102 default 0: negatives uniform; 1: alias over set_neg_weights */
     /* ---- device-side additions (no reference counterpart: its RNG is unseeded, embedder.rs:1182) ---- */
-    uint32_t mini_epochs_per_batch;/* bulk-synchronous sub-steps per reference batch; 0 -> nb_sampling_by_edge */
+    uint32_t mini_epochs_per_batch;/* bulk-synchronous sub-steps per reference batch;
+                                      0 -> max(nb_sampling_by_edge, ceil(nb_sampling_by_edge * E/n / 3)) */
     uint64_t seed;                 /* Philox4x32-10 key */
     uint32_t flags;                /* ANNEMBED_FLAG_* */
     uint32_t reserved;
@@ -78,6 +79,7 @@ typedef struct annembed_cuda_stats {
     uint64_t h2d_bytes;            /* since create / reset_stats */
     uint64_t d2h_bytes;
     double   model_bytes;          /* positive_samples * (12 + 36 d): SURVEY.md 8(d) algorithmic bytes */
+    uint64_t mini_epochs_per_batch;/* the value in effect (resolved default) */
 } annembed_cuda_stats;
 
 typedef struct annembed_cuda_ctx annembed_cuda_ctx;

@@ -14,7 +14,9 @@
  * Each function cites the reference lines it follows (paths relative to /root/reference/src).
  * Written from the behaviour of those lines; no reference source is copied (the reference is Rust).
  */
+#define _POSIX_C_SOURCE 200809L
 #include <math.h>
+#include <time.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,6 +26,13 @@
 #endif
 
 #define PROBA_MIN 1.0e-4f /* embedder.rs:50 */
+
+static double wall_seconds(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 /* ------------------------------------------------------------------------------------------
  * Edge weights.  tools/kdumap.rs:132-235 (get_scale_from_proba_normalisation) mapped over nodes
@@ -343,7 +352,8 @@ int64_t oracle_optimize(uint64_t n, uint32_t d, const uint64_t *row_ptr, const u
                         const float *p, const float *emb_scale, float *y, double b,
                         double grad_step_init, uint32_t nb_sampling_by_edge, uint32_t nb_grad_batch,
                         const float *neg_w, uint64_t seed, uint32_t first_batch,
-                        uint32_t n_batches_to_run, double sample_fraction, int n_threads)
+                        uint32_t n_batches_to_run, double sample_fraction, int n_threads,
+                        double *loop_seconds /* nullable: wall time of the sampling loop only */)
 {
     if (d > 64) return -1;
     const uint64_t E = row_ptr[n];
@@ -366,8 +376,10 @@ int64_t oracle_optimize(uint64_t n, uint32_t d, const uint64_t *row_ptr, const u
 #endif
     const uint64_t nb_sample = (uint64_t)((double)nb_sampling_by_edge * (double)E * sample_fraction); /* :858 */
     int64_t done = 0;
+    double t_loop = 0.0;
     for (uint32_t iter = first_batch; iter < first_batch + n_batches_to_run && iter <= nb_grad_batch; iter++) {
         const double grad_step = grad_step_init * (1.0 - (double)iter / (double)nb_grad_batch); /* :875 */
+        const double t0 = wall_seconds();
 #pragma omp parallel
         {
             rng_t rng;
@@ -396,8 +408,10 @@ int64_t oracle_optimize(uint64_t n, uint32_t d, const uint64_t *row_ptr, const u
                 sgd_sample(y, d, i, j, (double)p[e], (double)emb_scale[i], b, grad_step, negs, 5, g);
             }
         }
+        t_loop += wall_seconds() - t0;
         done += (int64_t)nb_sample;
     }
+    if (loop_seconds) *loop_seconds = t_loop;
     alias_free(&pos);
     if (have_neg) alias_free(&negt);
     free(src);

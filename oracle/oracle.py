@@ -121,8 +121,8 @@ def hubness_weights(row_ptr, col):
 
 
 def optimize(row_ptr, col, p, emb_scale, y0, b=1.0, grad_step=2.0, nb_sampling_by_edge=10, nb_grad_batch=20,
-             neg_w=None, seed=0, first_batch=1, n_batches=None, sample_fraction=1.0, n_threads=0):
-    """embedder.rs:794-904 Hogwild loop.  Returns (y, positive_samples_processed)."""
+             neg_w=None, seed=0, first_batch=1, n_batches=None, sample_fraction=1.0, n_threads=0, timing=False):
+    """embedder.rs:794-904 Hogwild loop.  Returns (y, positive_samples_processed[, loop_seconds])."""
     row_ptr, col = _graph(row_ptr, col)
     p = np.ascontiguousarray(p, np.float32)
     emb_scale = np.ascontiguousarray(emb_scale, np.float32)
@@ -130,6 +130,7 @@ def optimize(row_ptr, col, p, emb_scale, y0, b=1.0, grad_step=2.0, nb_sampling_b
     n, d = y.shape
     if n_batches is None:
         n_batches = nb_grad_batch
+    secs = C.c_double(0.0)
     negp = None
     if neg_w is not None:
         neg_w = np.ascontiguousarray(neg_w, np.float32)
@@ -138,9 +139,11 @@ def optimize(row_ptr, col, p, emb_scale, y0, b=1.0, grad_step=2.0, nb_sampling_b
                                  _p(p, C.c_float), _p(emb_scale, C.c_float), _p(y, C.c_float), C.c_double(b),
                                  C.c_double(grad_step), C.c_uint32(nb_sampling_by_edge), C.c_uint32(nb_grad_batch),
                                  negp, C.c_uint64(seed), C.c_uint32(first_batch), C.c_uint32(n_batches),
-                                 C.c_double(sample_fraction), C.c_int(n_threads))
+                                 C.c_double(sample_fraction), C.c_int(n_threads), C.byref(secs))
     if done < 0:
         raise RuntimeError(f"oracle_optimize failed: {done}")
+    if timing:
+        return y, int(done), secs.value
     return y, int(done)
 
 

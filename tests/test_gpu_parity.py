@@ -1,0 +1,318 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the committed golden vectors.  Tolerances are the north star's (BASELINE.json):
+edge weights <= 1e-5 relative (fp32), one fixed-sample step <= 1e-4, cross-entropy <= 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import annembed_b200 as A
+from oracle import oracle
+from tests.conftest import random_graph
+from tests.studies import hostsim_binding as hs
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath_small.npz"))
+
+
+def ctx_for(row_ptr, col, dist, **kw):
+    p = A.EmbedderParams(**kw)
+    ctx = A.CudaContext(p)
+    ctx.set_graph_csr(row_ptr, col, dist)
+    return ctx
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
+
+
+# ------------------------------------------------------------------ K1 (T2, T3)
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_edge_weights_golden(tag):
+    rho, beta = G[f"w_{tag}_params"]
+    ctx = ctx_for(G["row_ptr"], G["col"], G["dist"], scale_rho=float(rho), beta=float(beta))
+    scale, p = ctx.edge_weights()
+    assert rel_err(scale, G[f"w_{tag}_scale"]) <= 1e-6
+    assert rel_err(p, G[f"w_{tag}_p"]) <= 1e-5
+    np.testing.assert_allclose(ctx.get_perplexity(), G[f"w_{tag}_perplexity"], rtol=2e-5)
+
+
+@pytest.mark.parametrize("seed,kmin,kmax,beta,rho", [(1, 1, 1, 1.0, 1.0), (2, 2, 16, 1.0, 0.75), (3, 6, 6, 2.0, 1.0),
+                                                     (4, 3, 31, 0.5, 1.3), (5, 10, 10, 1.0, 1.0)])
+def test_edge_weights_vs_oracle_random_ragged(seed, kmin, kmax, beta, rho):
+    row_ptr, col, dist = random_graph(5000, kmin, kmax, seed, zero_frac=0.05, dup_rows=50)
+    ctx = ctx_for(row_ptr, col, dist, scale_rho=rho, beta=beta)
+    scale, p = ctx.edge_weights()
+    s_ref, p_ref = oracle.edge_weights(row_ptr, col, dist, rho, beta)
+    assert rel_err(scale, s_ref) <= 1e-6
+    assert rel_err(p, p_ref) <= 1e-5
+    sums = np.add.reduceat(p.astype(np.float64), row_ptr[:-1].astype(np.int64))
+    assert np.abs(sums - 1).max() < 1e-5
+
+
+def test_edge_weights_degenerate_rows():
+    # all-equal row, all-zero row, zero scale with positive last distance, floor active (kdumap.rs:161-234)
+    row_ptr = np.array([0, 3, 6, 8, 10, 12, 14], np.uint64)
+    col = np.array([1, 2, 3, 0, 2, 3, 3, 4, 2, 4, 2, 3, 0, 1], np.uint32)
+    dist = np.array([2, 2, 2, 0, 0, 0, 0, 5, 0, 1, 0, 9, 1, 500], np.float32)
+    ctx = ctx_for(row_ptr, col, dist)
+    scale, p = ctx.edge_weights()
+    s_ref, p_ref = oracle.edge_weights(row_ptr, col, dist)
+    np.testing.assert_allclose(scale, s_ref, rtol=1e-6)
+    np.testing.assert_allclose(p, p_ref, rtol=1e-5)
+    np.testing.assert_allclose(p[:6], 1 / 3, rtol=1e-6)
+
+
+def test_edge_weights_scale_equivariance_on_device():
+    row_ptr, col, dist = random_graph(2000, 4, 12, seed=11)
+    s1, p1 = ctx_for(row_ptr, col, dist).edge_weights()
+    s2, p2 = ctx_for(row_ptr, col, (dist * np.float32(8.0)).astype(np.float32)).edge_weights()   # power of two: exact
+    np.testing.assert_array_equal(p1, p2)
+    np.testing.assert_array_equal(s2, s1 * np.float32(8.0))
+
+
+def test_edge_weights_umap_bisection_vs_oracle():
+    row_ptr, col, dist = random_graph(300, 5, 9, seed=21)
+    dist = (dist * np.float32(3.0)).astype(np.float32)
+    ctx = ctx_for(row_ptr, col, dist)
+    norm = 2.0
+    scale, w, status = ctx.edge_weights_umap(norm)
+    n_checked = 0
+    for i in range(300):
+        lo, hi = int(row_ptr[i]), int(row_ptr[i + 1])
+        rc, s_ref, w_ref = oracle.scale_from_umap(dist[lo:hi], norm)
+        if rc < 0:
+            assert status[i] == 2
+            continue
+        assert status[i] == rc
+        if rc == 0:
+            n_checked += 1
+            assert abs(float(w[lo:hi].sum()) - norm) < 3e-5
+            np.testing.assert_allclose(scale[i], s_ref, rtol=2e-3)
+            np.testing.assert_allclose(w[lo:hi], w_ref, rtol=2e-3, atol=1e-6)
+    assert n_checked > 50
+
+
+# ------------------------------------------------------------------ K2
+def test_embedded_scales_vs_oracle():
+    row_ptr, col, dist = random_graph(70000, 3, 8, seed=31)
+    ctx = ctx_for(row_ptr, col, dist)
+    scale, _ = ctx.edge_weights()
+    es = ctx.get_embedded_scales()
+    # fp64 mean on the device; the reference's sequential fp32 sum differs by ~1e-5 relative at this size
+    assert rel_err(es, oracle.embedded_scales(scale, f64_sum=True)) <= 1e-6
+    assert rel_err(es, oracle.embedded_scales(scale, f64_sum=False)) <= 1e-4
+    ctx2 = ctx_for(G["row_ptr"], G["col"], G["dist"])
+    ctx2.edge_weights()
+    assert rel_err(ctx2.get_embedded_scales(), G["emb_scale"]) <= 1e-6
+
+
+# ------------------------------------------------------------------ K3 (T4)
+@pytest.mark.parametrize("d", [2, 3, 15])
+@pytest.mark.parametrize("b", [1.0, 0.5])
+@pytest.mark.parametrize("gs", [1.0, 0.05])
+def test_step_fixed_golden(d, b, gs):
+    ctx = ctx_for(G["row_ptr"], G["col"], G["dist"], asked_dim=d, b=b)
+    ctx.set_edge_weights(G["w_a_scale"], G["w_a_p"])
+    ctx.set_embedding(G[f"y0_d{d}"])
+    ctx.step_fixed(G[f"edges_d{d}"], G[f"negs_d{d}"], gs)
+    y = ctx.get_embedding()
+    ref = G[f"step_d{d}_b{b}_g{gs}"]
+    # 1e-4 relative to the coordinate scale (layout box is O(1)); 64 chained samples
+    assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_step_fixed_vs_oracle_single_samples_and_clips():
+    row_ptr, col, dist = random_graph(1000, 4, 10, seed=41)
+    scale, p = oracle.edge_weights(row_ptr, col, dist)
+    es = oracle.embedded_scales(scale)
+    rng = np.random.default_rng(5)
+    for d, b, gs, box in ((2, 1.0, 2.0, 0.2), (2, 1.0, 0.3, 10.0), (8, 0.7, 1.0, 1.0), (32, 1.0, 1.0, 1.0)):
+        y0 = rng.uniform(-box / 2, box / 2, size=(1000, d)).astype(np.float32)
+        ctx = ctx_for(row_ptr, col, dist, asked_dim=d, b=b)
+        ctx.set_edge_weights(scale, p)
+        for trial in range(20):                      # independent single samples: no error accumulation
+            e = rng.integers(0, len(col), size=1).astype(np.uint64)
+            ng = rng.integers(0, 1000, size=(1, 5)).astype(np.uint32)
+            ctx.set_embedding(y0)
+            ctx.step_fixed(e, ng, gs)
+            y = ctx.get_embedding()
+            ref = oracle.step_fixed(row_ptr, col, p, es, y0, b, gs, e, ng)
+            moved = np.abs(ref - y0).max()
+            assert np.abs(y - ref).max() <= 1e-4 * max(moved, np.abs(ref).max(), 1e-3)
+        # the host build of the same device code agrees with the GPU to fp32 rounding
+        e = rng.integers(0, len(col), size=50).astype(np.uint64)
+        ng = rng.integers(0, 1000, size=(50, 5)).astype(np.uint32)
+        ctx.set_embedding(y0)
+        ctx.step_fixed(e, ng, gs)
+        np.testing.assert_allclose(ctx.get_embedding(), hs.step_fixed(row_ptr, col, p, es, y0, b, gs, e, ng),
+                                   rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ K5 (T5)
+@pytest.mark.parametrize("d", [2, 3, 15])
+@pytest.mark.parametrize("b", [1.0, 0.5])
+def test_cross_entropy_golden(d, b):
+    ctx = ctx_for(G["row_ptr"], G["col"], G["dist"], asked_dim=d, b=b)
+    ctx.set_edge_weights(G["w_a_scale"], G["w_a_p"])
+    ctx.set_embedding(G[f"y0_d{d}"])
+    ce = ctx.cross_entropy()
+    assert abs(ce - float(G[f"ce_d{d}_b{b}"])) <= 1e-6 * abs(float(G[f"ce_d{d}_b{b}"]))
+
+
+def test_cross_entropy_large_vs_oracle():
+    row_ptr, col, dist = random_graph(50000, 6, 6, seed=51)
+    ctx = ctx_for(row_ptr, col, dist)
+    scale, p = ctx.edge_weights()
+    y = np.random.default_rng(2).uniform(-5, 5, size=(50000, 2)).astype(np.float32)
+    ctx.set_embedding(y)
+    ref = oracle.cross_entropy(row_ptr, col, p, ctx.get_embedded_scales(), y, 1.0)
+    assert abs(ctx.cross_entropy() - ref) <= 1e-6 * abs(ref)
+
+
+# ------------------------------------------------------------------ sampler (T6) and K4
+def test_device_draws_match_host_build_bit_for_bit():
+    row_ptr, col, dist = random_graph(3000, 3, 12, seed=61)
+    ctx = ctx_for(row_ptr, col, dist, nb_sampling_by_edge=10, mini_epochs_per_batch=7, seed=1234567890123)
+    scale, p = ctx.edge_weights()
+    for epoch in (0, 1, 77):
+        c_dev, n_dev = ctx.debug_draws(epoch)
+        c_host, n_host = hs.draws(row_ptr, col, p, 10, 7, 1234567890123, epoch)
+        np.testing.assert_array_equal(c_dev, c_host)
+        np.testing.assert_array_equal(n_dev, n_host)
+    # hubness sampler: alias draws follow the weights
+    w = oracle.hubness_weights(row_ptr, col)
+    np.testing.assert_array_equal(ctx.get_hubness_counts(), np.bincount(col, minlength=3000))
+    ctxh = ctx_for(row_ptr, col, dist, hubness_weighting=True, mini_epochs_per_batch=1)
+    ctxh.edge_weights()
+    ctxh.set_neg_weights(w)
+    hist = np.zeros(3000)
+    for epoch in range(30):
+        c, negs = ctxh.debug_draws(epoch)
+        hist += np.bincount(negs[c > 0].reshape(-1), minlength=3000)
+    freq = hist / hist.sum()
+    assert np.corrcoef(freq, w / w.sum())[0, 1] > 0.9
+
+
+@pytest.mark.parametrize("d,hub", [(2, False), (2, True), (5, False), (15, False)])
+def test_epoch_kernel_matches_host_replay(d, hub):
+    """K4 against the host build of the same mini-epoch body: same draws, same order, fp32 rounding apart."""
+    row_ptr, col, dist = random_graph(4000, 3, 10, seed=71)
+    n = 4000
+    kw = dict(asked_dim=d, nb_grad_batch=4, nb_sampling_by_edge=10, mini_epochs_per_batch=5, grad_step=1.0, seed=99,
+              hubness_weighting=hub)
+    ctx = ctx_for(row_ptr, col, dist, **kw)
+    scale, p = ctx.edge_weights()
+    es = ctx.get_embedded_scales()
+    if hub:
+        ctx.set_neg_weights(oracle.hubness_weights(row_ptr, col))
+    y0 = np.random.default_rng(1).uniform(-2, 2, size=(n, d)).astype(np.float32)
+    ctx.set_embedding(y0)
+    ctx.optimize_batches(1, 1)                       # 5 mini-epochs at gamma = 0.75
+    y = ctx.get_embedding()
+    st = ctx.get_stats()
+    assert st["epoch_launches"] == 5 and st["mini_epochs_per_batch"] == 5
+    if hub:
+        return                                       # host replay needs the device alias table; covered by draws test
+    y_host, done = hs.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, 10, 4, 5, 99, None, 1, 1)
+    assert st["positive_samples"] == done
+    assert abs(done / (10 * len(col)) - 1) < 0.02    # one batch = nb_sampling_by_edge * E samples in expectation
+    # chaotic amplification of fp32 rounding over 5 mini-epochs stays small on almost every node
+    err = np.abs(y - y_host).max(axis=1)
+    assert np.quantile(err, 0.99) < 1e-3 and np.median(err) < 1e-5
+
+
+def test_optimize_is_deterministic_and_schedule_matches_reference():
+    row_ptr, col, dist = random_graph(3000, 5, 9, seed=81)
+    kw = dict(nb_grad_batch=5, grad_step=1.0, seed=7)
+    y0 = np.random.default_rng(3).uniform(-.5, .5, size=(3000, 2)).astype(np.float32)
+    outs = []
+    for _ in range(2):
+        ctx = ctx_for(row_ptr, col, dist, **kw)
+        ctx.edge_weights(want_outputs=False)
+        ctx.set_embedding(y0)
+        ce0, ce1 = ctx.optimize()
+        outs.append(ctx.get_embedding())
+        assert np.isfinite(outs[-1]).all() and np.isfinite([ce0, ce1]).all()
+    np.testing.assert_array_equal(outs[0], outs[1])
+    # last batch has grad_step 0 (embedder.rs:873-876): it must not move anything
+    before = outs[0]
+    ctx.optimize_batches(5, 1)
+    np.testing.assert_array_equal(ctx.get_embedding(), before)
+    # reset restores the initial layout
+    ctx.reset_embedding()
+    np.testing.assert_array_equal(ctx.get_embedding(), y0)
+    # a different seed gives a different layout
+    ctx2 = ctx_for(row_ptr, col, dist, **{**kw, "seed": 8})
+    ctx2.edge_weights(want_outputs=False)
+    ctx2.set_embedding(y0)
+    ctx2.optimize(want_ce=False)
+    assert np.abs(ctx2.get_embedding() - before).max() > 1e-3
+
+
+# ------------------------------------------------------------------ ABI behaviour (T9)
+def test_abi_error_codes_and_state_machine():
+    row_ptr, col, dist = random_graph(100, 2, 5, seed=91)
+    p = A.EmbedderParams()
+    ctx = A.CudaContext(p)
+
+    def status(fn, *a):
+        with pytest.raises(A.AnnembedCudaError) as e:
+            fn(*a)
+        return e.value.status
+
+    assert status(ctx.edge_weights) == 5                                   # graph not set
+    assert status(ctx.optimize) == 5
+    bad = row_ptr.copy(); bad[4] = bad[3]                                   # node 3 empty -> kdumap.rs:75-85
+    bad_col = np.delete(col, np.s_[int(row_ptr[3]):int(row_ptr[4])])
+    bad_dist = np.delete(dist, np.s_[int(row_ptr[3]):int(row_ptr[4])])
+    bad[4:] = row_ptr[4:] - (row_ptr[4] - row_ptr[3])
+    assert status(ctx.set_graph_csr, bad, bad_col, bad_dist) == 3
+    uns = dist.copy(); lo = int(row_ptr[10]); uns[lo], uns[lo + 1] = uns[lo + 1] + 1, uns[lo]
+    assert status(ctx.set_graph_csr, row_ptr, col, uns) == 4
+    c2 = col.copy(); c2[0] = 0                                              # self edge of node 0
+    assert status(ctx.set_graph_csr, row_ptr, c2, dist) == 1
+    c3 = col.copy(); c3[5] = 100
+    assert status(ctx.set_graph_csr, row_ptr, c3, dist) == 1
+    tiny = (np.array([0, 1, 2, 3], np.uint64), np.array([1, 2, 0], np.uint32), np.ones(3, np.float32))
+    assert status(ctx.set_graph_csr, *tiny) == 8                            # nobody acceptable as negative
+    ctx.set_graph_csr(row_ptr, col, dist)
+    assert status(ctx.optimize) == 5                                        # embedding not set
+    ctx.set_embedding(np.zeros((100, 2), np.float32))
+    assert status(ctx.optimize) == 5                                        # weights not computed (embedder.rs:802-808)
+    ctx.edge_weights(want_outputs=False)
+    ctx.optimize()
+    # context reuse with another graph
+    r2, c2, d2 = random_graph(64, 3, 3, seed=92)
+    ctx.set_graph_csr(r2, c2, d2)
+    assert status(ctx.get_embedding) == 5
+    ctx.edge_weights(want_outputs=False)
+    ctx.set_embedding(np.random.default_rng(0).uniform(-1, 1, (64, 2)).astype(np.float32))
+    ctx.optimize()
+    assert np.isfinite(ctx.get_embedding()).all()
+    ctx.close()
+    hp = A.EmbedderParams(hubness_weighting=True)
+    ctxh = A.CudaContext(hp)
+    ctxh.set_graph_csr(row_ptr, col, dist)
+    ctxh.edge_weights(want_outputs=False)
+    ctxh.set_embedding(np.zeros((100, 2), np.float32))
+    assert status(ctxh.optimize) == 5                                       # hubness sampler not provided
+
+
+def test_embedder_mirror_end_to_end():
+    """Embedder::new / embed / get_embedded_reindexed through the host mirror."""
+    row_ptr, col, dist = random_graph(2000, 6, 6, seed=93)
+    ids = np.random.default_rng(4).permutation(2000).astype(np.uint64)
+    g = A.KGraph(row_ptr, col, dist, ids)
+    params = A.EmbedderParams(dmap_init=False, nb_grad_batch=6, grad_step=1.0, hubness_weighting=True)
+    emb = A.Embedder(g, params)
+    assert emb.embed() == 1
+    y = emb.get_embedded()
+    r = emb.get_embedded_reindexed()
+    assert y.shape == (2000, 2) and np.isfinite(y).all()
+    np.testing.assert_array_equal(r[ids.astype(np.int64)], y)
+    assert emb.cross_entropy[1] < emb.cross_entropy[0]
+    assert emb.get_hubness().sum() == len(col)
+    with pytest.raises(A.EmbedError):
+        A.Embedder(g, A.EmbedderParams(dmap_init=True)).embed()

@@ -1,0 +1,123 @@
+"""Host-side logic: KGraph CSR interchange file, re-indexing, shard ranges, Philox known answers and the
+counter-based sampler (host build of the product's __host__ __device__ code, tests/hostsim)."""
+import numpy as np
+import pytest
+
+import annembed_b200 as A
+from annembed_b200.dist import shard_range
+from tests.conftest import random_graph
+from tests.studies import hostsim_binding as hs
+from oracle import oracle
+
+
+def test_csr_file_roundtrip(tmp_path):
+    row_ptr, col, dist = random_graph(50, 1, 7, seed=1)
+    ids = np.random.default_rng(0).permutation(50).astype(np.uint64)
+    g = A.KGraph(row_ptr, col, dist, ids)
+    path = str(tmp_path / "g.csr")
+    A.write_csr(path, g)
+    g2 = A.read_csr(path)
+    np.testing.assert_array_equal(g.row_ptr, g2.row_ptr)
+    np.testing.assert_array_equal(g.col, g2.col)
+    np.testing.assert_array_equal(g.dist, g2.dist)
+    np.testing.assert_array_equal(g.data_id, g2.data_id)
+    assert g2.get_max_nbng() == g.get_max_nbng() == 7 and g2.get_nb_nodes() == 50
+    assert g2.get_idx_from_dataid(g2.get_data_id_from_idx(17)) == 17
+    with open(path, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(ValueError):
+        A.read_csr(path)
+    with pytest.raises(ValueError):
+        A.KGraph(row_ptr, col[:-1], dist)
+
+
+def test_reindexing_follows_data_ids():
+    """get_embedded_reindexed: row i -> row DataId(i) (embedder.rs:397-403)."""
+    idx = np.array([[1], [2], [0]])
+    g = A.KGraph.from_knn(idx, np.ones((3, 1), np.float32), data_id=np.array([2, 0, 1]))
+    e = A.Embedder(g, A.EmbedderParams(dmap_init=False))
+    e.embedding = np.array([[0, 0], [1, 1], [2, 2]], np.float32)
+    np.testing.assert_array_equal(e.get_embedded_reindexed(), [[1, 1], [2, 2], [0, 0]])
+    np.testing.assert_array_equal(e.get_embedded_by_dataid(2), [0, 0])
+    g.data_id = np.array([0, 1, 7], np.uint64)
+    with pytest.raises(IndexError):
+        e.get_embedded_reindexed()
+    e2 = A.Embedder(g, A.EmbedderParams())
+    with pytest.raises(RuntimeError):
+        e2.get_embedded_reindexed()
+
+
+def test_shard_ranges_partition_nodes():
+    for n in (1, 7, 70000, 11_000_000):
+        for r in (1, 2, 3, 4, 8):
+            ranges = [shard_range(n, k, r) for k in range(r)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(r - 1))
+            pad = (n + r - 1) // r
+            assert all(hi - lo <= pad for lo, hi in ranges)
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors for philox4x32 with 10 rounds."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, exp in kat:
+        np.testing.assert_array_equal(hs.philox(ctr, key), np.array(exp, np.uint32))
+
+
+def test_sampler_expectation_and_rejection():
+    """T6 on the host build: E[count_e] = nbs*E/n/M * p_e ; negatives avoid {i, j} U N(i) (embedder.rs:1246-1252)."""
+    row_ptr, col, dist = random_graph(400, 4, 10, seed=5)
+    n = 400
+    scale, p = oracle.edge_weights(row_ptr, col, dist)
+    nbs, M = 10, 5
+    kappa = nbs * len(col) / n / M
+    tot = np.zeros(len(col))
+    src = np.repeat(np.arange(n), np.diff(row_ptr.astype(np.int64)))
+    for epoch in range(200):
+        c, negs = hs.draws(row_ptr, col, p, nbs, M, seed=9, epoch=epoch)
+        tot += c
+        assert np.all(np.abs(c.astype(np.float64) - kappa * p) < 1.0)       # floor(lambda + u)
+        fired = c > 0
+        assert np.all(negs[~fired] == 0xFFFFFFFF)
+        ng = negs[fired]
+        assert ng.max() < n
+        assert not np.any(ng == src[fired, None]) and not np.any(ng == col[fired, None])
+        for e in np.nonzero(fired)[0][:50]:
+            i = src[e]
+            assert not np.intersect1d(negs[e], col[int(row_ptr[i]):int(row_ptr[i + 1])]).size
+    assert np.abs(tot / 200 - kappa * p).max() < 0.18          # 5 sigma of a Bernoulli mean over 200 epochs
+    assert abs((tot / 200).sum() / (kappa * p).sum() - 1) < 0.01
+    # determinism and key sensitivity
+    c1, n1 = hs.draws(row_ptr, col, p, nbs, M, seed=9, epoch=3)
+    c2, n2 = hs.draws(row_ptr, col, p, nbs, M, seed=9, epoch=3)
+    c3, n3 = hs.draws(row_ptr, col, p, nbs, M, seed=10, epoch=3)
+    np.testing.assert_array_equal(c1, c2); np.testing.assert_array_equal(n1, n2)
+    assert np.any(n1 != n3)
+
+
+def test_negative_uniformity_chi2():
+    """Accepted negatives are uniform over the nodes allowed for the sampled edge (embedder.rs:1121,1246-1252)."""
+    n = 64
+    row_ptr, col, dist = random_graph(n, 3, 5, seed=2)
+    scale, p = oracle.edge_weights(row_ptr, col, dist)
+    src = np.repeat(np.arange(n), np.diff(row_ptr.astype(np.int64)))
+    allowed = np.ones((len(col), n))
+    for e in range(len(col)):
+        i = src[e]
+        allowed[e, i] = 0
+        allowed[e, col[int(row_ptr[i]):int(row_ptr[i + 1])]] = 0
+    allowed /= allowed.sum(1, keepdims=True)
+    hist = np.zeros(n)
+    expect = np.zeros(n)
+    for epoch in range(300):
+        c, negs = hs.draws(row_ptr, col, p, 10, 1, seed=1, epoch=epoch)
+        fired = c > 0
+        hist += np.bincount(negs[fired].reshape(-1), minlength=n)
+        expect += 5 * allowed[fired].sum(0)
+    chi2 = ((hist - expect) ** 2 / expect).sum()
+    assert chi2 < n + 6 * np.sqrt(2 * n), chi2          # chi2(63): mean 63, sd 11
