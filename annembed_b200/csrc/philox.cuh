@@ -39,6 +39,24 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return o;
 }
 
+struct Philox2 { uint32_t x, y; };
+
+// Philox2x32-10: half the work of the 4x32 variant for 64 random bits (per-node uniforms, replayed by in-edge owners)
+__host__ __device__ __forceinline__ Philox2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
+{
+    const uint32_t M = 0xD256D193u, W = 0x9E3779B9u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi, lo;
+        philox_mulhilo(M, c0, hi, lo);
+        c0 = hi ^ k ^ c1;
+        c1 = lo;
+        k += W;
+    }
+    Philox2 o; o.x = c0; o.y = c1;
+    return o;
+}
+
 // 24-bit uniform in [0,1), exact in fp32
 __host__ __device__ __forceinline__ float u01_24(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
 

@@ -169,6 +169,8 @@ struct EpochArgs {
     const uint4 *__restrict__ in_rec;   // {src node, edge id, bits(p_e), bits(inv_s2[src])}, entry q at in_rec[q - in_base]
     uint64_t in_base;
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
+    const float *__restrict__ cum;       // v2: inclusive cumulative probability along each row (last entry exactly 1)
+    uint32_t k2;                         // v2: Philox2x32 key of the per-node uniform
     uint32_t n, lo, hi;
     uint32_t epoch, k0, k1;
     float kappa;                        // expected firings of edge e in this mini-epoch = kappa * p_e
@@ -300,6 +302,126 @@ __host__ __device__ __forceinline__ unsigned int epoch_node(const EpochArgs &a, 
     }
     store_row<DP>(a.y_next, node, y);
     return applied;
+}
+
+
+// =====================================================================================================
+// v2 sampler: systematic (low-variance) sampling per node.
+// Node i owns one uniform u_i(epoch) (Philox2x32-10 of (node, epoch)).  Its sample points are s + u_i,
+// s = 0,1,..; edge m of the row covers [kappa*P_{m-1}, kappa*P_m) where P is the cumulative edge probability
+// of the row (row sums are 1), so  count_m = ceil(kappa*P_m - u) - ceil(kappa*P_{m-1} - u),
+// E[count_m] = kappa * p_m  (the reference's expectation, embedder.rs:858,987,1182) and every node fires
+// ceil(kappa - u) times per mini-epoch: the reference samples every node at the same rate (P(e) = p_e / N).
+// The destination's owner replays the decision from (src, epoch, P_lo, P_hi): no communication, no atomics.
+// =====================================================================================================
+__host__ __device__ __forceinline__ float node_uniform(uint32_t node, uint32_t epoch, uint32_t k2)
+{
+    return u01_24(philox2x32_10(node, epoch, k2).x);
+}
+__host__ __device__ __forceinline__ int cum_ceil(float kappa, float P, float u)
+{
+    return (int)ceilf(fmaf(kappa, P, -u));
+}
+
+// the 5 accepted negatives of firing s of `node` (v2 streams: counter (node, sub, epoch, tag))
+//   tag 1: sub = s          words x,y,z,w -> negatives 0..3
+//   tag 2: sub = s >> 2     word (s & 3)  -> negative 4
+//   tag 3: sub = s, tag 3 + t: accept words (hubness) ; tag 0x80000000|q<<8|t : redraws
+template <bool HUB>
+__host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t node, uint32_t s, uint32_t j,
+                                                           uint64_t r0, uint64_t r1, uint32_t (&negs)[ANNEMBED_NB_NEG])
+{
+    const Philox4 A = philox4x32_10(node, s, a.epoch, 1u, a.k0, a.k1);
+    const Philox4 B = philox4x32_10(node, s >> 2, a.epoch, 2u, a.k0, a.k1);
+    const uint32_t w4 = (s & 2u) ? ((s & 1u) ? B.w : B.z) : ((s & 1u) ? B.y : B.x);
+    uint32_t wi[ANNEMBED_NB_NEG] = {A.x, A.y, A.z, A.w, w4};
+    uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
+    if constexpr (HUB) {
+        const Philox4 C = philox4x32_10(node, s, a.epoch, 3u, a.k0, a.k1);
+        const Philox4 D = philox4x32_10(node, s, a.epoch, 4u, a.k0, a.k1);
+        wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = D.x;
+    }
+#pragma unroll
+    for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+        uint32_t k = map_negative<HUB>(a, wi[q], wa[q]);
+        bool rej = negative_rejected(a, k, node, j, r0, r1);
+        for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
+            const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
+            k = map_negative<HUB>(a, R.x, R.y);
+            rej = negative_rejected(a, k, node, j, r0, r1);
+        }
+        negs[q] = rej ? ANNEMBED_NO_NODE : k;
+    }
+}
+
+// in_rec (v2): {src node, bits(P_lo), bits(P_hi), bits(inv_s2[src])}; p_e is taken as P_hi - P_lo on both sides.
+template <int DP, bool HUB>
+__host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &a, uint32_t node)
+{
+    float y[DP], g[DP];
+    load_row<DP>(a.y_snap, node, y);
+    const float inv_s2 = a.inv_s2[node];
+    const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
+    const float u = node_uniform(node, a.epoch, a.k2);
+    unsigned int s = 0;
+    // phase A: out-edges in row order; firing index s runs over the node's sample points
+    float P_lo = 0.0f;
+    int c_lo = 0;                                     // ceil(-u) == 0 for u in [0,1)
+    for (uint64_t m = r0; m < r1; m++) {
+        const float P_hi = a.cum[m];
+        const int c_hi = cum_ceil(a.kappa, P_hi, u);
+        const int c = c_hi - c_lo;
+        const float pe = P_hi - P_lo;
+        P_lo = P_hi; c_lo = c_hi;
+        if (c <= 0) continue;
+        const uint32_t j = a.col[m];
+        float yj[DP];
+        load_row<DP>(a.y_snap, j, yj);
+        for (int f = 0; f < c; f++, s++) {
+            uint32_t negs[ANNEMBED_NB_NEG];
+            draw_negatives_v2<HUB>(a, node, s, j, r0, r1, negs);
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
+            if constexpr (DP <= 4) {
+                float yk[ANNEMBED_NB_NEG][DP];
+#pragma unroll
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+                    load_row<DP>(a.y_snap, negs[q] == ANNEMBED_NO_NODE ? node : negs[q], yk[q]);
+                attract<DP>(y, yj, g, pe, inv_s2, a.K);
+#pragma unroll
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+                    if (negs[q] != ANNEMBED_NO_NODE) repulse<DP>(y, yk[q], g, inv_s2, a.K);
+            } else {
+                attract<DP>(y, yj, g, pe, inv_s2, a.K);
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+                    if (negs[q] == ANNEMBED_NO_NODE) continue;
+                    float yk[DP];
+                    load_row<DP>(a.y_snap, negs[q], yk);
+                    repulse<DP>(y, yk, g, inv_s2, a.K);
+                }
+            }
+        }
+    }
+    // phase B: in-edges in transposed-index order
+    const uint64_t q0 = a.in_ptr[node - a.lo], q1 = a.in_ptr[node - a.lo + 1];
+    for (uint64_t q = q0; q < q1; q++) {
+        const uint4 rec = a.in_rec[q - a.in_base];
+        const float us = node_uniform(rec.x, a.epoch, a.k2);
+        const float Pl = as_float(rec.y), Ph = as_float(rec.z);
+        const int c = cum_ceil(a.kappa, Ph, us) - cum_ceil(a.kappa, Pl, us);
+        if (c <= 0) continue;
+        float ys[DP];
+        load_row<DP>(a.y_snap, rec.x, ys);
+        const float inv_s2_src = as_float(rec.w);
+        const float pe = Ph - Pl;
+        for (int f = 0; f < c; f++) {
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
+            attract<DP>(ys, y, g, pe, inv_s2_src, a.K);
+        }
+    }
+    store_row<DP>(a.y_next, node, y);
+    return s;
 }
 
 } // namespace annembed

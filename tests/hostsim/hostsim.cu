@@ -24,7 +24,15 @@ struct HostCtx {
     std::vector<uint64_t> in_ptr;
     std::vector<uint4> in_rec;
     std::vector<float> inv_s2;
+    std::vector<float> cum;
 };
+static int g_version = 1;
+extern "C" void hostsim_set_version(int v) { g_version = v; }
+extern "C" void hostsim_philox2(const uint32_t ctr[2], uint32_t key, uint32_t out[2])
+{
+    Philox2 r = philox2x32_10(ctr[0], ctr[1], key);
+    out[0] = r.x; out[1] = r.y;
+}
 
 static void build(HostCtx &h, uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *p, const float *emb_scale)
 {
@@ -35,10 +43,18 @@ static void build(HostCtx &h, uint64_t n, const uint64_t *row_ptr, const uint32_
     for (uint64_t e = 0; e < E; e++) h.in_ptr[col[e] + 1]++;
     for (uint64_t i = 0; i < n; i++) h.in_ptr[i + 1] += h.in_ptr[i];
     h.in_rec.resize(E);
+    h.cum.resize(E);
+    for (uint64_t i = 0; i < n; i++) {
+        float acc = 0.0f;
+        for (uint64_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) { acc += p[e]; h.cum[e] = acc < 1.0f ? acc : 1.0f; }
+        h.cum[row_ptr[i + 1] - 1] = 1.0f;
+    }
     std::vector<uint64_t> fill(h.in_ptr.begin(), h.in_ptr.end() - 1);
     for (uint64_t i = 0; i < n; i++)
         for (uint64_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) {   // ascending edge id inside each destination
-            uint4 r; r.x = (uint32_t)i; r.y = (uint32_t)e; r.z = as_uint(p[e]); r.w = as_uint(h.inv_s2[i]);
+            uint4 r; r.x = (uint32_t)i; r.w = as_uint(h.inv_s2[i]);
+            if (g_version == 1) { r.y = (uint32_t)e; r.z = as_uint(p[e]); }
+            else { r.y = as_uint(e == row_ptr[i] ? 0.0f : h.cum[e - 1]); r.z = as_uint(h.cum[e]); }
             h.in_rec[fill[col[e]]++] = r;
         }
 }
@@ -48,7 +64,8 @@ static uint64_t run_epoch(const EpochArgs &a)
 {
     uint64_t tot = 0;
 #pragma omp parallel for schedule(dynamic, 1024) reduction(+ : tot)
-    for (int64_t i = (int64_t)a.lo; i < (int64_t)a.hi; i++) tot += epoch_node<DP, HUB>(a, (uint32_t)i);
+    for (int64_t i = (int64_t)a.lo; i < (int64_t)a.hi; i++)
+        tot += g_version == 1 ? epoch_node<DP, HUB>(a, (uint32_t)i) : epoch_node_v2<DP, HUB>(a, (uint32_t)i);
     return tot;
 }
 
@@ -87,6 +104,7 @@ extern "C" int64_t hostsim_optimize(uint64_t n, uint32_t d, const uint64_t *row_
             a.row_ptr = row_ptr; a.col = col; a.p = p; a.inv_s2 = h.inv_s2.data();
             a.in_ptr = h.in_ptr.data(); a.in_rec = h.in_rec.data(); a.in_base = 0;
             a.neg_alias = (const uint2 *)neg_alias;
+            a.cum = h.cum.data(); a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
             a.n = (uint32_t)n; a.lo = 0; a.hi = (uint32_t)n;
             a.epoch = (iter - 1) * M + m; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
             a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);

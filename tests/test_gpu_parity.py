@@ -197,10 +197,13 @@ def test_device_draws_match_host_build_bit_for_bit():
 
 @pytest.mark.parametrize("d,hub", [(2, False), (2, True), (5, False), (15, False)])
 def test_epoch_kernel_matches_host_replay(d, hub):
-    """K4 against the host build of the same mini-epoch body: same draws, same order, fp32 rounding apart."""
+    """K4 against the host build of the same mini-epoch body: same draws, same order, fp32 rounding apart.
+    ONE mini-epoch is compared: the dynamics are chaotic (repulsion coefficients up to 2 triple a perturbation per
+    close negative), so rounding differences between nvcc's fma contraction and the host build grow afterwards."""
     row_ptr, col, dist = random_graph(4000, 3, 10, seed=71)
     n = 4000
-    kw = dict(asked_dim=d, nb_grad_batch=4, nb_sampling_by_edge=10, mini_epochs_per_batch=5, grad_step=1.0, seed=99,
+    # nb_sampling_by_edge = 1 and one mini-epoch per batch: a batch is exactly one launch of K4
+    kw = dict(asked_dim=d, nb_grad_batch=4, nb_sampling_by_edge=1, mini_epochs_per_batch=1, grad_step=1.0, seed=99,
               hubness_weighting=hub)
     ctx = ctx_for(row_ptr, col, dist, **kw)
     scale, p = ctx.edge_weights()
@@ -209,18 +212,23 @@ def test_epoch_kernel_matches_host_replay(d, hub):
         ctx.set_neg_weights(oracle.hubness_weights(row_ptr, col))
     y0 = np.random.default_rng(1).uniform(-2, 2, size=(n, d)).astype(np.float32)
     ctx.set_embedding(y0)
-    ctx.optimize_batches(1, 1)                       # 5 mini-epochs at gamma = 0.75
+    ctx.optimize_batches(1, 1)                       # 1 mini-epoch at gamma = 0.75
     y = ctx.get_embedding()
     st = ctx.get_stats()
-    assert st["epoch_launches"] == 5 and st["mini_epochs_per_batch"] == 5
+    assert st["epoch_launches"] == 1 and st["mini_epochs_per_batch"] == 1
+    assert np.isfinite(y).all() and np.abs(y - y0).max() > 1e-2
     if hub:
         return                                       # host replay needs the device alias table; covered by draws test
-    y_host, done = hs.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, 10, 4, 5, 99, None, 1, 1)
+    y_host, done = hs.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, 1, 4, 1, 99, None, 1, 1)
     assert st["positive_samples"] == done
-    assert abs(done / (10 * len(col)) - 1) < 0.02    # one batch = nb_sampling_by_edge * E samples in expectation
-    # chaotic amplification of fp32 rounding over 5 mini-epochs stays small on almost every node
+    assert abs(done / len(col) - 1) < 0.03           # one batch = nb_sampling_by_edge * E samples in expectation
     err = np.abs(y - y_host).max(axis=1)
-    assert np.quantile(err, 0.99) < 1e-3 and np.median(err) < 1e-5
+    assert np.quantile(err, 0.999) < 1e-4 and np.median(err) < 1e-6, (np.quantile(err, 0.999), np.median(err), err.max())
+    # second mini-epoch (batch 2) still agrees on almost every node
+    ctx.optimize_batches(2, 1)
+    y_host2, _ = hs.optimize(row_ptr, col, p, es, y_host, 1.0, 1.0, 1, 4, 1, 99, None, 2, 1)
+    err2 = np.abs(ctx.get_embedding() - y_host2).max(axis=1)
+    assert np.quantile(err2, 0.99) < 1e-3, (np.quantile(err2, 0.99), err2.max())
 
 
 def test_optimize_is_deterministic_and_schedule_matches_reference():

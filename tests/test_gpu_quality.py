@@ -1,0 +1,57 @@
+"""T7: end-to-end statistical parity of the final layout -- CUDA epoch loop vs the Hogwild oracle.
+
+Same graph, same initial layout, same parameters (examples/mnist_digits.rs:92-100: 30 batches, grad_step 1,
+10 samples/edge).  The reference is unseeded and asynchronous, so parity is distributional:
+means over independent runs of the quality statistics of embedder.rs:620-753 (+ kNN preservation) within 1 %."""
+import numpy as np
+import pytest
+
+import annembed_b200 as A
+import workloads
+from oracle import oracle, quality
+
+pytestmark = pytest.mark.gpu
+
+N, K, NBNG, RUNS = 20000, 10, 50, 3
+
+
+@pytest.fixture(scope="module")
+def problem():
+    x, _ = workloads.gaussian_mixture(N, 784, seed=0)
+    idx, dist = workloads.knn_exact(x, K, device="cuda")
+    row_ptr, col, dist = workloads.csr_from_knn(idx, dist)
+    y0 = workloads.pca_init(x, 2)
+    return row_ptr, col, dist, y0
+
+
+def mean_stats(stats):
+    keys = ("nb_without_match", "mean_nbmatch", "knn_preservation", "median_ratio", "mean_ratio")
+    return {k: float(np.mean([s[k] for s in stats])) for k in keys}
+
+
+def test_quality_statistics_within_one_percent_of_oracle(problem):
+    row_ptr, col, dist, y0 = problem
+    scale, p = oracle.edge_weights(row_ptr, col, dist, 1.0, 1.0)
+    es = oracle.embedded_scales(scale)
+    ref, ours = [], []
+    for seed in range(RUNS):
+        y, _ = oracle.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, 10, 30, seed=seed + 1)
+        ref.append(quality.quality_stats(row_ptr, col, y, NBNG))
+        ctx = A.CudaContext(A.EmbedderParams(nb_grad_batch=30, grad_step=1.0, seed=100 + seed))
+        ctx.set_graph_csr(row_ptr, col, dist)
+        ctx.edge_weights(want_outputs=False)
+        ctx.set_embedding(y0)
+        ce0, ce1 = ctx.optimize()
+        ours.append(quality.quality_stats(row_ptr, col, ctx.get_embedding(), NBNG))
+        ours[-1]["ce"] = ce1
+        ref[-1]["ce"] = oracle.cross_entropy(row_ptr, col, p, es, y, 1.0)
+        ctx.close()
+    r, o = mean_stats(ref), mean_stats(ours)
+    print("oracle", r, "\ncuda  ", o)
+    for k in ("mean_nbmatch", "knn_preservation", "median_ratio"):
+        assert abs(o[k] - r[k]) <= 0.01 * abs(r[k]), (k, o[k], r[k])
+    assert abs(o["mean_ratio"] - r["mean_ratio"]) <= 0.02 * r["mean_ratio"]
+    # a count of rare events: within 1 % of the node count
+    assert abs(o["nb_without_match"] - r["nb_without_match"]) <= 0.01 * N
+    ce_r, ce_o = np.mean([s["ce"] for s in ref]), np.mean([s["ce"] for s in ours])
+    assert abs(ce_o - ce_r) <= 0.05 * ce_r
