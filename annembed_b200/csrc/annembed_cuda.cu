@@ -71,6 +71,7 @@ struct annembed_cuda_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int n_sm = 148;
+    int l2_persist_max = 0, l2_window_max = 0;   // bytes (device attributes)
 
     // graph (replicated on every rank)
     uint64_t n = 0, E = 0;
@@ -78,7 +79,7 @@ struct annembed_cuda_ctx {
     DevBuf<uint64_t> row_ptr;
     DevBuf<uint32_t> col;
     DevBuf<float> dist, rho;
-    DevBuf<float> scale, proba;
+    DevBuf<float> scale, proba, cum;
     bool have_graph = false, have_weights = false, have_build = false, have_embedding = false, have_alias = false;
 
     // optimizer context (≙ EntropyOptim, embedder.rs:936-951)
@@ -300,7 +301,7 @@ __global__ void k_in_ptr(uint64_t E, uint64_t n, const uint32_t *__restrict__ so
 }
 
 __global__ void k_in_rec(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_t *__restrict__ sorted_eid,
-                         const uint64_t *__restrict__ row_ptr, const float *__restrict__ p,
+                         const uint64_t *__restrict__ row_ptr, const float *__restrict__ cum,
                          const float *__restrict__ inv_s2, uint4 *__restrict__ rec)
 {
     const uint64_t q = q_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,7 +309,8 @@ __global__ void k_in_rec(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_
     const uint32_t e = sorted_eid[q];
     uint64_t a = 0, b = n;                       // largest i with row_ptr[i] <= e
     while (b - a > 1) { const uint64_t mid = (a + b) >> 1; if (row_ptr[mid] <= e) a = mid; else b = mid; }
-    rec[q - q_lo] = make_uint4((uint32_t)a, e, __float_as_uint(p[e]), __float_as_uint(inv_s2[a]));
+    const float P_lo = (row_ptr[a] == e) ? 0.0f : cum[e - 1];
+    rec[q - q_lo] = make_uint4((uint32_t)a, __float_as_uint(P_lo), __float_as_uint(cum[e]), __float_as_uint(inv_s2[a]));
 }
 
 __global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint32_t *__restrict__ out)
@@ -350,16 +352,173 @@ __global__ void k_step_fixed(float *Y, uint64_t n, const uint64_t *__restrict__ 
     }
 }
 
-// K4: one mini-epoch over the owned node range
+// K4 (generic fallback): one thread per owned node, rows read from global memory.  Used when a row can be longer
+// than 16 neighbours; also the on-device cross-check of the tiled kernel below (tests/test_gpu_parity.py).
 template <int DP, bool HUB>
-__global__ void __launch_bounds__(256) k_epoch(EpochArgs a, unsigned long long *sample_counter)
+__global__ void __launch_bounds__(256) k_epoch_generic(EpochArgs a, unsigned long long *sample_counter)
 {
     const uint32_t node = a.lo + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int applied = 0;
-    if (node < a.hi) applied = epoch_node<DP, HUB>(a, node);
+    if (node < a.hi) applied = epoch_node_v2<DP, HUB>(a, node);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) applied += __shfl_xor_sync(0xffffffffu, applied, o);
-    if ((threadIdx.x & 31) == 0 && applied) atomicAdd(sample_counter, (unsigned long long)applied);
+    if ((threadIdx.x & 31) == 0 && applied) atomicAdd(sample_counter + (blockIdx.x & 255), (unsigned long long)applied);
+}
+
+// K4 (tiled): one warp owns a tile of 32 consecutive nodes.
+//  phase A  lane = node.  The row (<= KREG neighbours) is kept in registers for the rejection test and mirrored,
+//           transposed, in shared memory for the edge pick; every node fires ceil(kappa - u) times (systematic
+//           sampling), so lanes stay converged; the 6 gathers of a firing are issued before the arithmetic.
+//  phase B  lanes sweep the tile's in-edge records (coalesced 16-byte loads), replay the source's firing decision
+//           (Philox2x32 of (src, epoch)), gather the source row for the ones that fired and queue them in shared
+//           memory; each owner lane then applies its own entries in transposed-index order.
+//  No atomics on the layout, no block-level barrier: warps are independent.
+constexpr int EPOCH_QCAP = 128;                 // queue entries per warp
+template <int DP, int KREG>
+struct EpochTile {
+    static constexpr int WARPS = DP <= 4 ? 8 : (DP <= 16 ? 4 : 2);
+    static constexpr int ROW_BYTES = 32 * KREG * (4 + 4 + 2);                   // col, cum, ceil counts (u16)
+    static constexpr int QUEUE_BYTES = EPOCH_QCAP * (4 * DP + 4 + 4 + 4 + 4);   // y_src, p, inv_s2, q_rel, count
+    static constexpr int PER_WARP = ROW_BYTES + QUEUE_BYTES;
+    static constexpr int SMEM = WARPS * PER_WARP;
+};
+
+template <int DP, bool HUB, int KREG>
+__global__ void __launch_bounds__(EpochTile<DP, KREG>::WARPS * 32)
+k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
+{
+    using TL = EpochTile<DP, KREG>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t)blockIdx.x * TL::WARPS + wib;
+    const uint64_t n0 = (uint64_t)a.lo + tile * 32;
+    if (n0 >= a.hi) return;                                    // whole warp leaves together
+    unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
+    float *s_qy = reinterpret_cast<float *>(base);                              // [QCAP][DP]   (16-byte aligned first)
+    uint32_t *s_col = reinterpret_cast<uint32_t *>(base + EPOCH_QCAP * 4 * DP); // [KREG][32]
+    float *s_cum = reinterpret_cast<float *>(s_col + 32 * KREG);                // [KREG][32]
+    float *s_qp = s_cum + 32 * KREG;                                            // [QCAP]
+    float *s_qs = s_qp + EPOCH_QCAP;                                            // [QCAP]
+    uint32_t *s_qq = reinterpret_cast<uint32_t *>(s_qs + EPOCH_QCAP);           // [QCAP]
+    uint32_t *s_qc = s_qq + EPOCH_QCAP;                                         // [QCAP]
+    unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_qc + EPOCH_QCAP); // [KREG][32]
+
+    const uint32_t node = (uint32_t)n0 + lane;
+    const bool valid = node < a.hi;
+    float y[DP], g[DP];
+    uint32_t rc[KREG];
+    float inv_s2 = 1.0f;
+    int T = 0;
+#pragma unroll
+    for (int m = 0; m < KREG; m++) rc[m] = ANNEMBED_NO_NODE;
+    if (valid) {
+        load_row<DP>(a.y_snap, node, y);
+        inv_s2 = a.inv_s2[node];
+        const uint64_t r0 = a.row_ptr[node];
+        const int k = (int)(a.row_ptr[node + 1] - r0);
+        const float u = node_uniform(node, a.epoch, a.k2);
+#pragma unroll
+        for (int m = 0; m < KREG; m++) {
+            if (m < k) {
+                const uint32_t c = __ldcs(a.col + r0 + m);
+                const float P = __ldcs(a.cum + r0 + m);
+                const int ch = cum_ceil(a.kappa, P, u);
+                rc[m] = c;
+                s_col[m * 32 + lane] = c;
+                s_cum[m * 32 + lane] = P;
+                s_ch[m * 32 + lane] = (unsigned short)ch;
+                T = ch;
+            }
+        }
+    }
+    __syncwarp();
+    // ---------------- phase A
+    {
+        int m = 0, m_prev = -1;
+        uint32_t j = 0;
+        float pe = 0.0f;
+        float yj[DP];
+        Philox4 B;
+        for (int s = 0; s < T; s++) {
+            while ((int)s_ch[m * 32 + lane] <= s) m++;          // ch[k-1] == T > s
+            if (m != m_prev) {
+                j = s_col[m * 32 + lane];
+                const float P_hi = s_cum[m * 32 + lane];
+                const float P_lo = m ? s_cum[(m - 1) * 32 + lane] : 0.0f;
+                pe = P_hi - P_lo;
+                load_row<DP>(a.y_snap, j, yj);
+                m_prev = m;
+            }
+            const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
+            if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
+            auto rej = [&](uint32_t kk) -> bool {
+                bool r = (kk == node) | (kk == j);
+#pragma unroll
+                for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
+                return r;
+            };
+            uint32_t negs[ANNEMBED_NB_NEG];
+            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
+            apply_firing<DP>(a, node, y, yj, g, pe, inv_s2, negs);
+        }
+    }
+    // ---------------- phase B
+    const uint64_t my_q0 = valid ? a.in_ptr[node - a.lo] : 0, my_q1 = valid ? a.in_ptr[node - a.lo + 1] : 0;
+    const uint64_t Q0 = __shfl_sync(0xffffffffu, my_q0, 0);
+    const int last_lane = (int)min((uint64_t)31, (uint64_t)a.hi - n0 - 1);
+    const uint64_t Q1 = __shfl_sync(0xffffffffu, my_q1, last_lane);
+    const uint32_t my_lo = (uint32_t)(my_q0 - Q0), my_hi = (uint32_t)(my_q1 - Q0);
+    uint32_t qcount = 0;                                         // entries in the queue (warp uniform)
+    auto flush = [&]() {
+        __syncwarp();
+        // first queue entry of this owner: lower_bound of my_lo over the (ascending) q_rel tags
+        uint32_t lo_i = 0, hi_i = qcount;
+        while (lo_i < hi_i) { const uint32_t mid = (lo_i + hi_i) >> 1; if (s_qq[mid] < my_lo) lo_i = mid + 1; else hi_i = mid; }
+        for (uint32_t t = lo_i; t < qcount && s_qq[t] < my_hi; t++) {
+            float ys[DP];
+#pragma unroll
+            for (int c = 0; c < DP; c++) ys[c] = s_qy[t * DP + c];
+            const float pe = s_qp[t], is2 = s_qs[t];
+            const uint32_t cnt = s_qc[t];
+            for (uint32_t f = 0; f < cnt; f++) {
+#pragma unroll
+                for (int c = 0; c < DP; c++) g[c] = 0.0f;
+                attract<DP>(ys, y, g, pe, is2, a.K);
+            }
+        }
+        __syncwarp();
+        qcount = 0;
+    };
+    for (uint64_t qb = Q0; qb < Q1; qb += 32) {
+        const uint64_t q = qb + lane;
+        int c = 0;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (q < Q1) {
+            rec = __ldcs(a.in_rec + (q - a.in_base));
+            const float us = node_uniform(rec.x, a.epoch, a.k2);
+            c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
+        }
+        const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
+        if (c > 0) {
+            const uint32_t slot = qcount + __popc(fired & ((1u << lane) - 1u));
+            float ys[DP];
+            load_row<DP>(a.y_snap, rec.x, ys);
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) s_qy[slot * DP + cc] = ys[cc];
+            s_qp[slot] = as_float(rec.z) - as_float(rec.y);
+            s_qs[slot] = as_float(rec.w);
+            s_qq[slot] = (uint32_t)(q - Q0);
+            s_qc[slot] = (uint32_t)c;
+        }
+        qcount += __popc(fired);
+        if (qcount + 32 > EPOCH_QCAP) flush();
+    }
+    if (qcount) flush();
+    if (valid) store_row<DP>(a.y_next, node, y);
+    unsigned int applied = (unsigned int)T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) applied += __shfl_xor_sync(0xffffffffu, applied, o);
+    if (lane == 0 && applied) atomicAdd(sample_counter + (blockIdx.x & 255), (unsigned long long)applied);
 }
 
 // K5: embedder.rs:1127-1163 + cauchy_edge_weight :1322-1345, fp64 like the reference
@@ -402,17 +561,36 @@ __global__ void k_debug_draws(EpochArgs a, uint32_t *__restrict__ counts, uint32
     const uint64_t node = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= a.n) return;
     const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
+    const float u = node_uniform((uint32_t)node, a.epoch, a.k2);
+    int c_lo = 0;
     for (uint64_t m = r0; m < r1; m++) {
-        const uint32_t e = (uint32_t)m;
-        const Philox4 A = philox4x32_10(e, 0u, a.epoch, 0u, a.k0, a.k1);
-        const int c = firing_count(a.p[m], a.kappa, A.x);
+        const int c_hi = cum_ceil(a.kappa, a.cum[m], u);
+        const int c = c_hi - c_lo;
         counts[m] = (uint32_t)c;
         if (negs_out) {
             uint32_t negs[ANNEMBED_NB_NEG] = {ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE};
-            if (c > 0) draw_negatives<HUB>(a, e, 0u, A, (uint32_t)node, a.col[m], r0, r1, negs);
+            if (c > 0) {
+                const uint32_t s = (uint32_t)c_lo;              // the node's firing index at which this edge first fires
+                const Philox4 A = philox4x32_10((uint32_t)node, s, a.epoch, 1u, a.k0, a.k1);
+                const Philox4 B = philox4x32_10((uint32_t)node, s >> 2, a.epoch, 2u, a.k0, a.k1);
+                const GlobalRowRejector rej{a.col, r0, r1, (uint32_t)node, a.col[m]};
+                draw_negatives_v2<HUB>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
+            }
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) negs_out[5 * m + q] = negs[q];
         }
+        c_lo = c_hi;
     }
+}
+
+// inclusive cumulative edge probability along each row, clamped to 1 and exactly 1 on the last edge
+__global__ void k_row_cumsum(uint64_t n, const uint64_t *__restrict__ row_ptr, const float *__restrict__ p, float *__restrict__ cum)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    float acc = 0.0f;
+    for (uint64_t m = r0; m < r1; m++) { acc = __fadd_rn(acc, p[m]); cum[m] = fminf(acc, 1.0f); }
+    cum[r1 - 1] = 1.0f;
 }
 
 // =====================================================================================================
@@ -494,8 +672,12 @@ extern "C" int annembed_cuda_create(annembed_cuda_ctx **out, const annembed_cuda
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&ctx->l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    if (ctx->l2_persist_max > 0 && !(ctx->prm.flags & ANNEMBED_FLAG_NO_L2_PERSIST))
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ctx->l2_persist_max);
     if ((e = ctx->partials.alloc(4096)) != cudaSuccess) return fail("cudaMalloc", e);
-    if ((e = ctx->counter.alloc(1)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = ctx->counter.alloc(256)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = ctx->errword.alloc(2)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -722,7 +904,9 @@ static int ensure_build(annembed_cuda_ctx *ctx)
     REQUIRE(ctx->have_weights, ANNEMBED_ERR_STATE, "edge weights not computed (embedder.rs:802-808: initial_space not constructed)");
     const uint64_t n = ctx->n, E = ctx->E;
     CU(cudaEventRecord(ctx->ev_a, ctx->stream));
-    CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); CU(ctx->in_ptr_all.alloc(n + 2));
+    CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); CU(ctx->in_ptr_all.alloc(n + 2)); CU(ctx->cum.alloc(E));
+    k_row_cumsum<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr.p, ctx->proba.p, ctx->cum.p);
+    ctx->st.kernel_launches++;
     int rc;
     // K2
     if ((rc = sum_f64(ctx, ctx->scale.p, n, ctx->partials.p + 4095))) return rc;
@@ -749,7 +933,7 @@ static int ensure_build(annembed_cuda_ctx *ctx)
         const uint64_t cnt = qr[1] - qr[0];
         CU(ctx->in_rec.alloc(std::max<uint64_t>(cnt, 1)));
         if (cnt) {
-            k_in_rec<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, ctx->row_ptr.p, ctx->proba.p,
+            k_in_rec<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, ctx->row_ptr.p, ctx->cum.p,
                                                                  ctx->inv_s2.p, ctx->in_rec.p);
             ctx->st.kernel_launches++;
         }
@@ -834,14 +1018,15 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
     return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
 }
 
-// Mini-epochs per reference batch.  Default: about 3 own firings per node per mini-epoch
-// (nb_sampling_by_edge * mean degree / 3), where the bulk-synchronous layout statistics meet the serial
+#define ANNEMBED_FIRINGS_PER_MINI_EPOCH 2.5
+// Mini-epochs per reference batch.  Default: about 2.5 own firings per node per mini-epoch
+// (nb_sampling_by_edge * mean degree / 2.5), where the bulk-synchronous layout statistics meet the serial
 // reference's within 1 % (tests/studies/semantics_study.py).
 static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
 {
     if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;
     const double per_node = (double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)std::max<uint64_t>(ctx->n, 1));
-    return (uint32_t)std::max<double>((double)ctx->prm.nb_sampling_by_edge, std::ceil(per_node / 3.0));
+    return (uint32_t)std::max<double>(1.0, std::ceil(per_node / ANNEMBED_FIRINGS_PER_MINI_EPOCH));
 }
 
 static SgdConst make_const(const annembed_cuda_ctx *ctx, double grad_step)
@@ -896,6 +1081,8 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.row_ptr = ctx->row_ptr.p; a.col = ctx->col.p; a.p = ctx->proba.p; a.inv_s2 = ctx->inv_s2.p;
     a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
     a.neg_alias = ctx->neg_alias.p;
+    a.cum = ctx->cum.p;
+    a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);
     a.n = (uint32_t)ctx->n; a.lo = ctx->lo; a.hi = ctx->hi;
     a.epoch = epoch;
     a.k0 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu); a.k1 = (uint32_t)(ctx->prm.seed >> 32);
@@ -905,17 +1092,59 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     return a;
 }
 
-template <bool HUB>
-static void launch_epoch(annembed_cuda_ctx *ctx, const EpochArgs &a)
+// The gathers of the layout are the only reuse in the epoch kernel (7 random rows per sample); everything else
+// streams.  Pin the snapshot in L2 (persisting access-policy window) so that the streaming arrays do not evict it.
+static void set_l2_window(annembed_cuda_ctx *ctx, const void *ptr, size_t bytes)
 {
-    const unsigned int nb = nblocks(a.hi - a.lo, 256);
-    if (nb == 0) return;
+    if (ctx->l2_persist_max <= 0 || ctx->l2_window_max <= 0 || (ctx->prm.flags & ANNEMBED_FLAG_NO_L2_PERSIST)) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    const size_t win = std::min(bytes, (size_t)ctx->l2_window_max);
+    v.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+    v.accessPolicyWindow.num_bytes = win;
+    v.accessPolicyWindow.hitRatio = win ? (float)std::min(1.0, (double)ctx->l2_persist_max / (double)win) : 0.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
+template <int DP, bool HUB, int KREG>
+static cudaError_t launch_tiled(annembed_cuda_ctx *ctx, const EpochArgs &a)
+{
+    using TL = EpochTile<DP, KREG>;
+    static bool configured[64] = {false};
+    auto kern = k_epoch_tiled<DP, HUB, KREG>;
+    if (!configured[ctx->device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM);
+        if (e != cudaSuccess) return e;
+        configured[ctx->device & 63] = true;
+    }
+    const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;
+    const unsigned int nb = (unsigned int)((tiles + TL::WARPS - 1) / TL::WARPS);
+    kern<<<nb, TL::WARPS * 32, TL::SMEM, ctx->stream>>>(a, ctx->counter.p);
+    return cudaGetLastError();
+}
+
+template <int DP, bool HUB>
+static cudaError_t launch_epoch_dp(annembed_cuda_ctx *ctx, const EpochArgs &a)
+{
+    if (a.hi <= a.lo) return cudaSuccess;
+    const bool force_generic = (ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL) != 0;
+    if (!force_generic && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
+    if (!force_generic && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);
+    k_epoch_generic<DP, HUB><<<nblocks(a.hi - a.lo, 256), 256, 0, ctx->stream>>>(a, ctx->counter.p);
+    return cudaGetLastError();
+}
+
+template <bool HUB>
+static cudaError_t launch_epoch(annembed_cuda_ctx *ctx, const EpochArgs &a)
+{
     switch (ctx->DP) {
-    case 2: k_epoch<2, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
-    case 4: k_epoch<4, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
-    case 8: k_epoch<8, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
-    case 16: k_epoch<16, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
-    default: k_epoch<32, HUB><<<nb, 256, 0, ctx->stream>>>(a, ctx->counter.p); break;
+    case 2: return launch_epoch_dp<2, HUB>(ctx, a);
+    case 4: return launch_epoch_dp<4, HUB>(ctx, a);
+    case 8: return launch_epoch_dp<8, HUB>(ctx, a);
+    case 16: return launch_epoch_dp<16, HUB>(ctx, a);
+    default: return launch_epoch_dp<32, HUB>(ctx, a);
     }
 }
 
@@ -943,7 +1172,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     while (ctx->ev.size() < 2 * n_launch + 2 * n_launch * (ctx->nranks > 1)) {
         cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
     }
-    CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->counter.p, 0, 256 * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev_a, ctx->stream));
     size_t li = 0;
     const size_t xoff = 2 * n_launch;
@@ -951,8 +1180,9 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
         const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
         for (uint32_t m = 0; m < M; m++, li++) {
             const EpochArgs a = make_epoch_args(ctx, (iter - 1) * M + m, grad_step);
+            set_l2_window(ctx, a.y_snap, (size_t)ctx->n * ctx->DP * sizeof(float));
             CU(cudaEventRecord(ctx->ev[2 * li], ctx->stream));
-            if (hub) launch_epoch<true>(ctx, a); else launch_epoch<false>(ctx, a);
+            CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
             CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
             if (ctx->nranks > 1) {
                 // replicate the updated rows: in-place all-gather of the owned slice of y_next
@@ -966,10 +1196,13 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
             ctx->cur ^= 1;
         }
     }
+    set_l2_window(ctx, nullptr, 0);
     CU(cudaEventRecord(ctx->ev_b, ctx->stream));
-    unsigned long long cnt = 0;
-    CU(cudaMemcpyAsync(&cnt, ctx->counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long cnts[256];
+    CU(cudaMemcpyAsync(cnts, ctx->counter.p, sizeof(cnts), cudaMemcpyDeviceToHost, ctx->stream));
     if ((rc = sync_stream(ctx))) return rc;
+    unsigned long long cnt = 0;
+    for (int i = 0; i < 256; i++) cnt += cnts[i];
     float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
     double kms = 0, xms = 0;
     for (size_t i = 0; i < n_launch; i++) {
@@ -1073,6 +1306,7 @@ extern "C" int annembed_cuda_debug_draws(annembed_cuda_ctx *ctx, uint32_t epoch,
     DevBuf<uint32_t> dc, dn;
     CU(dc.alloc(ctx->E));
     if (neg_out) CU(dn.alloc(ctx->E * 5));
+    if ((rc = ensure_build(ctx))) return rc;
     EpochArgs a = make_epoch_args(ctx, epoch, 0.0);
     if (hub) k_debug_draws<true><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);
     else k_debug_draws<false><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);

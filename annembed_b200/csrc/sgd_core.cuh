@@ -325,15 +325,32 @@ __host__ __device__ __forceinline__ int cum_ceil(float kappa, float P, float u)
 
 // the 5 accepted negatives of firing s of `node` (v2 streams: counter (node, sub, epoch, tag))
 //   tag 1: sub = s          words x,y,z,w -> negatives 0..3
-//   tag 2: sub = s >> 2     word (s & 3)  -> negative 4
-//   tag 3: sub = s, tag 3 + t: accept words (hubness) ; tag 0x80000000|q<<8|t : redraws
-template <bool HUB>
-__host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t node, uint32_t s, uint32_t j,
-                                                           uint64_t r0, uint64_t r1, uint32_t (&negs)[ANNEMBED_NB_NEG])
+//   tag 2: sub = s >> 2     word (s & 3)  -> negative 4        (one call serves 4 consecutive firings)
+//   tag 3,4: sub = s        accept words of the hubness alias sampler
+//   tag 0x80000000|q<<8|t   redraw t of negative q after a rejection (embedder.rs:1246-1252)
+__host__ __device__ __forceinline__ uint32_t philox_word(const Philox4 &B, uint32_t i)
 {
-    const Philox4 A = philox4x32_10(node, s, a.epoch, 1u, a.k0, a.k1);
-    const Philox4 B = philox4x32_10(node, s >> 2, a.epoch, 2u, a.k0, a.k1);
-    const uint32_t w4 = (s & 2u) ? ((s & 1u) ? B.w : B.z) : ((s & 1u) ? B.y : B.x);
+    return (i & 2u) ? ((i & 1u) ? B.w : B.z) : ((i & 1u) ? B.y : B.x);
+}
+
+struct GlobalRowRejector {          // nodeparam.rs:83-85 linear scan of the origin's row in global memory
+    const uint32_t *__restrict__ col;
+    uint64_t r0, r1;
+    uint32_t node, j;
+    __host__ __device__ __forceinline__ bool operator()(uint32_t k) const
+    {
+        if (k == node || k == j) return true;
+        for (uint64_t m = r0; m < r1; m++)
+            if (col[m] == k) return true;
+        return false;
+    }
+};
+
+template <bool HUB, class Rej>
+__host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t node, uint32_t s, const Philox4 &A,
+                                                           uint32_t w4, const Rej &rejected,
+                                                           uint32_t (&negs)[ANNEMBED_NB_NEG])
+{
     uint32_t wi[ANNEMBED_NB_NEG] = {A.x, A.y, A.z, A.w, w4};
     uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
     if constexpr (HUB) {
@@ -344,13 +361,41 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
         uint32_t k = map_negative<HUB>(a, wi[q], wa[q]);
-        bool rej = negative_rejected(a, k, node, j, r0, r1);
+        bool rej = rejected(k);
         for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
             const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
             k = map_negative<HUB>(a, R.x, R.y);
-            rej = negative_rejected(a, k, node, j, r0, r1);
+            rej = rejected(k);
         }
         negs[q] = rej ? ANNEMBED_NO_NODE : k;
+    }
+}
+
+// one firing of `node` on edge (node -> j): attraction against the local copy of y_j, then 5 repulsions
+template <int DP>
+__host__ __device__ __forceinline__ void apply_firing(const EpochArgs &a, uint32_t node, float (&y)[DP], float (&yj)[DP],
+                                                      float (&g)[DP], float pe, float inv_s2,
+                                                      const uint32_t (&negs)[ANNEMBED_NB_NEG])
+{
+#pragma unroll
+    for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
+    if constexpr (DP <= 4) {
+        float yk[ANNEMBED_NB_NEG][DP];                  // issue the five gathers before the dependent arithmetic
+#pragma unroll
+        for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+            load_row<DP>(a.y_snap, negs[q] == ANNEMBED_NO_NODE ? node : negs[q], yk[q]);
+        attract<DP>(y, yj, g, pe, inv_s2, a.K);
+#pragma unroll
+        for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+            if (negs[q] != ANNEMBED_NO_NODE) repulse<DP>(y, yk[q], g, inv_s2, a.K);
+    } else {
+        attract<DP>(y, yj, g, pe, inv_s2, a.K);
+        for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+            if (negs[q] == ANNEMBED_NO_NODE) continue;
+            float yk[DP];
+            load_row<DP>(a.y_snap, negs[q], yk);
+            repulse<DP>(y, yk, g, inv_s2, a.K);
+        }
     }
 }
 
@@ -377,29 +422,13 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
         const uint32_t j = a.col[m];
         float yj[DP];
         load_row<DP>(a.y_snap, j, yj);
+        const GlobalRowRejector rej{a.col, r0, r1, node, j};
         for (int f = 0; f < c; f++, s++) {
+            const Philox4 A = philox4x32_10(node, s, a.epoch, 1u, a.k0, a.k1);
+            const Philox4 B = philox4x32_10(node, s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, node, s, j, r0, r1, negs);
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
-            if constexpr (DP <= 4) {
-                float yk[ANNEMBED_NB_NEG][DP];
-#pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
-                    load_row<DP>(a.y_snap, negs[q] == ANNEMBED_NO_NODE ? node : negs[q], yk[q]);
-                attract<DP>(y, yj, g, pe, inv_s2, a.K);
-#pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
-                    if (negs[q] != ANNEMBED_NO_NODE) repulse<DP>(y, yk[q], g, inv_s2, a.K);
-            } else {
-                attract<DP>(y, yj, g, pe, inv_s2, a.K);
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-                    if (negs[q] == ANNEMBED_NO_NODE) continue;
-                    float yk[DP];
-                    load_row<DP>(a.y_snap, negs[q], yk);
-                    repulse<DP>(y, yk, g, inv_s2, a.K);
-                }
-            }
+            draw_negatives_v2<HUB>(a, node, s, A, philox_word(B, s & 3u), rej, negs);
+            apply_firing<DP>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
     // phase B: in-edges in transposed-index order

@@ -57,13 +57,15 @@ typedef struct annembed_cuda_params {
     uint32_t hubness_weighting;    /* :102 default 0: negatives uniform; 1: alias over set_neg_weights */
     /* ---- device-side additions (no reference counterpart: its RNG is unseeded, embedder.rs:1182) ---- */
     uint32_t mini_epochs_per_batch;/* bulk-synchronous sub-steps per reference batch;
-                                      0 -> max(nb_sampling_by_edge, ceil(nb_sampling_by_edge * E/n / 3)) */
+                                      0 -> ceil(nb_sampling_by_edge * E/n / 2.5): ~2.5 firings per node per sub-step */
     uint64_t seed;                 /* Philox4x32-10 key */
     uint32_t flags;                /* ANNEMBED_FLAG_* */
     uint32_t reserved;
 } annembed_cuda_params;
 
 #define ANNEMBED_FLAG_NONE 0u
+#define ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL 1u   /* force the thread-per-node epoch kernel (cross-check of the tiled one) */
+#define ANNEMBED_FLAG_NO_L2_PERSIST 2u            /* do not pin the layout snapshot in L2 (A/B measurements) */
 
 typedef struct annembed_cuda_stats {
     double   edge_weights_ms;      /* K0+K1 device time, last call */

@@ -26,7 +26,7 @@ struct HostCtx {
     std::vector<float> inv_s2;
     std::vector<float> cum;
 };
-static int g_version = 1;
+static int g_version = 2;   // 2 = the product's systematic sampler; 1 = first design (per-edge counts), kept for studies
 extern "C" void hostsim_set_version(int v) { g_version = v; }
 extern "C" void hostsim_philox2(const uint32_t ctr[2], uint32_t key, uint32_t out[2])
 {
@@ -117,31 +117,45 @@ extern "C" int64_t hostsim_optimize(uint64_t n, uint32_t d, const uint64_t *row_
     return total;
 }
 
-// the draws of one mini-epoch (same contract as annembed_cuda_debug_draws)
+// the draws of one mini-epoch (same contract as annembed_cuda_debug_draws; v2 sampler)
 extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *p, uint32_t nbs,
                               uint32_t M, uint64_t seed, uint32_t epoch, const uint32_t *neg_alias, uint32_t *counts,
                               uint32_t *negs_out)
 {
     const uint64_t E = row_ptr[n];
+    std::vector<float> cum(E);
+    for (uint64_t i = 0; i < n; i++) {
+        float acc = 0.0f;
+        for (uint64_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) { acc += p[e]; cum[e] = acc < 1.0f ? acc : 1.0f; }
+        cum[row_ptr[i + 1] - 1] = 1.0f;
+    }
     EpochArgs a;
     memset(&a, 0, sizeof a);
-    a.row_ptr = row_ptr; a.col = col; a.p = p; a.neg_alias = (const uint2 *)neg_alias;
+    a.row_ptr = row_ptr; a.col = col; a.p = p; a.neg_alias = (const uint2 *)neg_alias; a.cum = cum.data();
     a.n = (uint32_t)n; a.epoch = epoch; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
     a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
     for (uint64_t node = 0; node < n; node++) {
         const uint64_t r0 = row_ptr[node], r1 = row_ptr[node + 1];
+        const float u = node_uniform((uint32_t)node, epoch, a.k2);
+        int c_lo = 0;
         for (uint64_t m = r0; m < r1; m++) {
-            const Philox4 A = philox4x32_10((uint32_t)m, 0u, epoch, 0u, a.k0, a.k1);
-            const int c = firing_count(p[m], a.kappa, A.x);
+            const int c_hi = cum_ceil(a.kappa, cum[m], u);
+            const int c = c_hi - c_lo;
             counts[m] = (uint32_t)c;
             if (negs_out) {
                 uint32_t negs[5] = {ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE};
                 if (c > 0) {
-                    if (neg_alias) draw_negatives<true>(a, (uint32_t)m, 0u, A, (uint32_t)node, col[m], r0, r1, negs);
-                    else draw_negatives<false>(a, (uint32_t)m, 0u, A, (uint32_t)node, col[m], r0, r1, negs);
+                    const uint32_t s = (uint32_t)c_lo;
+                    const Philox4 A = philox4x32_10((uint32_t)node, s, epoch, 1u, a.k0, a.k1);
+                    const Philox4 B = philox4x32_10((uint32_t)node, s >> 2, epoch, 2u, a.k0, a.k1);
+                    const GlobalRowRejector rej{col, r0, r1, (uint32_t)node, col[m]};
+                    if (neg_alias) draw_negatives_v2<true>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
+                    else draw_negatives_v2<false>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
                 }
                 for (int q = 0; q < 5; q++) negs_out[5 * m + q] = negs[q];
             }
+            c_lo = c_hi;
         }
     }
 }

@@ -231,6 +231,40 @@ def test_epoch_kernel_matches_host_replay(d, hub):
     assert np.quantile(err2, 0.99) < 1e-3, (np.quantile(err2, 0.99), err2.max())
 
 
+@pytest.mark.parametrize("d,kmax,hub", [(2, 6, False), (2, 14, True), (3, 8, False), (15, 10, False), (32, 5, False)])
+def test_tiled_epoch_kernel_equals_generic_kernel(d, kmax, hub):
+    """The warp-tiled K4 and the thread-per-node K4 run the same per-node program (same draws, same order)."""
+    row_ptr, col, dist = random_graph(5000, 2, kmax, seed=72)
+    y0 = np.random.default_rng(2).uniform(-1, 1, size=(5000, d)).astype(np.float32)
+    outs = []
+    for flags in (0, 1):                             # 1 = ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL
+        ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=3, grad_step=1.0, seed=5, flags=flags,
+                      hubness_weighting=hub, mini_epochs_per_batch=4)
+        ctx.edge_weights(want_outputs=False)
+        if hub:
+            ctx.set_neg_weights(oracle.hubness_weights(row_ptr, col))
+        ctx.set_embedding(y0)
+        ctx.optimize_batches(1, 1)
+        outs.append((ctx.get_embedding(), ctx.get_stats()["positive_samples"]))
+    assert outs[0][1] == outs[1][1]
+    err = np.abs(outs[0][0] - outs[1][0]).max(axis=1)
+    assert np.quantile(err, 0.999) < 1e-4, (np.quantile(err, 0.999), err.max())
+
+
+def test_rows_longer_than_16_use_the_generic_kernel():
+    row_ptr, col, dist = random_graph(3000, 17, 40, seed=73)
+    ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=3, grad_step=1.0)
+    scale, p = ctx.edge_weights()
+    es = ctx.get_embedded_scales()
+    y0 = np.random.default_rng(2).uniform(-1, 1, size=(3000, 2)).astype(np.float32)
+    ctx.set_embedding(y0)
+    ctx.optimize_batches(1, 1)
+    st = ctx.get_stats()
+    M = st["mini_epochs_per_batch"]
+    y_host, done = hs.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, 10, 3, M, 0x5EED, None, 1, 1)
+    assert st["positive_samples"] == done and np.isfinite(ctx.get_embedding()).all()
+
+
 def test_optimize_is_deterministic_and_schedule_matches_reference():
     row_ptr, col, dist = random_graph(3000, 5, 9, seed=81)
     kw = dict(nb_grad_batch=5, grad_step=1.0, seed=7)

@@ -81,7 +81,9 @@ def test_sampler_expectation_and_rejection():
     for epoch in range(200):
         c, negs = hs.draws(row_ptr, col, p, nbs, M, seed=9, epoch=epoch)
         tot += c
-        assert np.all(np.abs(c.astype(np.float64) - kappa * p) < 1.0)       # floor(lambda + u)
+        assert np.all(np.abs(c.astype(np.float64) - kappa * p) < 1.0 + 1e-4)   # systematic sampling: floor or ceil
+        per_node = np.add.reduceat(c.astype(np.int64), row_ptr[:-1].astype(np.int64))
+        assert set(np.unique(per_node)) <= {int(np.floor(kappa)), int(np.ceil(kappa))}    # every node: ceil(kappa - u)
         fired = c > 0
         assert np.all(negs[~fired] == 0xFFFFFFFF)
         ng = negs[fired]

@@ -5,7 +5,7 @@ set -x
 TAG=${1:-r01}
 NODES=${2:-11000000}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|DeviceRadixSort|Onesweep' -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --nodes $NODES --steps 1 --warmup 0 --batches 4 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_epoch -s 10 -c 2 -f -o gpurun_out/k4_${TAG} \
     python bench.py --nodes $NODES --steps 1 --warmup 0 --batches 2 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu_full_${TAG}.log 2>&1
