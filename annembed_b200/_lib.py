@@ -31,7 +31,7 @@ class Stats(C.Structure):
         ("epoch_kernel_ms", C.c_double), ("exchange_ms", C.c_double), ("cross_entropy_ms", C.c_double),
         ("epoch_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("positive_samples", C.c_uint64),
         ("edge_updates", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("model_bytes", C.c_double),
-        ("mini_epochs_per_batch", C.c_uint64),
+        ("mini_epochs_per_batch", C.c_uint64), ("l2_persist_max_bytes", C.c_uint64), ("l2_window_max_bytes", C.c_uint64),
     ]
 
     def as_dict(self):

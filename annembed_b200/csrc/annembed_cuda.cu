@@ -75,7 +75,7 @@ struct annembed_cuda_ctx {
 
     // graph (replicated on every rank)
     uint64_t n = 0, E = 0;
-    uint32_t kmax = 0;
+    uint32_t kmax = 0, kmin = 0;
     DevBuf<uint64_t> row_ptr;
     DevBuf<uint32_t> col;
     DevBuf<float> dist, rho;
@@ -129,7 +129,7 @@ enum { GERR_EMPTY = 1, GERR_COL = 2, GERR_SELF = 3, GERR_UNSORTED = 4, GERR_ROWP
 
 __global__ void k_validate_graph(uint64_t n, uint64_t E, const uint64_t *__restrict__ row_ptr,
                                  const uint32_t *__restrict__ col, const float *__restrict__ dist,
-                                 unsigned long long *err, unsigned int *kmax)
+                                 unsigned long long *err, unsigned int *kmax, unsigned int *kmin)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -149,6 +149,7 @@ __global__ void k_validate_graph(uint64_t n, uint64_t E, const uint64_t *__restr
             prev = d;
         }
         atomicMax(kmax, (unsigned int)(r1 - r0));
+        atomicMin(kmin, (unsigned int)(r1 - r0));
     }
     if (code) atomicMin(err, ((unsigned long long)i << 4) | code);
 }
@@ -377,61 +378,82 @@ constexpr int EPOCH_QCAP = 128;                 // queue entries per warp
 template <int DP, int KREG>
 struct EpochTile {
     static constexpr int WARPS = DP <= 4 ? 8 : (DP <= 16 ? 4 : 2);
-    static constexpr int ROW_BYTES = 32 * KREG * (4 + 4 + 2);                   // col, cum, ceil counts (u16)
-    static constexpr int QUEUE_BYTES = EPOCH_QCAP * (4 * DP + 4 + 4 + 4 + 4);   // y_src, p, inv_s2, q_rel, count
-    static constexpr int PER_WARP = ROW_BYTES + QUEUE_BYTES;
+    static constexpr int MINB = DP <= 2 ? 4 : (DP <= 4 ? 3 : (DP <= 8 ? 2 : 1));   // blocks/SM the register budget aims at
+    static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
+    static constexpr int QF = DP == 2 ? 4 : DP + 4;                              // floats per queue entry: y_src, p, 1/s^2 (16-byte rows)
+    static constexpr int QUEUE_BYTES = EPOCH_QCAP * (4 * QF + 4);                // + firing count
+    static constexpr int ROW_BYTES = 32 * RS * (4 + 4 + 2) + 32 * 4;             // col, cum, ceil counts (u16), + slack
+    static constexpr int PER_WARP = ((QUEUE_BYTES + ROW_BYTES + 15) / 16) * 16;
     static constexpr int SMEM = WARPS * PER_WARP;
 };
 
 template <int DP, bool HUB, int KREG>
-__global__ void __launch_bounds__(EpochTile<DP, KREG>::WARPS * 32)
+__global__ void __launch_bounds__(EpochTile<DP, KREG>::WARPS * 32, EpochTile<DP, KREG>::MINB)
 k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
 {
     using TL = EpochTile<DP, KREG>;
+    constexpr int RS = TL::RS, QF = TL::QF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t tile = (uint64_t)blockIdx.x * TL::WARPS + wib;
     const uint64_t n0 = (uint64_t)a.lo + tile * 32;
     if (n0 >= a.hi) return;                                    // whole warp leaves together
     unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
-    float *s_qy = reinterpret_cast<float *>(base);                              // [QCAP][DP]   (16-byte aligned first)
-    uint32_t *s_col = reinterpret_cast<uint32_t *>(base + EPOCH_QCAP * 4 * DP); // [KREG][32]
-    float *s_cum = reinterpret_cast<float *>(s_col + 32 * KREG);                // [KREG][32]
-    float *s_qp = s_cum + 32 * KREG;                                            // [QCAP]
-    float *s_qs = s_qp + EPOCH_QCAP;                                            // [QCAP]
-    uint32_t *s_qq = reinterpret_cast<uint32_t *>(s_qs + EPOCH_QCAP);           // [QCAP]
-    uint32_t *s_qc = s_qq + EPOCH_QCAP;                                         // [QCAP]
-    unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_qc + EPOCH_QCAP); // [KREG][32]
+    float *s_q = reinterpret_cast<float *>(base);                               // [QCAP][QF]  (16-byte aligned)
+    uint32_t *s_qc = reinterpret_cast<uint32_t *>(s_q + EPOCH_QCAP * QF);       // [QCAP]
+    uint32_t *s_col = s_qc + EPOCH_QCAP;                                        // [32][RS]
+    float *s_cum = reinterpret_cast<float *>(s_col + 32 * RS);                  // [32][RS]
+    unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_cum + 32 * RS); // [32][RS]
 
+    const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
     const uint32_t node = (uint32_t)n0 + lane;
-    const bool valid = node < a.hi;
+    const bool valid = lane < nvalid;
     float y[DP], g[DP];
     uint32_t rc[KREG];
     float inv_s2 = 1.0f;
     int T = 0;
-#pragma unroll
-    for (int m = 0; m < KREG; m++) rc[m] = ANNEMBED_NO_NODE;
-    if (valid) {
-        load_row<DP>(a.y_snap, node, y);
-        inv_s2 = a.inv_s2[node];
-        const uint64_t r0 = a.row_ptr[node];
-        const int k = (int)(a.row_ptr[node + 1] - r0);
-        const float u = node_uniform(node, a.epoch, a.k2);
-#pragma unroll
-        for (int m = 0; m < KREG; m++) {
-            if (m < k) {
-                const uint32_t c = __ldcs(a.col + r0 + m);
-                const float P = __ldcs(a.cum + r0 + m);
-                const int ch = cum_ceil(a.kappa, P, u);
-                rc[m] = c;
-                s_col[m * 32 + lane] = c;
-                s_cum[m * 32 + lane] = P;
-                s_ch[m * 32 + lane] = (unsigned short)ch;
-                T = ch;
+    // ---------------- stage the tile's rows: coalesced global reads, [lane][m] layout with odd stride in smem
+    {
+        uint64_t rp = a.row_ptr[valid ? node : (uint32_t)n0];
+        uint64_t rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+        if (lane == nvalid - 1) rp_next = a.row_ptr[node + 1];
+        const uint64_t R0 = __shfl_sync(0xffffffffu, rp, 0);
+        const uint64_t R1 = __shfl_sync(0xffffffffu, rp_next, nvalid - 1);
+        const int k = valid ? (int)(rp_next - rp) : 0;
+        const uint32_t tile_edges = (uint32_t)(R1 - R0);
+        if (a.regular_k) {
+            // every row has exactly regular_k entries: edge e of the tile belongs to lane e / k
+            const uint32_t kk = a.regular_k, inv_k = (65536u + kk - 1u) / kk;
+            for (uint32_t e = lane; e < tile_edges; e += 32) {
+                const uint32_t nl = (e * inv_k) >> 16, m = e - nl * kk;
+                s_col[nl * RS + m] = __ldcs(a.col + R0 + e);
+                s_cum[nl * RS + m] = __ldcs(a.cum + R0 + e);
+            }
+        } else {
+            for (int m = 0; m < k; m++) {
+                s_col[lane * RS + m] = a.col[rp + m];
+                s_cum[lane * RS + m] = a.cum[rp + m];
             }
         }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < KREG; m++) rc[m] = ANNEMBED_NO_NODE;
+        if (valid) {
+            load_row<DP>(a.y_snap, node, y);
+            inv_s2 = __ldcs(a.inv_s2 + node);
+            const float u = node_uniform(node, a.epoch, a.k2);
+#pragma unroll
+            for (int m = 0; m < KREG; m++) {
+                if (m < k) {
+                    rc[m] = s_col[lane * RS + m];
+                    const int ch = cum_ceil(a.kappa, s_cum[lane * RS + m], u);
+                    s_ch[lane * RS + m] = (unsigned short)ch;
+                    T = ch;
+                }
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     // ---------------- phase A
     {
         int m = 0, m_prev = -1;
@@ -440,11 +462,11 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
         float yj[DP];
         Philox4 B;
         for (int s = 0; s < T; s++) {
-            while ((int)s_ch[m * 32 + lane] <= s) m++;          // ch[k-1] == T > s
+            while ((int)s_ch[lane * RS + m] <= s) m++;          // ch[k-1] == T > s
             if (m != m_prev) {
-                j = s_col[m * 32 + lane];
-                const float P_hi = s_cum[m * 32 + lane];
-                const float P_lo = m ? s_cum[(m - 1) * 32 + lane] : 0.0f;
+                j = s_col[lane * RS + m];
+                const float P_hi = s_cum[lane * RS + m];
+                const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
                 pe = P_hi - P_lo;
                 load_row<DP>(a.y_snap, j, yj);
                 m_prev = m;
@@ -463,38 +485,53 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
         }
     }
     // ---------------- phase B
-    const uint64_t my_q0 = valid ? a.in_ptr[node - a.lo] : 0, my_q1 = valid ? a.in_ptr[node - a.lo + 1] : 0;
+    uint64_t my_q0 = a.in_ptr[(valid ? node : (uint32_t)n0) - a.lo];
+    uint64_t my_q1 = __shfl_down_sync(0xffffffffu, my_q0, 1);
+    if (lane == nvalid - 1) my_q1 = a.in_ptr[node - a.lo + 1];
     const uint64_t Q0 = __shfl_sync(0xffffffffu, my_q0, 0);
-    const int last_lane = (int)min((uint64_t)31, (uint64_t)a.hi - n0 - 1);
-    const uint64_t Q1 = __shfl_sync(0xffffffffu, my_q1, last_lane);
-    const uint32_t my_lo = (uint32_t)(my_q0 - Q0), my_hi = (uint32_t)(my_q1 - Q0);
-    uint32_t qcount = 0;                                         // entries in the queue (warp uniform)
+    const uint64_t Q1 = __shfl_sync(0xffffffffu, my_q1, nvalid - 1);
+    // this owner's in-edge positions relative to the sweep cursor (advanced by 32 per round)
+    int rel_lo = valid ? (int)(my_q0 - Q0) : 0x3fffffff, rel_hi = valid ? (int)(my_q1 - Q0) : 0x3fffffff;
+    uint32_t qcount = 0, seg_start = 0, seg_cnt = 0;           // queue fill (warp uniform); this owner's entries in it
     auto flush = [&]() {
         __syncwarp();
-        // first queue entry of this owner: lower_bound of my_lo over the (ascending) q_rel tags
-        uint32_t lo_i = 0, hi_i = qcount;
-        while (lo_i < hi_i) { const uint32_t mid = (lo_i + hi_i) >> 1; if (s_qq[mid] < my_lo) lo_i = mid + 1; else hi_i = mid; }
-        for (uint32_t t = lo_i; t < qcount && s_qq[t] < my_hi; t++) {
+        for (uint32_t t = seg_start, te = seg_start + seg_cnt; t < te; t++) {
             float ys[DP];
+            if constexpr (DP == 2) {
+                const float4 e4 = *reinterpret_cast<const float4 *>(s_q + t * QF);
+                ys[0] = e4.x; ys[1] = e4.y;
+                uint32_t cnt = s_qc[t];
+                do {
 #pragma unroll
-            for (int c = 0; c < DP; c++) ys[c] = s_qy[t * DP + c];
-            const float pe = s_qp[t], is2 = s_qs[t];
-            const uint32_t cnt = s_qc[t];
-            for (uint32_t f = 0; f < cnt; f++) {
+                    for (int c = 0; c < DP; c++) g[c] = 0.0f;
+                    attract<DP>(ys, y, g, e4.z, e4.w, a.K);
+                } while (--cnt);
+            } else {
 #pragma unroll
-                for (int c = 0; c < DP; c++) g[c] = 0.0f;
-                attract<DP>(ys, y, g, pe, is2, a.K);
+                for (int c = 0; c < DP; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(s_q + t * QF + c);   // QF*4 bytes: 8-byte aligned rows
+                    ys[c] = v.x; ys[c + 1] = v.y; ys[c + 2] = v.z; ys[c + 3] = v.w;
+                }
+                const float pe = s_q[t * QF + DP], is2 = s_q[t * QF + DP + 1];
+                uint32_t cnt = s_qc[t];
+                do {
+#pragma unroll
+                    for (int c = 0; c < DP; c++) g[c] = 0.0f;
+                    attract<DP>(ys, y, g, pe, is2, a.K);
+                } while (--cnt);
             }
         }
         __syncwarp();
-        qcount = 0;
+        qcount = 0; seg_cnt = 0;
     };
+    uint4 rec_next = make_uint4(0, 0, 0, 0);
+    if (Q0 + lane < Q1) rec_next = __ldcs(a.in_rec + (Q0 + lane - a.in_base));
     for (uint64_t qb = Q0; qb < Q1; qb += 32) {
-        const uint64_t q = qb + lane;
+        const uint4 rec = rec_next;
+        const bool have = qb + lane < Q1;
+        if (qb + 32 + lane < Q1) rec_next = __ldcs(a.in_rec + (qb + 32 + lane - a.in_base));   // prefetch the next round
         int c = 0;
-        uint4 rec = make_uint4(0, 0, 0, 0);
-        if (q < Q1) {
-            rec = __ldcs(a.in_rec + (q - a.in_base));
+        if (have) {
             const float us = node_uniform(rec.x, a.epoch, a.k2);
             c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
         }
@@ -503,12 +540,29 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
             const uint32_t slot = qcount + __popc(fired & ((1u << lane) - 1u));
             float ys[DP];
             load_row<DP>(a.y_snap, rec.x, ys);
+            if constexpr (DP == 2) {
+                *reinterpret_cast<float4 *>(s_q + slot * QF) =
+                    make_float4(ys[0], ys[1], as_float(rec.z) - as_float(rec.y), as_float(rec.w));
+            } else {
 #pragma unroll
-            for (int cc = 0; cc < DP; cc++) s_qy[slot * DP + cc] = ys[cc];
-            s_qp[slot] = as_float(rec.z) - as_float(rec.y);
-            s_qs[slot] = as_float(rec.w);
-            s_qq[slot] = (uint32_t)(q - Q0);
+                for (int cc = 0; cc < DP; cc++) s_q[slot * QF + cc] = ys[cc];
+                s_q[slot * QF + DP] = as_float(rec.z) - as_float(rec.y);
+                s_q[slot * QF + DP + 1] = as_float(rec.w);
+            }
             s_qc[slot] = (uint32_t)c;
+        }
+        // which of this round's fired lanes belong to this owner (in-edges are sorted by destination)
+        {
+            const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));
+            if (hi_c > lo_c) {
+                const unsigned range = (0xffffffffu >> (32 - (hi_c - lo_c))) << lo_c;
+                const uint32_t mine = __popc(fired & range);
+                if (mine) {
+                    if (seg_cnt == 0) seg_start = qcount + __popc(fired & ((1u << lo_c) - 1u));
+                    seg_cnt += mine;
+                }
+            }
+            rel_lo -= 32; rel_hi -= 32;
         }
         qcount += __popc(fired);
         if (qcount + 32 > EPOCH_QCAP) flush();
@@ -757,10 +811,10 @@ extern "C" int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, c
     if ((rc = h2d(ctx, ctx->col.p, col, E * sizeof(uint32_t)))) return rc;
     if ((rc = h2d(ctx, ctx->dist.p, dist, E * sizeof(float)))) return rc;
     // validate on the device
-    unsigned long long init[2] = {~0ull, 0ull};
+    unsigned long long init[2] = {~0ull, 0xFFFFFFFF00000000ull};   // error word; {kmax (low), kmin (high)}
     CU(cudaMemcpyAsync(ctx->errword.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     k_validate_graph<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, E, ctx->row_ptr.p, ctx->col.p, ctx->dist.p, ctx->errword.p,
-                                                               (unsigned int *)(ctx->errword.p + 1));
+                                                               (unsigned int *)(ctx->errword.p + 1), (unsigned int *)(ctx->errword.p + 1) + 1);
     ctx->st.kernel_launches++;
     unsigned long long res[2];
     CU(cudaMemcpyAsync(res, ctx->errword.p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
@@ -780,6 +834,7 @@ extern "C" int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, c
         return ANNEMBED_ERR_INVALID_ARG;
     }
     ctx->kmax = (uint32_t)(res[1] & 0xFFFFFFFFu);
+    ctx->kmin = (uint32_t)(res[1] >> 32);
     if (n < (uint64_t)ctx->kmax + 3) {
         ctx->err = "graph too small: no node acceptable as negative sample (embedder.rs:1241-1252 would not terminate)";
         return ANNEMBED_ERR_NO_NEGATIVE;
@@ -1018,9 +1073,9 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
     return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
 }
 
-#define ANNEMBED_FIRINGS_PER_MINI_EPOCH 2.5
-// Mini-epochs per reference batch.  Default: about 2.5 own firings per node per mini-epoch
-// (nb_sampling_by_edge * mean degree / 2.5), where the bulk-synchronous layout statistics meet the serial
+#define ANNEMBED_FIRINGS_PER_MINI_EPOCH 2.0
+// Mini-epochs per reference batch.  Default: about 2 own firings per node per mini-epoch
+// (nb_sampling_by_edge * mean degree / 2), where the bulk-synchronous layout statistics meet the serial
 // reference's within 1 % (tests/studies/semantics_study.py).
 static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
 {
@@ -1082,6 +1137,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
+    a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;
     a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);
     a.n = (uint32_t)ctx->n; a.lo = ctx->lo; a.hi = ctx->hi;
     a.epoch = epoch;
@@ -1117,6 +1173,7 @@ static cudaError_t launch_tiled(annembed_cuda_ctx *ctx, const EpochArgs &a)
     if (!configured[ctx->device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[ctx->device & 63] = true;
     }
     const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;
@@ -1285,6 +1342,8 @@ extern "C" int annembed_cuda_get_stats(annembed_cuda_ctx *ctx, annembed_cuda_sta
     if (!ctx || !stats) return ANNEMBED_ERR_INVALID_ARG;
     *stats = ctx->st;
     stats->mini_epochs_per_batch = ctx->have_graph ? eff_mini_epochs(ctx) : ctx->prm.mini_epochs_per_batch;
+    stats->l2_persist_max_bytes = (uint64_t)std::max(ctx->l2_persist_max, 0);
+    stats->l2_window_max_bytes = (uint64_t)std::max(ctx->l2_window_max, 0);
     return ANNEMBED_OK;
 }
 extern "C" int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx)

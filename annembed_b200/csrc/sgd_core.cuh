@@ -171,6 +171,7 @@ struct EpochArgs {
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
     const float *__restrict__ cum;       // v2: inclusive cumulative probability along each row (last entry exactly 1)
     uint32_t k2;                         // v2: Philox2x32 key of the per-node uniform
+    uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
     uint32_t n, lo, hi;
     uint32_t epoch, k0, k1;
     float kappa;                        // expected firings of edge e in this mini-epoch = kappa * p_e

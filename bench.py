@@ -292,6 +292,7 @@ def run_ours(a):
             "ms_per_step": 1e3 * elapsed_max / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "mini_epochs_per_batch": int(mini),
+                       "l2_persist_max_bytes": int(st["l2_persist_max_bytes"]), "l2_window_max_bytes": int(st["l2_window_max_bytes"]),
                        "l2": "inputs larger than L2 (graph + transposed index > 2 GB per pass); no flush needed",
                        "parallelism": f"node-sharded x{world}, replicated layout, all-gather per mini-epoch" if world > 1 else "single GPU",
                        "positive_samples_per_step": samples / a.steps, "input_build_s": t_in,
