@@ -86,6 +86,7 @@ struct annembed_cuda_ctx {
     DevBuf<float> emb_scale, inv_s2;
     DevBuf<uint64_t> in_ptr_all;   // n+1, transposed index of the whole graph
     DevBuf<uint4> in_rec;          // in-edge records of the owned slice
+    DevBuf<uint8_t> in_own;        // owner lane of each record in its warp tile
     uint64_t in_base = 0;
     DevBuf<uint2> neg_alias;
     DevBuf<float> y[2], y0;
@@ -302,8 +303,9 @@ __global__ void k_in_ptr(uint64_t E, uint64_t n, const uint32_t *__restrict__ so
 }
 
 __global__ void k_in_rec(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_t *__restrict__ sorted_eid,
-                         const uint64_t *__restrict__ row_ptr, const float *__restrict__ cum,
-                         const float *__restrict__ inv_s2, uint4 *__restrict__ rec)
+                         const uint32_t *__restrict__ sorted_dst, uint32_t lo, const uint64_t *__restrict__ row_ptr,
+                         const float *__restrict__ cum, const float *__restrict__ inv_s2, uint4 *__restrict__ rec,
+                         uint8_t *__restrict__ own)
 {
     const uint64_t q = q_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= q_hi) return;
@@ -312,6 +314,7 @@ __global__ void k_in_rec(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_
     while (b - a > 1) { const uint64_t mid = (a + b) >> 1; if (row_ptr[mid] <= e) a = mid; else b = mid; }
     const float P_lo = (row_ptr[a] == e) ? 0.0f : cum[e - 1];
     rec[q - q_lo] = make_uint4((uint32_t)a, __float_as_uint(P_lo), __float_as_uint(cum[e]), __float_as_uint(inv_s2[a]));
+    own[q - q_lo] = (uint8_t)((sorted_dst[q] - lo) & 31u);
 }
 
 __global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint32_t *__restrict__ out)
@@ -378,10 +381,10 @@ constexpr int EPOCH_QCAP = 128;                 // queue entries per warp
 template <int DP, int KREG>
 struct EpochTile {
     static constexpr int WARPS = DP <= 4 ? 8 : (DP <= 16 ? 4 : 2);
-    static constexpr int MINB = DP <= 2 ? 4 : (DP <= 4 ? 3 : (DP <= 8 ? 2 : 1));   // blocks/SM the register budget aims at
+    static constexpr int MINB = DP <= 4 ? 3 : (DP <= 8 ? 2 : 1);                  // blocks/SM the register budget aims at
     static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
-    static constexpr int QF = DP == 2 ? 4 : DP + 4;                              // floats per queue entry: y_src, p, 1/s^2 (16-byte rows)
-    static constexpr int QUEUE_BYTES = EPOCH_QCAP * (4 * QF + 4);                // + firing count
+    static constexpr int QF = DP == 2 ? 4 : DP + 4;                              // floats per queue entry: y_src, factor A (16-byte rows)
+    static constexpr int QUEUE_BYTES = EPOCH_QCAP * 4 * QF + 32 * 4 * DP;        // + the tile's positions after phase A
     static constexpr int ROW_BYTES = 32 * RS * (4 + 4 + 2) + 32 * 4;             // col, cum, ceil counts (u16), + slack
     static constexpr int PER_WARP = ((QUEUE_BYTES + ROW_BYTES + 15) / 16) * 16;
     static constexpr int SMEM = WARPS * PER_WARP;
@@ -400,8 +403,8 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
     if (n0 >= a.hi) return;                                    // whole warp leaves together
     unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
     float *s_q = reinterpret_cast<float *>(base);                               // [QCAP][QF]  (16-byte aligned)
-    uint32_t *s_qc = reinterpret_cast<uint32_t *>(s_q + EPOCH_QCAP * QF);       // [QCAP]
-    uint32_t *s_col = s_qc + EPOCH_QCAP;                                        // [32][RS]
+    float *s_yref = s_q + EPOCH_QCAP * QF;                                      // [32][DP]
+    uint32_t *s_col = reinterpret_cast<uint32_t *>(s_yref + 32 * DP);           // [32][RS]
     float *s_cum = reinterpret_cast<float *>(s_col + 32 * RS);                  // [32][RS]
     unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_cum + 32 * RS); // [32][RS]
 
@@ -485,6 +488,10 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
         }
     }
     // ---------------- phase B
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < DP; c++) s_yref[lane * DP + c] = y[c];
+    }
     uint64_t my_q0 = a.in_ptr[(valid ? node : (uint32_t)n0) - a.lo];
     uint64_t my_q1 = __shfl_down_sync(0xffffffffu, my_q0, 1);
     if (lane == nvalid - 1) my_q1 = a.in_ptr[node - a.lo + 1];
@@ -497,39 +504,38 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
         __syncwarp();
         for (uint32_t t = seg_start, te = seg_start + seg_cnt; t < te; t++) {
             float ys[DP];
+            float A;
             if constexpr (DP == 2) {
                 const float4 e4 = *reinterpret_cast<const float4 *>(s_q + t * QF);
-                ys[0] = e4.x; ys[1] = e4.y;
-                uint32_t cnt = s_qc[t];
-                do {
-#pragma unroll
-                    for (int c = 0; c < DP; c++) g[c] = 0.0f;
-                    attract<DP>(ys, y, g, e4.z, e4.w, a.K);
-                } while (--cnt);
+                ys[0] = e4.x; ys[1] = e4.y; A = e4.z;
             } else {
 #pragma unroll
                 for (int c = 0; c < DP; c += 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(s_q + t * QF + c);   // QF*4 bytes: 8-byte aligned rows
+                    const float4 v = *reinterpret_cast<const float4 *>(s_q + t * QF + c);
                     ys[c] = v.x; ys[c + 1] = v.y; ys[c + 2] = v.z; ys[c + 3] = v.w;
                 }
-                const float pe = s_q[t * QF + DP], is2 = s_q[t * QF + DP + 1];
-                uint32_t cnt = s_qc[t];
-                do {
-#pragma unroll
-                    for (int c = 0; c < DP; c++) g[c] = 0.0f;
-                    attract<DP>(ys, y, g, pe, is2, a.K);
-                } while (--cnt);
+                A = s_q[t * QF + DP];
             }
+            apply_in_edge<DP>(y, ys, A);
         }
         __syncwarp();
         qcount = 0; seg_cnt = 0;
     };
     uint4 rec_next = make_uint4(0, 0, 0, 0);
-    if (Q0 + lane < Q1) rec_next = __ldcs(a.in_rec + (Q0 + lane - a.in_base));
+    uint32_t own_next = 0;
+    if (Q0 + lane < Q1) {
+        rec_next = __ldcs(a.in_rec + (Q0 + lane - a.in_base));
+        own_next = __ldcs(a.in_own + (Q0 + lane - a.in_base));
+    }
+    __syncwarp();
     for (uint64_t qb = Q0; qb < Q1; qb += 32) {
         const uint4 rec = rec_next;
+        const uint32_t own = own_next;
         const bool have = qb + lane < Q1;
-        if (qb + 32 + lane < Q1) rec_next = __ldcs(a.in_rec + (qb + 32 + lane - a.in_base));   // prefetch the next round
+        if (qb + 32 + lane < Q1) {                             // prefetch the next round
+            rec_next = __ldcs(a.in_rec + (qb + 32 + lane - a.in_base));
+            own_next = __ldcs(a.in_own + (qb + 32 + lane - a.in_base));
+        }
         int c = 0;
         if (have) {
             const float us = node_uniform(rec.x, a.epoch, a.k2);
@@ -538,18 +544,19 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
         const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
         if (c > 0) {
             const uint32_t slot = qcount + __popc(fired & ((1u << lane) - 1u));
-            float ys[DP];
+            float ys[DP], yr[DP];
             load_row<DP>(a.y_snap, rec.x, ys);
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) yr[cc] = s_yref[own * DP + cc];
+            const float coef = attract_coeff(sqdist<DP>(yr, ys), F_SUB(as_float(rec.z), as_float(rec.y)), as_float(rec.w), a.K);
+            const float A = in_edge_factor(coef, c);
             if constexpr (DP == 2) {
-                *reinterpret_cast<float4 *>(s_q + slot * QF) =
-                    make_float4(ys[0], ys[1], as_float(rec.z) - as_float(rec.y), as_float(rec.w));
+                *reinterpret_cast<float4 *>(s_q + slot * QF) = make_float4(ys[0], ys[1], A, 0.0f);
             } else {
 #pragma unroll
                 for (int cc = 0; cc < DP; cc++) s_q[slot * QF + cc] = ys[cc];
-                s_q[slot * QF + DP] = as_float(rec.z) - as_float(rec.y);
-                s_q[slot * QF + DP + 1] = as_float(rec.w);
+                s_q[slot * QF + DP] = A;
             }
-            s_qc[slot] = (uint32_t)c;
         }
         // which of this round's fired lanes belong to this owner (in-edges are sorted by destination)
         {
@@ -987,9 +994,10 @@ static int ensure_build(annembed_cuda_ctx *ctx)
         ctx->in_base = qr[0];
         const uint64_t cnt = qr[1] - qr[0];
         CU(ctx->in_rec.alloc(std::max<uint64_t>(cnt, 1)));
+        CU(ctx->in_own.alloc(std::max<uint64_t>(cnt, 1)));
         if (cnt) {
-            k_in_rec<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, ctx->row_ptr.p, ctx->cum.p,
-                                                                 ctx->inv_s2.p, ctx->in_rec.p);
+            k_in_rec<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, dst_sorted.p, ctx->lo, ctx->row_ptr.p,
+                                                                 ctx->cum.p, ctx->inv_s2.p, ctx->in_rec.p, ctx->in_own.p);
             ctx->st.kernel_launches++;
         }
         if ((rc = sync_stream(ctx))) return rc;
@@ -1073,9 +1081,9 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
     return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
 }
 
-#define ANNEMBED_FIRINGS_PER_MINI_EPOCH 2.0
-// Mini-epochs per reference batch.  Default: about 2 own firings per node per mini-epoch
-// (nb_sampling_by_edge * mean degree / 2), where the bulk-synchronous layout statistics meet the serial
+#define ANNEMBED_FIRINGS_PER_MINI_EPOCH 3.0
+// Mini-epochs per reference batch.  Default: about 3 own firings per node per mini-epoch
+// (nb_sampling_by_edge * mean degree / 3), where the bulk-synchronous layout statistics meet the serial
 // reference's within 1 % (tests/studies/semantics_study.py).
 static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
 {
@@ -1134,7 +1142,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.y_snap = ctx->y[ctx->cur].p;
     a.y_next = ctx->y[ctx->cur ^ 1].p;
     a.row_ptr = ctx->row_ptr.p; a.col = ctx->col.p; a.p = ctx->proba.p; a.inv_s2 = ctx->inv_s2.p;
-    a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
+    a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base; a.in_own = ctx->in_own.p;
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
     a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;
@@ -1173,7 +1181,6 @@ static cudaError_t launch_tiled(annembed_cuda_ctx *ctx, const EpochArgs &a)
     if (!configured[ctx->device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM);
         if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[ctx->device & 63] = true;
     }
     const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;

@@ -34,6 +34,20 @@ __host__ __device__ __forceinline__ float fast_div(float a, float b)
     return a / b;
 #endif
 }
+// Explicitly rounded fp32 operations: nvcc may not contract or reorder them, so every kernel that inlines the
+// functions below (tiled, generic, fixed-step) produces bit-identical results for the same inputs.
+#ifdef __CUDA_ARCH__
+#define F_ADD(a, b) __fadd_rn((a), (b))
+#define F_SUB(a, b) __fsub_rn((a), (b))
+#define F_MUL(a, b) __fmul_rn((a), (b))
+#define F_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+#define F_ADD(a, b) ((a) + (b))
+#define F_SUB(a, b) ((a) - (b))
+#define F_MUL(a, b) ((a) * (b))
+#define F_FMA(a, b, c) fmaf((a), (b), (c))
+#endif
+
 __host__ __device__ __forceinline__ float as_float(uint32_t u)
 {
 #ifdef __CUDA_ARCH__
@@ -89,16 +103,27 @@ __host__ __device__ __forceinline__ float sqdist(const float (&a)[DP], const flo
 {
     float s = 0.0f;
 #pragma unroll
-    for (int c = 0; c < DP; c++) { const float t = a[c] - b[c]; s += t * t; }   // embedder.rs:1206-1211 order
+    for (int c = 0; c < DP; c++) { const float t = F_SUB(a[c], b[c]); s = F_FMA(t, t, s); }   // embedder.rs:1206-1211 order
     return s;
 }
 
 // common coefficient, embedder.rs:1216-1222 / :1276-1282
 __host__ __device__ __forceinline__ float cauchy_coeff(float u, float inv_s2, const SgdConst &K)
 {
-    if (K.b_is_one) return fast_div(K.two_b * inv_s2, 1.0f + u);
+    if (K.b_is_one) return fast_div(F_MUL(K.two_b, inv_s2), F_ADD(1.0f, u));
     const float pw = powf(u, K.b);
-    return K.two_b * (1.0f / (1.0f + pw)) * powf(u, K.b - 1.0f) * inv_s2;
+    return F_MUL(F_MUL(F_MUL(K.two_b, fast_div(1.0f, F_ADD(1.0f, pw))), powf(u, F_SUB(K.b, 1.0f))), inv_s2);
+}
+
+// attraction coefficient of a positive edge of proba p at squared distance D (embedder.rs:1212-1229); 0 when the
+// points coincide (:1223).  Negative = the ends move towards each other, at most 49 % of the gap each.
+__host__ __device__ __forceinline__ float attract_coeff(float D, float p, float inv_s2, const SgdConst &K)
+{
+    const float u = F_MUL(D, inv_s2);
+    if (!(u > 0.0f)) return 0.0f;
+    const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 1.0e4f));                 // alfa = 1/PROBA_MIN :1225-1226
+    const float w = F_FMA(F_SUB(1.0f, p), rep, -p);                               // -p + (1-p) * rep
+    return fmaxf(F_MUL(F_MUL(K.gamma, cauchy_coeff(u, inv_s2, K)), w), -0.49f);   // :1228-1229
 }
 
 // Positive edge (i -> j, proba p): embedder.rs:1202-1238.  yi/yj are local copies, g the sample's gradient.
@@ -106,15 +131,14 @@ template <int DP>
 __host__ __device__ __forceinline__ void attract(float (&yi)[DP], float (&yj)[DP], float (&g)[DP], float p,
                                                  float inv_s2, const SgdConst &K)
 {
-    const float u = sqdist<DP>(yi, yj) * inv_s2;
-    if (u > 0.0f) {
-        const float rep = fast_div(1.0f, fmaxf(u * u, 1.0e4f));                  // alfa = 1/PROBA_MIN :1225-1226
-        const float a = fmaxf(K.gamma * cauchy_coeff(u, inv_s2, K) * (-p + (1.0f - p) * rep), -0.49f); // :1228-1229
+    const float D = sqdist<DP>(yi, yj);
+    if (F_MUL(D, inv_s2) > 0.0f) {
+        const float a = attract_coeff(D, p, inv_s2, K);
 #pragma unroll
-        for (int c = 0; c < DP; c++) g[c] = (yj[c] - yi[c]) * a;                  // :1230
+        for (int c = 0; c < DP; c++) g[c] = F_MUL(F_SUB(yj[c], yi[c]), a);        // :1230
     }
 #pragma unroll
-    for (int c = 0; c < DP; c++) { yi[c] -= g[c]; yj[c] += g[c]; }                // :1237-1238
+    for (int c = 0; c < DP; c++) { yi[c] = F_SUB(yi[c], g[c]); yj[c] = F_ADD(yj[c], g[c]); }   // :1237-1238
 }
 
 // Negative node k: embedder.rs:1263-1297.  Only yi moves; g keeps its previous value when the
@@ -125,14 +149,35 @@ __host__ __device__ __forceinline__ void repulse(float (&yi)[DP], const float (&
 {
     const float dk = sqdist<DP>(yi, yk);
     if (dk > 0.0f) {
-        const float u = dk * inv_s2;
-        const float rep = fast_div(1.0f, fmaxf(u * u, 0.0625f));                  // alfa = 1/16 :1286-1288
-        const float a = fminf(K.gamma * cauchy_coeff(u, inv_s2, K) * rep, 2.0f);
+        const float u = F_MUL(dk, inv_s2);
+        const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 0.0625f));            // alfa = 1/16 :1286-1288
+        const float a = fminf(F_MUL(F_MUL(K.gamma, cauchy_coeff(u, inv_s2, K)), rep), 2.0f);
 #pragma unroll
-        for (int c = 0; c < DP; c++) g[c] = (yk[c] - yi[c]) * a;
+        for (int c = 0; c < DP; c++) g[c] = F_MUL(F_SUB(yk[c], yi[c]), a);
     }
 #pragma unroll
-    for (int c = 0; c < DP; c++) yi[c] -= g[c];
+    for (int c = 0; c < DP; c++) yi[c] = F_SUB(yi[c], g[c]);
+}
+
+// ---- destination side of a positive edge (src -> node) inside a mini-epoch -------------------------------------
+// The destination's owner evaluates the attraction coefficient once, at its position after its own firings
+// (y_ref), for the c firings the source drew for this edge.  With the coefficient a frozen, the pair's gap shrinks
+// by (1 + 2a) per firing (both ends move, embedder.rs:1237-1238), so the destination moves by
+//   A * (y - y_src),  A = a * (1 + (1+2a) + ... + (1+2a)^(c-1)).
+// Applying "y += A (y - y_src)" entry after entry keeps every step a contraction towards y_src (|A| < 1/2) and
+// leaves only a 2-flop dependency between consecutive in-edges of a node.
+__host__ __device__ __forceinline__ float in_edge_factor(float a, int c)
+{
+    float A = a, f = 1.0f;
+    const float r = F_FMA(2.0f, a, 1.0f);
+    for (int i = 1; i < c; i++) { f = F_MUL(f, r); A = F_FMA(a, f, A); }
+    return A;
+}
+template <int DP>
+__host__ __device__ __forceinline__ void apply_in_edge(float (&y)[DP], const float (&ys)[DP], float A)
+{
+#pragma unroll
+    for (int c = 0; c < DP; c++) y[c] = F_FMA(F_SUB(y[c], ys[c]), A, y[c]);
 }
 
 // One complete reference sample applied in place on a layout (serial semantics, K3).
@@ -168,6 +213,7 @@ struct EpochArgs {
     const uint64_t *__restrict__ in_ptr; // transposed index of the owned nodes: in_ptr[node-lo] .. in_ptr[node-lo+1]
     const uint4 *__restrict__ in_rec;   // {src node, edge id, bits(p_e), bits(inv_s2[src])}, entry q at in_rec[q - in_base]
     uint64_t in_base;
+    const uint8_t *__restrict__ in_own;  // (dst - lo) & 31 of every owned in-edge: its owner lane in the warp tile
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
     const float *__restrict__ cum;       // v2: inclusive cumulative probability along each row (last entry exactly 1)
     uint32_t k2;                         // v2: Philox2x32 key of the per-node uniform
@@ -417,7 +463,7 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
         const float P_hi = a.cum[m];
         const int c_hi = cum_ceil(a.kappa, P_hi, u);
         const int c = c_hi - c_lo;
-        const float pe = P_hi - P_lo;
+        const float pe = F_SUB(P_hi, P_lo);
         P_lo = P_hi; c_lo = c_hi;
         if (c <= 0) continue;
         const uint32_t j = a.col[m];
@@ -432,7 +478,10 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
             apply_firing<DP>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
-    // phase B: in-edges in transposed-index order
+    // phase B: in-edges in transposed-index order, coefficients evaluated at the position after phase A
+    float yref[DP];
+#pragma unroll
+    for (int cc = 0; cc < DP; cc++) yref[cc] = y[cc];
     const uint64_t q0 = a.in_ptr[node - a.lo], q1 = a.in_ptr[node - a.lo + 1];
     for (uint64_t q = q0; q < q1; q++) {
         const uint4 rec = a.in_rec[q - a.in_base];
@@ -442,13 +491,8 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
         if (c <= 0) continue;
         float ys[DP];
         load_row<DP>(a.y_snap, rec.x, ys);
-        const float inv_s2_src = as_float(rec.w);
-        const float pe = Ph - Pl;
-        for (int f = 0; f < c; f++) {
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
-            attract<DP>(ys, y, g, pe, inv_s2_src, a.K);
-        }
+        const float coef = attract_coeff(sqdist<DP>(yref, ys), F_SUB(Ph, Pl), as_float(rec.w), a.K);
+        apply_in_edge<DP>(y, ys, in_edge_factor(coef, c));
     }
     store_row<DP>(a.y_next, node, y);
     return s;

@@ -1,0 +1,100 @@
+"""Full-size checks at BASELINE.json shapes through size-independent properties (the oracle cannot finish these
+sizes in seconds): exact sample accounting, determinism (checksum of the layout), the reference's zero-step last
+batch (embedder.rs:873-876), weight normalisation, and K1/K5 against the oracle on a slice."""
+import numpy as np
+import pytest
+import torch
+
+import annembed_b200 as A
+import workloads
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def higgs_graph():
+    if torch.cuda.mem_get_info()[1] < 60e9:
+        pytest.skip("needs a large-memory GPU")
+    return workloads.blocked_knn_graph(11_000_000, 28, 6, seed=0, device="cuda")
+
+
+def checksum(y):
+    v = np.ascontiguousarray(y).view(np.uint32).astype(np.uint64)
+    return int((v * np.arange(1, v.size + 1, dtype=np.uint64).reshape(v.shape)).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
+
+
+def test_c3_11m_properties(higgs_graph):
+    row_ptr, col, dist = higgs_graph
+    n, E = len(row_ptr) - 1, len(col)
+    assert (dist == 0).sum() > 1000                      # duplicate rows exercise the zero-distance branches
+    params = A.EmbedderParams(dmap_init=False, scale_rho=0.75, grad_step=1.0, nb_grad_batch=40, seed=11)
+    y0 = workloads.random_init(n, 2, seed=0)
+    sums = []
+    for rep in range(2):
+        ctx = A.CudaContext(params)
+        ctx.set_graph_csr(row_ptr, col, dist)
+        scale, p = ctx.edge_weights()
+        if rep == 0:
+            # K1 on the full graph: rows sum to 1; oracle parity on the whole graph (the C oracle is fast enough for K1)
+            s_ref, p_ref = oracle.edge_weights(row_ptr, col, dist, 0.75, 1.0)
+            assert np.max(np.abs(p - p_ref) / p_ref) <= 1e-5
+            assert np.max(np.abs(scale - s_ref) / np.maximum(s_ref, 1e-30)) <= 1e-6
+            rs = np.add.reduceat(p.astype(np.float64), row_ptr[:-1].astype(np.int64))
+            assert np.abs(rs - 1).max() < 1e-5
+        ctx.set_embedding(y0)
+        ctx.optimize_batches(1, 2)
+        st = ctx.get_stats()
+        M = st["mini_epochs_per_batch"]
+        # systematic sampling: every node fires ceil(kappa - u) times per mini-epoch -> total within n per mini-epoch
+        expect = 2 * 10 * E
+        assert abs(st["positive_samples"] - expect) <= 2 * M * n * 0.51 + 1
+        y = ctx.get_embedding()
+        assert np.isfinite(y).all()
+        sums.append(checksum(y))
+        if rep == 1:
+            ce = ctx.cross_entropy()
+            es = ctx.get_embedded_scales()
+            ce_ref = oracle.cross_entropy(row_ptr, col, p, es, y, 1.0)        # K5 at full size vs the oracle
+            assert abs(ce - ce_ref) <= 1e-6 * abs(ce_ref)
+            before = y.copy()
+            ctx.optimize_batches(40, 1)                 # last batch: grad_step == 0
+            np.testing.assert_array_equal(ctx.get_embedding(), before)
+        ctx.close()
+    assert sums[0] == sums[1]                            # bit-identical reruns
+
+
+def test_c4_dim15_short_run():
+    row_ptr, col, dist = workloads.blocked_knn_graph(1_000_000, 28, 6, seed=1, device="cuda")
+    n = len(row_ptr) - 1
+    params = A.EmbedderParams(asked_dim=15, dmap_init=False, scale_rho=0.75, grad_step=1.0, nb_grad_batch=10, seed=3)
+    ctx = A.CudaContext(params)
+    ctx.set_graph_csr(row_ptr, col, dist)
+    ctx.edge_weights(want_outputs=False)
+    y0 = workloads.random_init(n, 15, seed=0)
+    ctx.set_embedding(y0)
+    ce0, ce1 = ctx.optimize()
+    y = ctx.get_embedding()
+    assert y.shape == (n, 15) and np.isfinite(y).all() and np.isfinite([ce0, ce1]).all()
+    assert np.abs(y - y0).max() > 0.1
+
+
+def test_c1_mnist_shape_full_embed():
+    x, _ = workloads.gaussian_mixture(70000, 784, seed=0)
+    idx, dist = workloads.knn_exact(x, 10, device="cuda")
+    g = A.KGraph.from_knn(idx, dist)
+    y0 = workloads.pca_init(x, 2)
+    params = A.EmbedderParams(nb_grad_batch=30, grad_step=1.0)      # examples/mnist_digits.rs:92-100
+    emb = A.Embedder(g, params, initial_embedding=y0)
+    assert emb.embed() == 1
+    y = emb.get_embedded_reindexed()
+    assert np.isfinite(y).all()
+    st = emb.stats
+    assert abs(st["positive_samples"] / (30 * 10 * len(g.col)) - 1) < 0.01
+    # neighbours end up closer than random pairs (the layout carries the graph)
+    rp, col, _ = g.get_neighbours()
+    src = np.repeat(np.arange(70000), 10)
+    d_nb = np.linalg.norm(y[src] - y[col.astype(np.int64)], axis=1).mean()
+    rnd = np.random.default_rng(0).integers(0, 70000, size=(700000, 2))
+    d_rnd = np.linalg.norm(y[rnd[:, 0]] - y[rnd[:, 1]], axis=1).mean()
+    assert d_nb < 0.1 * d_rnd

@@ -247,8 +247,8 @@ def test_tiled_epoch_kernel_equals_generic_kernel(d, kmax, hub):
         ctx.optimize_batches(1, 1)
         outs.append((ctx.get_embedding(), ctx.get_stats()["positive_samples"]))
     assert outs[0][1] == outs[1][1]
-    err = np.abs(outs[0][0] - outs[1][0]).max(axis=1)
-    assert np.quantile(err, 0.999) < 1e-4, (np.quantile(err, 0.999), err.max())
+    # both kernels inline the same explicitly-rounded device functions in the same order: bit-identical layouts
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
 
 
 def test_rows_longer_than_16_use_the_generic_kernel():
