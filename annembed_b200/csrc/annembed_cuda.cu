@@ -381,10 +381,10 @@ constexpr int EPOCH_QCAP = 128;                 // queue entries per warp
 template <int DP, int KREG>
 struct EpochTile {
     static constexpr int WARPS = DP <= 4 ? 8 : (DP <= 16 ? 4 : 2);
-    static constexpr int MINB = DP <= 4 ? 3 : (DP <= 8 ? 2 : 1);                  // blocks/SM the register budget aims at
+    static constexpr int MINB = DP <= 4 ? 3 : (DP <= 8 ? 2 : 1);               // blocks/SM the register budget aims at
     static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
     static constexpr int QF = DP == 2 ? 4 : DP + 4;                              // floats per queue entry: y_src, factor A (16-byte rows)
-    static constexpr int QUEUE_BYTES = EPOCH_QCAP * 4 * QF + 32 * 4 * DP;        // + the tile's positions after phase A
+    static constexpr int QUEUE_BYTES = (DP <= 4 ? 0 : EPOCH_QCAP * 4 * QF) + 32 * 4 * DP;   // queue (DP > 4 only) + positions after phase A
     static constexpr int ROW_BYTES = 32 * RS * (4 + 4 + 2) + 32 * 4;             // col, cum, ceil counts (u16), + slack
     static constexpr int PER_WARP = ((QUEUE_BYTES + ROW_BYTES + 15) / 16) * 16;
     static constexpr int SMEM = WARPS * PER_WARP;
@@ -402,8 +402,8 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
     const uint64_t n0 = (uint64_t)a.lo + tile * 32;
     if (n0 >= a.hi) return;                                    // whole warp leaves together
     unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
-    float *s_q = reinterpret_cast<float *>(base);                               // [QCAP][QF]  (16-byte aligned)
-    float *s_yref = s_q + EPOCH_QCAP * QF;                                      // [32][DP]
+    float *s_q = reinterpret_cast<float *>(base);                               // [QCAP][QF]  (16-byte aligned; DP > 4 only)
+    float *s_yref = s_q + (DP <= 4 ? 0 : EPOCH_QCAP * QF);                      // [32][DP]
     uint32_t *s_col = reinterpret_cast<uint32_t *>(s_yref + 32 * DP);           // [32][RS]
     float *s_cum = reinterpret_cast<float *>(s_col + 32 * RS);                  // [32][RS]
     unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_cum + 32 * RS); // [32][RS]
@@ -484,7 +484,7 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
             };
             uint32_t negs[ANNEMBED_NB_NEG];
             draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
-            apply_firing<DP>(a, node, y, yj, g, pe, inv_s2, negs);
+            apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
     // ---------------- phase B
@@ -499,82 +499,129 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
     const uint64_t Q1 = __shfl_sync(0xffffffffu, my_q1, nvalid - 1);
     // this owner's in-edge positions relative to the sweep cursor (advanced by 32 per round)
     int rel_lo = valid ? (int)(my_q0 - Q0) : 0x3fffffff, rel_hi = valid ? (int)(my_q1 - Q0) : 0x3fffffff;
-    uint32_t qcount = 0, seg_start = 0, seg_cnt = 0;           // queue fill (warp uniform); this owner's entries in it
-    auto flush = [&]() {
+    const uint32_t n_in = (uint32_t)(Q1 - Q0);                  // in-edges of the tile
+    const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
+    const uint8_t *ownp = a.in_own + (Q0 - a.in_base) + lane;
+    if constexpr (DP <= 4) {
+        // no queue: the entries of a round stay in registers and owners pull theirs with shuffles, in lane (= index) order
+        uint4 rec_next = make_uint4(0, 0, 0, 0);
+        uint32_t own_next = 0;
+        if (lane < n_in) { rec_next = __ldcs(recp); own_next = __ldcs(ownp); }
         __syncwarp();
-        for (uint32_t t = seg_start, te = seg_start + seg_cnt; t < te; t++) {
-            float ys[DP];
-            float A;
-            if constexpr (DP == 2) {
-                const float4 e4 = *reinterpret_cast<const float4 *>(s_q + t * QF);
-                ys[0] = e4.x; ys[1] = e4.y; A = e4.z;
-            } else {
-#pragma unroll
-                for (int c = 0; c < DP; c += 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(s_q + t * QF + c);
-                    ys[c] = v.x; ys[c + 1] = v.y; ys[c + 2] = v.z; ys[c + 3] = v.w;
-                }
-                A = s_q[t * QF + DP];
+        for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
+            const uint4 rec = rec_next;
+            const uint32_t own = own_next;
+            const bool have = base_q + lane < n_in;
+            if (base_q + 32 + lane < n_in) {                   // prefetch the next round
+                rec_next = __ldcs(recp + base_q + 32);
+                own_next = __ldcs(ownp + base_q + 32);
             }
-            apply_in_edge<DP>(y, ys, A);
-        }
-        __syncwarp();
-        qcount = 0; seg_cnt = 0;
-    };
-    uint4 rec_next = make_uint4(0, 0, 0, 0);
-    uint32_t own_next = 0;
-    if (Q0 + lane < Q1) {
-        rec_next = __ldcs(a.in_rec + (Q0 + lane - a.in_base));
-        own_next = __ldcs(a.in_own + (Q0 + lane - a.in_base));
-    }
-    __syncwarp();
-    for (uint64_t qb = Q0; qb < Q1; qb += 32) {
-        const uint4 rec = rec_next;
-        const uint32_t own = own_next;
-        const bool have = qb + lane < Q1;
-        if (qb + 32 + lane < Q1) {                             // prefetch the next round
-            rec_next = __ldcs(a.in_rec + (qb + 32 + lane - a.in_base));
-            own_next = __ldcs(a.in_own + (qb + 32 + lane - a.in_base));
-        }
-        int c = 0;
-        if (have) {
-            const float us = node_uniform(rec.x, a.epoch, a.k2);
-            c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
-        }
-        const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
-        if (c > 0) {
-            const uint32_t slot = qcount + __popc(fired & ((1u << lane) - 1u));
-            float ys[DP], yr[DP];
-            load_row<DP>(a.y_snap, rec.x, ys);
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) yr[cc] = s_yref[own * DP + cc];
-            const float coef = attract_coeff(sqdist<DP>(yr, ys), F_SUB(as_float(rec.z), as_float(rec.y)), as_float(rec.w), a.K);
-            const float A = in_edge_factor(coef, c);
-            if constexpr (DP == 2) {
-                *reinterpret_cast<float4 *>(s_q + slot * QF) = make_float4(ys[0], ys[1], A, 0.0f);
-            } else {
-#pragma unroll
-                for (int cc = 0; cc < DP; cc++) s_q[slot * QF + cc] = ys[cc];
-                s_q[slot * QF + DP] = A;
+            int c = 0;
+            if (have) {
+                const float us = node_uniform(rec.x, a.epoch, a.k2);
+                c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
             }
-        }
-        // which of this round's fired lanes belong to this owner (in-edges are sorted by destination)
-        {
+            const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
+            float ys[DP], A = 0.0f;
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) ys[cc] = 0.0f;
+            if (c > 0) {
+                float yr[DP];
+                load_row<DP>(a.y_snap, rec.x, ys);
+#pragma unroll
+                for (int cc = 0; cc < DP; cc++) yr[cc] = s_yref[own * DP + cc];
+                const float coef = attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(as_float(rec.z), as_float(rec.y)), as_float(rec.w), a.K);
+                A = in_edge_factor(coef, c);
+            }
+            // this owner's fired in-edges of the round: lanes [rel_lo, rel_hi) (in-edges are sorted by destination)
             const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));
-            if (hi_c > lo_c) {
-                const unsigned range = (0xffffffffu >> (32 - (hi_c - lo_c))) << lo_c;
-                const uint32_t mine = __popc(fired & range);
-                if (mine) {
-                    if (seg_cnt == 0) seg_start = qcount + __popc(fired & ((1u << lo_c) - 1u));
-                    seg_cnt += mine;
+            unsigned mine = 0;
+            if (hi_c > lo_c) mine = fired & ((0xffffffffu >> (32 - (hi_c - lo_c))) << lo_c);
+            rel_lo -= 32; rel_hi -= 32;
+            while (__any_sync(0xffffffffu, mine != 0)) {
+                const int b = mine ? __ffs(mine) - 1 : lane;
+                float t[DP];
+#pragma unroll
+                for (int cc = 0; cc < DP; cc++) t[cc] = __shfl_sync(0xffffffffu, ys[cc], b);
+                const float Ab = __shfl_sync(0xffffffffu, A, b);
+                if (mine) { apply_in_edge<DP>(y, t, Ab); mine &= mine - 1; }
+            }
+        }
+    } else {
+        uint32_t qcount = 0, seg_start = 0, seg_cnt = 0;           // queue fill (warp uniform); this owner's entries in it
+        auto flush = [&]() {
+            __syncwarp();
+            for (uint32_t t = seg_start, te = seg_start + seg_cnt; t < te; t++) {
+                float ys[DP];
+                float A;
+                if constexpr (DP == 2) {
+                    const float4 e4 = *reinterpret_cast<const float4 *>(s_q + t * QF);
+                    ys[0] = e4.x; ys[1] = e4.y; A = e4.z;
+                } else {
+    #pragma unroll
+                    for (int c = 0; c < DP; c += 4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(s_q + t * QF + c);
+                        ys[c] = v.x; ys[c + 1] = v.y; ys[c + 2] = v.z; ys[c + 3] = v.w;
+                    }
+                    A = s_q[t * QF + DP];
+                }
+                apply_in_edge<DP>(y, ys, A);
+            }
+            __syncwarp();
+            qcount = 0; seg_cnt = 0;
+        };
+        uint4 rec_next = make_uint4(0, 0, 0, 0);
+        uint32_t own_next = 0;
+        if (lane < n_in) { rec_next = __ldcs(recp); own_next = __ldcs(ownp); }
+        __syncwarp();
+        for (uint64_t qb = Q0; qb < Q1; qb += 32) {
+            const uint4 rec = rec_next;
+            const uint32_t own = own_next;
+            const bool have = qb + lane < Q1;
+            if (qb + 32 + lane < Q1) {                             // prefetch the next round
+                rec_next = __ldcs(a.in_rec + (qb + 32 + lane - a.in_base));
+                own_next = __ldcs(a.in_own + (qb + 32 + lane - a.in_base));
+            }
+            int c = 0;
+            if (have) {
+                const float us = node_uniform(rec.x, a.epoch, a.k2);
+                c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
+            }
+            const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
+            if (c > 0) {
+                const uint32_t slot = qcount + __popc(fired & ((1u << lane) - 1u));
+                float ys[DP], yr[DP];
+                load_row<DP>(a.y_snap, rec.x, ys);
+    #pragma unroll
+                for (int cc = 0; cc < DP; cc++) yr[cc] = s_yref[own * DP + cc];
+                const float coef = attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(as_float(rec.z), as_float(rec.y)), as_float(rec.w), a.K);
+                const float A = in_edge_factor(coef, c);
+                if constexpr (DP == 2) {
+                    *reinterpret_cast<float4 *>(s_q + slot * QF) = make_float4(ys[0], ys[1], A, 0.0f);
+                } else {
+    #pragma unroll
+                    for (int cc = 0; cc < DP; cc++) s_q[slot * QF + cc] = ys[cc];
+                    s_q[slot * QF + DP] = A;
                 }
             }
-            rel_lo -= 32; rel_hi -= 32;
+            // which of this round's fired lanes belong to this owner (in-edges are sorted by destination)
+            {
+                const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));
+                if (hi_c > lo_c) {
+                    const unsigned range = (0xffffffffu >> (32 - (hi_c - lo_c))) << lo_c;
+                    const uint32_t mine = __popc(fired & range);
+                    if (mine) {
+                        if (seg_cnt == 0) seg_start = qcount + __popc(fired & ((1u << lo_c) - 1u));
+                        seg_cnt += mine;
+                    }
+                }
+                rel_lo -= 32; rel_hi -= 32;
+            }
+            qcount += __popc(fired);
+            if (qcount + 32 > EPOCH_QCAP) flush();
         }
-        qcount += __popc(fired);
-        if (qcount + 32 > EPOCH_QCAP) flush();
+        if (qcount) flush();
     }
-    if (qcount) flush();
     if (valid) store_row<DP>(a.y_next, node, y);
     unsigned int applied = (unsigned int)T;
 #pragma unroll
@@ -1194,8 +1241,9 @@ static cudaError_t launch_epoch_dp(annembed_cuda_ctx *ctx, const EpochArgs &a)
 {
     if (a.hi <= a.lo) return cudaSuccess;
     const bool force_generic = (ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL) != 0;
-    if (!force_generic && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
-    if (!force_generic && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);
+    const bool tiled_ok = !force_generic && ctx->prm.b == 1.0;     // the tiled kernel is specialised for b == 1
+    if (tiled_ok && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
+    if (tiled_ok && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);
     k_epoch_generic<DP, HUB><<<nblocks(a.hi - a.lo, 256), 256, 0, ctx->stream>>>(a, ctx->counter.p);
     return cudaGetLastError();
 }

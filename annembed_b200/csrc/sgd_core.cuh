@@ -107,56 +107,67 @@ __host__ __device__ __forceinline__ float sqdist(const float (&a)[DP], const flo
     return s;
 }
 
-// common coefficient, embedder.rs:1216-1222 / :1276-1282
+// common coefficient, embedder.rs:1216-1222 / :1276-1282.  B1 = (b == 1) known at compile time (the default model)
+template <bool B1>
 __host__ __device__ __forceinline__ float cauchy_coeff(float u, float inv_s2, const SgdConst &K)
 {
-    if (K.b_is_one) return fast_div(F_MUL(K.two_b, inv_s2), F_ADD(1.0f, u));
+    if (B1 || K.b_is_one) return fast_div(F_MUL(K.two_b, inv_s2), F_ADD(1.0f, u));
     const float pw = powf(u, K.b);
     return F_MUL(F_MUL(F_MUL(K.two_b, fast_div(1.0f, F_ADD(1.0f, pw))), powf(u, F_SUB(K.b, 1.0f))), inv_s2);
 }
 
-// attraction coefficient of a positive edge of proba p at squared distance D (embedder.rs:1212-1229); 0 when the
-// points coincide (:1223).  Negative = the ends move towards each other, at most 49 % of the gap each.
-__host__ __device__ __forceinline__ float attract_coeff(float D, float p, float inv_s2, const SgdConst &K)
+// attraction coefficient of a positive edge of proba p at squared distance D (embedder.rs:1212-1229).
+// Negative = the ends move towards each other, at most 49 % of the gap each.  Only meaningful when D > 0 (:1223).
+template <bool B1>
+__host__ __device__ __forceinline__ float attract_coeff_raw(float D, float p, float inv_s2, const SgdConst &K)
 {
     const float u = F_MUL(D, inv_s2);
-    if (!(u > 0.0f)) return 0.0f;
     const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 1.0e4f));                 // alfa = 1/PROBA_MIN :1225-1226
     const float w = F_FMA(F_SUB(1.0f, p), rep, -p);                               // -p + (1-p) * rep
-    return fmaxf(F_MUL(F_MUL(K.gamma, cauchy_coeff(u, inv_s2, K)), w), -0.49f);   // :1228-1229
+    return fmaxf(F_MUL(F_MUL(K.gamma, cauchy_coeff<B1>(u, inv_s2, K)), w), -0.49f);   // :1228-1229
+}
+template <bool B1>
+__host__ __device__ __forceinline__ float attract_coeff(float D, float p, float inv_s2, const SgdConst &K)
+{
+    const float a = attract_coeff_raw<B1>(D, p, inv_s2, K);
+    return (F_MUL(D, inv_s2) > 0.0f) ? a : 0.0f;                                  // coincident points: no move (:1223)
 }
 
 // Positive edge (i -> j, proba p): embedder.rs:1202-1238.  yi/yj are local copies, g the sample's gradient.
-template <int DP>
+// Branch-free: the coefficient is always evaluated and discarded by a select when the points coincide.
+template <int DP, bool B1 = false>
 __host__ __device__ __forceinline__ void attract(float (&yi)[DP], float (&yj)[DP], float (&g)[DP], float p,
                                                  float inv_s2, const SgdConst &K)
 {
     const float D = sqdist<DP>(yi, yj);
-    if (F_MUL(D, inv_s2) > 0.0f) {
-        const float a = attract_coeff(D, p, inv_s2, K);
+    const float a = attract_coeff_raw<B1>(D, p, inv_s2, K);
+    const bool ok = F_MUL(D, inv_s2) > 0.0f;
 #pragma unroll
-        for (int c = 0; c < DP; c++) g[c] = F_MUL(F_SUB(yj[c], yi[c]), a);        // :1230
+    for (int c = 0; c < DP; c++) {
+        const float gn = F_MUL(F_SUB(yj[c], yi[c]), a);                           // :1230
+        g[c] = ok ? gn : g[c];
+        yi[c] = F_SUB(yi[c], g[c]);                                               // :1237-1238
+        yj[c] = F_ADD(yj[c], g[c]);
     }
-#pragma unroll
-    for (int c = 0; c < DP; c++) { yi[c] = F_SUB(yi[c], g[c]); yj[c] = F_ADD(yj[c], g[c]); }   // :1237-1238
 }
 
-// Negative node k: embedder.rs:1263-1297.  Only yi moves; g keeps its previous value when the
-// two points coincide (the reference does the same).
-template <int DP>
+// Negative node k: embedder.rs:1263-1297.  Only yi moves; g keeps its previous value when the two points
+// coincide (the reference does the same).  `use` = false skips the negative entirely (no acceptable node found).
+template <int DP, bool B1 = false>
 __host__ __device__ __forceinline__ void repulse(float (&yi)[DP], const float (&yk)[DP], float (&g)[DP],
-                                                 float inv_s2, const SgdConst &K)
+                                                 float inv_s2, const SgdConst &K, bool use = true)
 {
     const float dk = sqdist<DP>(yi, yk);
-    if (dk > 0.0f) {
-        const float u = F_MUL(dk, inv_s2);
-        const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 0.0625f));            // alfa = 1/16 :1286-1288
-        const float a = fminf(F_MUL(F_MUL(K.gamma, cauchy_coeff(u, inv_s2, K)), rep), 2.0f);
+    const float u = F_MUL(dk, inv_s2);
+    const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 0.0625f));                // alfa = 1/16 :1286-1288
+    const float a = fminf(F_MUL(F_MUL(K.gamma, cauchy_coeff<B1>(u, inv_s2, K)), rep), 2.0f);
+    const bool ok = dk > 0.0f;
 #pragma unroll
-        for (int c = 0; c < DP; c++) g[c] = F_MUL(F_SUB(yk[c], yi[c]), a);
+    for (int c = 0; c < DP; c++) {
+        const float gn = F_MUL(F_SUB(yk[c], yi[c]), a);
+        g[c] = (ok && use) ? gn : g[c];
+        yi[c] = use ? F_SUB(yi[c], g[c]) : yi[c];
     }
-#pragma unroll
-    for (int c = 0; c < DP; c++) yi[c] = F_SUB(yi[c], g[c]);
 }
 
 // ---- destination side of a positive edge (src -> node) inside a mini-epoch -------------------------------------
@@ -419,7 +430,7 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
 }
 
 // one firing of `node` on edge (node -> j): attraction against the local copy of y_j, then 5 repulsions
-template <int DP>
+template <int DP, bool B1 = false>
 __host__ __device__ __forceinline__ void apply_firing(const EpochArgs &a, uint32_t node, float (&y)[DP], float (&yj)[DP],
                                                       float (&g)[DP], float pe, float inv_s2,
                                                       const uint32_t (&negs)[ANNEMBED_NB_NEG])
@@ -431,23 +442,23 @@ __host__ __device__ __forceinline__ void apply_firing(const EpochArgs &a, uint32
 #pragma unroll
         for (int q = 0; q < ANNEMBED_NB_NEG; q++)
             load_row<DP>(a.y_snap, negs[q] == ANNEMBED_NO_NODE ? node : negs[q], yk[q]);
-        attract<DP>(y, yj, g, pe, inv_s2, a.K);
+        attract<DP, B1>(y, yj, g, pe, inv_s2, a.K);
 #pragma unroll
         for (int q = 0; q < ANNEMBED_NB_NEG; q++)
             if (negs[q] != ANNEMBED_NO_NODE) repulse<DP>(y, yk[q], g, inv_s2, a.K);
     } else {
-        attract<DP>(y, yj, g, pe, inv_s2, a.K);
+        attract<DP, B1>(y, yj, g, pe, inv_s2, a.K);
         for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
             if (negs[q] == ANNEMBED_NO_NODE) continue;
             float yk[DP];
             load_row<DP>(a.y_snap, negs[q], yk);
-            repulse<DP>(y, yk, g, inv_s2, a.K);
+            repulse<DP, B1>(y, yk, g, inv_s2, a.K);
         }
     }
 }
 
 // in_rec (v2): {src node, bits(P_lo), bits(P_hi), bits(inv_s2[src])}; p_e is taken as P_hi - P_lo on both sides.
-template <int DP, bool HUB>
+template <int DP, bool HUB, bool B1 = false>
 __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &a, uint32_t node)
 {
     float y[DP], g[DP];
@@ -475,7 +486,7 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
             const Philox4 B = philox4x32_10(node, s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
             draw_negatives_v2<HUB>(a, node, s, A, philox_word(B, s & 3u), rej, negs);
-            apply_firing<DP>(a, node, y, yj, g, pe, inv_s2, negs);
+            apply_firing<DP, B1>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
     // phase B: in-edges in transposed-index order, coefficients evaluated at the position after phase A
@@ -491,7 +502,7 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
         if (c <= 0) continue;
         float ys[DP];
         load_row<DP>(a.y_snap, rec.x, ys);
-        const float coef = attract_coeff(sqdist<DP>(yref, ys), F_SUB(Ph, Pl), as_float(rec.w), a.K);
+        const float coef = attract_coeff<B1>(sqdist<DP>(yref, ys), F_SUB(Ph, Pl), as_float(rec.w), a.K);
         apply_in_edge<DP>(y, ys, in_edge_factor(coef, c));
     }
     store_row<DP>(a.y_next, node, y);
