@@ -84,9 +84,11 @@ def load(rebuild_if_stale: bool = True) -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if not os.path.exists(path) or (rebuild_if_stale and _build.needs_build()):
-        path = _build.build_library()
+    path = os.environ.get("ANNEMBED_CUDA_LIB")           # experiment variants of the same CUDA library
+    if not path:
+        path = _build.LIB
+        if not os.path.exists(path) or (rebuild_if_stale and _build.needs_build()):
+            path = _build.build_library()
     lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)          # AttributeError if the ABI and the header drift apart

@@ -32,13 +32,15 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Build the library; `extra_flags`/`out` build an experiment variant beside it (e.g. -DANNEMBED_MINB_D2=4)."""
+    target = out or LIB
+    if not force and out is None and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

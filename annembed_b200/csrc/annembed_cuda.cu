@@ -380,8 +380,14 @@ __global__ void __launch_bounds__(256) k_epoch_generic(EpochArgs a, unsigned lon
 constexpr int EPOCH_QCAP = 128;                 // queue entries per warp
 template <int DP, int KREG>
 struct EpochTile {
-    static constexpr int WARPS = DP <= 4 ? 8 : (DP <= 16 ? 4 : 2);
-    static constexpr int MINB = DP <= 4 ? 3 : (DP <= 8 ? 2 : 1);               // blocks/SM the register budget aims at
+#ifndef ANNEMBED_WARPS_D2
+#define ANNEMBED_WARPS_D2 4
+#endif
+    static constexpr int WARPS = DP <= 4 ? ANNEMBED_WARPS_D2 : (DP <= 16 ? 4 : 2);
+#ifndef ANNEMBED_MINB_D2
+#define ANNEMBED_MINB_D2 5
+#endif
+    static constexpr int MINB = DP <= 4 ? ANNEMBED_MINB_D2 : (DP <= 8 ? 2 : 1);               // blocks/SM the register budget aims at
     static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
     static constexpr int QF = DP == 2 ? 4 : DP + 4;                              // floats per queue entry: y_src, factor A (16-byte rows)
     static constexpr int QUEUE_BYTES = (DP <= 4 ? 0 : EPOCH_QCAP * 4 * QF) + 32 * 4 * DP;   // queue (DP > 4 only) + positions after phase A
@@ -457,23 +463,26 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
         }
         __syncwarp();
     }
-    // ---------------- phase A
-    {
-        int m = 0, m_prev = -1;
-        uint32_t j = 0;
-        float pe = 0.0f;
+    // ---------------- phase A  (software pipelined: the 6 row gathers of firing s+1 are in flight during the
+    //                            arithmetic of firing s; DRAM/L2 latency is hidden inside the warp)
+    if constexpr (DP <= 4) {
+        int m = 0;                       // edge cursor of the systematic sampler
+        int m_cur = -1;                  // edge whose partner copy yj is live (pair simulation across firings)
         float yj[DP];
         Philox4 B;
-        for (int s = 0; s < T; s++) {
+        // prefetched firing
+        int nm = -1;
+        float npe = 0.0f;
+        float nyj[DP], nyk[ANNEMBED_NB_NEG][DP];
+        unsigned nuse = 0;
+        auto prepare = [&](int s) {
             while ((int)s_ch[lane * RS + m] <= s) m++;          // ch[k-1] == T > s
-            if (m != m_prev) {
-                j = s_col[lane * RS + m];
-                const float P_hi = s_cum[lane * RS + m];
-                const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
-                pe = P_hi - P_lo;
-                load_row<DP>(a.y_snap, j, yj);
-                m_prev = m;
-            }
+            nm = m;
+            const uint32_t j = s_col[lane * RS + m];
+            const float P_hi = s_cum[lane * RS + m];
+            const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
+            npe = F_SUB(P_hi, P_lo);
+            load_row<DP>(a.y_snap, j, nyj);
             const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
             if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
             auto rej = [&](uint32_t kk) -> bool {
@@ -484,8 +493,63 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
             };
             uint32_t negs[ANNEMBED_NB_NEG];
             draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
-            apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
+            nuse = 0;
+#pragma unroll
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+                const bool ok = negs[q] != ANNEMBED_NO_NODE;
+                nuse |= ok ? (1u << q) : 0u;
+                load_row<DP>(a.y_snap, ok ? negs[q] : node, nyk[q]);
+            }
+        };
+        if (T > 0) prepare(0);
+        for (int s = 0; s < T; s++) {
+            float yk[ANNEMBED_NB_NEG][DP];
+            const float pe = npe;
+            const unsigned use = nuse;
+            if (nm != m_cur) {
+#pragma unroll
+                for (int c = 0; c < DP; c++) yj[c] = nyj[c];
+                m_cur = nm;
+            }
+#pragma unroll
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+#pragma unroll
+                for (int c = 0; c < DP; c++) yk[q][c] = nyk[q][c];
+            if (s + 1 < T) prepare(s + 1);
+#pragma unroll
+            for (int c = 0; c < DP; c++) g[c] = 0.0f;
+            attract<DP, true>(y, yj, g, pe, inv_s2, a.K);
+#pragma unroll
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, yk[q], g, inv_s2, a.K, (use >> q) & 1u);
         }
+    } else {   // wide rows: the prefetch registers do not fit, plain sequential firings
+            int m = 0, m_prev = -1;
+            uint32_t j = 0;
+            float pe = 0.0f;
+            float yj[DP];
+            Philox4 B;
+            for (int s = 0; s < T; s++) {
+                while ((int)s_ch[lane * RS + m] <= s) m++;          // ch[k-1] == T > s
+                if (m != m_prev) {
+                    j = s_col[lane * RS + m];
+                    const float P_hi = s_cum[lane * RS + m];
+                    const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
+                    pe = F_SUB(P_hi, P_lo);
+                    load_row<DP>(a.y_snap, j, yj);
+                    m_prev = m;
+                }
+                const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
+                if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
+                auto rej = [&](uint32_t kk) -> bool {
+                    bool r = (kk == node) | (kk == j);
+    #pragma unroll
+                    for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
+                    return r;
+                };
+                uint32_t negs[ANNEMBED_NB_NEG];
+                draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
+                apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
+            }
     }
     // ---------------- phase B
     if (valid) {
@@ -503,35 +567,56 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
     const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
     const uint8_t *ownp = a.in_own + (Q0 - a.in_base) + lane;
     if constexpr (DP <= 4) {
-        // no queue: the entries of a round stay in registers and owners pull theirs with shuffles, in lane (= index) order
-        uint4 rec_next = make_uint4(0, 0, 0, 0);
-        uint32_t own_next = 0;
-        if (lane < n_in) { rec_next = __ldcs(recp); own_next = __ldcs(ownp); }
-        __syncwarp();
-        for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
-            const uint4 rec = rec_next;
-            const uint32_t own = own_next;
-            const bool have = base_q + lane < n_in;
-            if (base_q + 32 + lane < n_in) {                   // prefetch the next round
-                rec_next = __ldcs(recp + base_q + 32);
-                own_next = __ldcs(ownp + base_q + 32);
-            }
-            int c = 0;
+        // No queue: the entries of a round stay in registers and owners pull theirs with shuffles, in lane (= index)
+        // order.  Pipelined two rounds deep: records of round r+2 and the source-row gathers of round r+1 are in
+        // flight while round r is applied.
+        uint4 rec2 = make_uint4(0, 0, 0, 0);                   // records of the round after next
+        uint32_t own2 = 0;
+        // prepared round: count, owner, record fields needed later, gathered source row
+        int nc = 0;
+        uint32_t nown = 0;
+        float nPl = 0.0f, nPh = 0.0f, nis2 = 0.0f, nys[DP];
+#pragma unroll
+        for (int cc = 0; cc < DP; cc++) nys[cc] = 0.0f;
+        auto prepare = [&](const uint4 &rec, uint32_t own, bool have) {
+            nc = 0;
             if (have) {
                 const float us = node_uniform(rec.x, a.epoch, a.k2);
-                c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
+                nc = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
+            }
+            nown = own; nPl = as_float(rec.y); nPh = as_float(rec.z); nis2 = as_float(rec.w);
+            if (nc > 0) load_row<DP>(a.y_snap, rec.x, nys);
+        };
+        {
+            uint4 rec1 = make_uint4(0, 0, 0, 0);
+            uint32_t own1 = 0;
+            if (lane < n_in) { rec1 = __ldcs(recp); own1 = __ldcs(ownp); }
+            if (32 + lane < n_in) { rec2 = __ldcs(recp + 32); own2 = __ldcs(ownp + 32); }
+            prepare(rec1, own1, lane < n_in);
+        }
+        __syncwarp();
+        for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
+            // take over the prepared round
+            const int c = nc;
+            const uint32_t own = nown;
+            const float Pl = nPl, Ph = nPh, is2 = nis2;
+            float ys[DP];
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) ys[cc] = nys[cc];
+            // prepare the next round (its records were loaded one iteration ago), fetch the records after it
+            {
+                const uint4 rec1 = rec2;
+                const uint32_t own1 = own2;
+                if (base_q + 64 + lane < n_in) { rec2 = __ldcs(recp + base_q + 64); own2 = __ldcs(ownp + base_q + 64); }
+                prepare(rec1, own1, base_q + 32 + lane < n_in);
             }
             const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
-            float ys[DP], A = 0.0f;
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) ys[cc] = 0.0f;
+            float A = 0.0f;
             if (c > 0) {
                 float yr[DP];
-                load_row<DP>(a.y_snap, rec.x, ys);
 #pragma unroll
                 for (int cc = 0; cc < DP; cc++) yr[cc] = s_yref[own * DP + cc];
-                const float coef = attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(as_float(rec.z), as_float(rec.y)), as_float(rec.w), a.K);
-                A = in_edge_factor(coef, c);
+                A = in_edge_factor(attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(Ph, Pl), is2, a.K), c);
             }
             // this owner's fired in-edges of the round: lanes [rel_lo, rel_hi) (in-edges are sorted by destination)
             const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));

@@ -203,6 +203,7 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     row_ptr, col, distances, y0, keep, t_in = make_inputs(a, f"cuda:{local}")
+    torch.cuda.empty_cache()
     params = params_for(a)
     ctx = A.CudaContext(params, device=local)
     uid = broadcast_unique_id(ctx.unique_id, rank, world)
