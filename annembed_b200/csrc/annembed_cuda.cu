@@ -71,6 +71,7 @@ struct annembed_cuda_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int n_sm = 148;
+    int last_epoch_kernels = 1;                  // kernels per mini-epoch of the path in use (tiled: 2, generic: 1)
     int l2_persist_max = 0, l2_window_max = 0;   // bytes (device attributes)
 
     // graph (replicated on every rank)
@@ -369,48 +370,47 @@ __global__ void __launch_bounds__(256) k_epoch_generic(EpochArgs a, unsigned lon
     if ((threadIdx.x & 31) == 0 && applied) atomicAdd(sample_counter + (blockIdx.x & 255), (unsigned long long)applied);
 }
 
-// K4 (tiled): one warp owns a tile of 32 consecutive nodes.
-//  phase A  lane = node.  The row (<= KREG neighbours) is kept in registers for the rejection test and mirrored,
-//           transposed, in shared memory for the edge pick; every node fires ceil(kappa - u) times (systematic
-//           sampling), so lanes stay converged; the 6 gathers of a firing are issued before the arithmetic.
-//  phase B  lanes sweep the tile's in-edge records (coalesced 16-byte loads), replay the source's firing decision
-//           (Philox2x32 of (src, epoch)), gather the source row for the ones that fired and queue them in shared
-//           memory; each owner lane then applies its own entries in transposed-index order.
-//  No atomics on the layout, no block-level barrier: warps are independent.
-constexpr int EPOCH_QCAP = 128;                 // queue entries per warp
+// K4 (tiled) = two kernels per mini-epoch; one warp owns a tile of 32 consecutive nodes in both, warps are independent
+// (no block barrier), nothing is atomic on the layout.
+//  k_epoch_out  lane = node.  The row (<= KREG neighbours) is kept in registers for the rejection test and mirrored in
+//               shared memory ([lane][m], odd stride) for the edge pick; every node fires ceil(kappa - u) times
+//               (systematic sampling) so lanes stay converged; the 6 gathers of firing s+1 are in flight during the
+//               arithmetic of firing s.  Writes the node's position after its own firings to y_next.
+//  k_epoch_in   lane = in-edge.  The warp sweeps the tile's in-edge records (coalesced 16-byte streaming loads, two
+//               rounds of records and one round of source-row gathers in flight), replays the source's firing decision
+//               (Philox2x32 of (src, epoch)), turns every fired in-edge into the affine map y -> (1+A) y - A y_src with
+//               A evaluated at the owner's position after k_epoch_out, composes the maps of each owner with a
+//               segmented warp scan and lets the owner lane apply the composite: y_next <- alpha * y_next + beta.
+//  Splitting keeps both register footprints small (k_epoch_in: ~48 registers) so that enough warps are resident to
+//  hide the random-gather latency.
 template <int DP, int KREG>
 struct EpochTile {
-#ifndef ANNEMBED_WARPS_D2
-#define ANNEMBED_WARPS_D2 4
+#ifndef ANNEMBED_WARPS_OUT
+#define ANNEMBED_WARPS_OUT 4
 #endif
-    static constexpr int WARPS = DP <= 4 ? ANNEMBED_WARPS_D2 : (DP <= 16 ? 4 : 2);
-#ifndef ANNEMBED_MINB_D2
-#define ANNEMBED_MINB_D2 5
+#ifndef ANNEMBED_MINB_OUT
+#define ANNEMBED_MINB_OUT 5
 #endif
-    static constexpr int MINB = DP <= 4 ? ANNEMBED_MINB_D2 : (DP <= 8 ? 2 : 1);               // blocks/SM the register budget aims at
+    static constexpr int WARPS = DP <= 4 ? ANNEMBED_WARPS_OUT : (DP <= 16 ? 4 : 2);
+    static constexpr int MINB = DP <= 4 ? ANNEMBED_MINB_OUT : (DP <= 8 ? 2 : 1);  // blocks/SM the register budget aims at
     static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
-    static constexpr int QF = DP == 2 ? 4 : DP + 4;                              // floats per queue entry: y_src, factor A (16-byte rows)
-    static constexpr int QUEUE_BYTES = (DP <= 4 ? 0 : EPOCH_QCAP * 4 * QF) + 32 * 4 * DP;   // queue (DP > 4 only) + positions after phase A
-    static constexpr int ROW_BYTES = 32 * RS * (4 + 4 + 2) + 32 * 4;             // col, cum, ceil counts (u16), + slack
-    static constexpr int PER_WARP = ((QUEUE_BYTES + ROW_BYTES + 15) / 16) * 16;
+    static constexpr int PER_WARP = ((32 * RS * (4 + 4 + 2) + 15) / 16) * 16;    // col, cum, ceil counts (u16)
     static constexpr int SMEM = WARPS * PER_WARP;
 };
 
 template <int DP, bool HUB, int KREG>
 __global__ void __launch_bounds__(EpochTile<DP, KREG>::WARPS * 32, EpochTile<DP, KREG>::MINB)
-k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
+k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
 {
     using TL = EpochTile<DP, KREG>;
-    constexpr int RS = TL::RS, QF = TL::QF;
+    constexpr int RS = TL::RS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t tile = (uint64_t)blockIdx.x * TL::WARPS + wib;
     const uint64_t n0 = (uint64_t)a.lo + tile * 32;
     if (n0 >= a.hi) return;                                    // whole warp leaves together
     unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
-    float *s_q = reinterpret_cast<float *>(base);                               // [QCAP][QF]  (16-byte aligned; DP > 4 only)
-    float *s_yref = s_q + (DP <= 4 ? 0 : EPOCH_QCAP * QF);                      // [32][DP]
-    uint32_t *s_col = reinterpret_cast<uint32_t *>(s_yref + 32 * DP);           // [32][RS]
+    uint32_t *s_col = reinterpret_cast<uint32_t *>(base);                       // [32][RS]
     float *s_cum = reinterpret_cast<float *>(s_col + 32 * RS);                  // [32][RS]
     unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_cum + 32 * RS); // [32][RS]
 
@@ -463,15 +463,14 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
         }
         __syncwarp();
     }
-    // ---------------- phase A  (software pipelined: the 6 row gathers of firing s+1 are in flight during the
-    //                            arithmetic of firing s; DRAM/L2 latency is hidden inside the warp)
+    // ---------------- the node's own firings
     if constexpr (DP <= 4) {
+        // software pipelined: the 6 row gathers of firing s+1 are in flight during the arithmetic of firing s
         int m = 0;                       // edge cursor of the systematic sampler
         int m_cur = -1;                  // edge whose partner copy yj is live (pair simulation across firings)
         float yj[DP];
         Philox4 B;
-        // prefetched firing
-        int nm = -1;
+        int nm = -1;                     // prefetched firing
         float npe = 0.0f;
         float nyj[DP], nyk[ANNEMBED_NB_NEG][DP];
         unsigned nuse = 0;
@@ -522,40 +521,66 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
 #pragma unroll
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, yk[q], g, inv_s2, a.K, (use >> q) & 1u);
         }
-    } else {   // wide rows: the prefetch registers do not fit, plain sequential firings
-            int m = 0, m_prev = -1;
-            uint32_t j = 0;
-            float pe = 0.0f;
-            float yj[DP];
-            Philox4 B;
-            for (int s = 0; s < T; s++) {
-                while ((int)s_ch[lane * RS + m] <= s) m++;          // ch[k-1] == T > s
-                if (m != m_prev) {
-                    j = s_col[lane * RS + m];
-                    const float P_hi = s_cum[lane * RS + m];
-                    const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
-                    pe = F_SUB(P_hi, P_lo);
-                    load_row<DP>(a.y_snap, j, yj);
-                    m_prev = m;
-                }
-                const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
-                if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
-                auto rej = [&](uint32_t kk) -> bool {
-                    bool r = (kk == node) | (kk == j);
-    #pragma unroll
-                    for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
-                    return r;
-                };
-                uint32_t negs[ANNEMBED_NB_NEG];
-                draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
-                apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
+    } else {
+        // wide rows: the prefetch registers do not fit, plain sequential firings
+        int m = 0, m_prev = -1;
+        uint32_t j = 0;
+        float pe = 0.0f;
+        float yj[DP];
+        Philox4 B;
+        for (int s = 0; s < T; s++) {
+            while ((int)s_ch[lane * RS + m] <= s) m++;
+            if (m != m_prev) {
+                j = s_col[lane * RS + m];
+                const float P_hi = s_cum[lane * RS + m];
+                const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
+                pe = F_SUB(P_hi, P_lo);
+                load_row<DP>(a.y_snap, j, yj);
+                m_prev = m;
             }
-    }
-    // ---------------- phase B
-    if (valid) {
+            const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
+            if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
+            auto rej = [&](uint32_t kk) -> bool {
+                bool r = (kk == node) | (kk == j);
 #pragma unroll
-        for (int c = 0; c < DP; c++) s_yref[lane * DP + c] = y[c];
+                for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
+                return r;
+            };
+            uint32_t negs[ANNEMBED_NB_NEG];
+            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
+            apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
+        }
     }
+    if (valid) store_row<DP>(a.y_next, node, y);
+    unsigned int applied = (unsigned int)T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) applied += __shfl_xor_sync(0xffffffffu, applied, o);
+    if (lane == 0 && applied) atomicAdd(sample_counter + (blockIdx.x & 255), (unsigned long long)applied);
+}
+
+#ifndef ANNEMBED_WARPS_IN
+#define ANNEMBED_WARPS_IN 4
+#endif
+#ifndef ANNEMBED_MINB_IN
+#define ANNEMBED_MINB_IN 10
+#endif
+template <int DP>
+__global__ void __launch_bounds__(ANNEMBED_WARPS_IN * 32, (DP <= 4 ? ANNEMBED_MINB_IN : (DP <= 8 ? 6 : (DP <= 16 ? 4 : 2))))
+k_epoch_in(EpochArgs a)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t)blockIdx.x * ANNEMBED_WARPS_IN + wib;
+    const uint64_t n0 = (uint64_t)a.lo + tile * 32;
+    if (n0 >= a.hi) return;
+    const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
+    const uint32_t node = (uint32_t)n0 + lane;
+    const bool valid = lane < nvalid;
+    // the owner's position after its own firings (written by k_epoch_out): reference point of the coefficients and
+    // the value the composite map is applied to
+    float y[DP];
+#pragma unroll
+    for (int c = 0; c < DP; c++) y[c] = 0.0f;
+    if (valid) load_row<DP>(a.y_next, node, y);
     uint64_t my_q0 = a.in_ptr[(valid ? node : (uint32_t)n0) - a.lo];
     uint64_t my_q1 = __shfl_down_sync(0xffffffffu, my_q0, 1);
     if (lane == nvalid - 1) my_q1 = a.in_ptr[node - a.lo + 1];
@@ -563,155 +588,100 @@ k_epoch_tiled(EpochArgs a, unsigned long long *sample_counter)
     const uint64_t Q1 = __shfl_sync(0xffffffffu, my_q1, nvalid - 1);
     // this owner's in-edge positions relative to the sweep cursor (advanced by 32 per round)
     int rel_lo = valid ? (int)(my_q0 - Q0) : 0x3fffffff, rel_hi = valid ? (int)(my_q1 - Q0) : 0x3fffffff;
-    const uint32_t n_in = (uint32_t)(Q1 - Q0);                  // in-edges of the tile
+    const uint32_t n_in = (uint32_t)(Q1 - Q0);                 // in-edges of the tile
+    if (n_in == 0) return;                                     // nothing to apply: y_next already holds the result
     const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
     const uint8_t *ownp = a.in_own + (Q0 - a.in_base) + lane;
-    if constexpr (DP <= 4) {
-        // No queue: the entries of a round stay in registers and owners pull theirs with shuffles, in lane (= index)
-        // order.  Pipelined two rounds deep: records of round r+2 and the source-row gathers of round r+1 are in
-        // flight while round r is applied.
-        uint4 rec2 = make_uint4(0, 0, 0, 0);                   // records of the round after next
-        uint32_t own2 = 0;
-        // prepared round: count, owner, record fields needed later, gathered source row
-        int nc = 0;
-        uint32_t nown = 0;
-        float nPl = 0.0f, nPh = 0.0f, nis2 = 0.0f, nys[DP];
+    float alpha_tot = 1.0f, beta_tot[DP];                      // composite of all rounds, applied once at the end
 #pragma unroll
-        for (int cc = 0; cc < DP; cc++) nys[cc] = 0.0f;
-        auto prepare = [&](const uint4 &rec, uint32_t own, bool have) {
-            nc = 0;
-            if (have) {
-                const float us = node_uniform(rec.x, a.epoch, a.k2);
-                nc = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
-            }
-            nown = own; nPl = as_float(rec.y); nPh = as_float(rec.z); nis2 = as_float(rec.w);
-            if (nc > 0) load_row<DP>(a.y_snap, rec.x, nys);
-        };
-        {
-            uint4 rec1 = make_uint4(0, 0, 0, 0);
-            uint32_t own1 = 0;
-            if (lane < n_in) { rec1 = __ldcs(recp); own1 = __ldcs(ownp); }
-            if (32 + lane < n_in) { rec2 = __ldcs(recp + 32); own2 = __ldcs(ownp + 32); }
-            prepare(rec1, own1, lane < n_in);
+    for (int c = 0; c < DP; c++) beta_tot[c] = 0.0f;
+
+    uint4 rec2 = make_uint4(0, 0, 0, 0);                       // records of the round after next
+    uint32_t own2 = 0;
+    int nc = 0;                                                // prepared round
+    uint32_t nown = 0;
+    float nPl = 0.0f, nPh = 0.0f, nis2 = 0.0f, nys[DP];
+#pragma unroll
+    for (int cc = 0; cc < DP; cc++) nys[cc] = 0.0f;
+    auto prepare = [&](const uint4 &rec, uint32_t own, bool have) {
+        nc = 0;
+        if (have) {
+            const float us = node_uniform(rec.x, a.epoch, a.k2);
+            nc = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
         }
-        __syncwarp();
-        for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
-            // take over the prepared round
-            const int c = nc;
-            const uint32_t own = nown;
-            const float Pl = nPl, Ph = nPh, is2 = nis2;
-            float ys[DP];
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) ys[cc] = nys[cc];
-            // prepare the next round (its records were loaded one iteration ago), fetch the records after it
-            {
-                const uint4 rec1 = rec2;
-                const uint32_t own1 = own2;
-                if (base_q + 64 + lane < n_in) { rec2 = __ldcs(recp + base_q + 64); own2 = __ldcs(ownp + base_q + 64); }
-                prepare(rec1, own1, base_q + 32 + lane < n_in);
-            }
-            const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
-            float A = 0.0f;
-            if (c > 0) {
-                float yr[DP];
-#pragma unroll
-                for (int cc = 0; cc < DP; cc++) yr[cc] = s_yref[own * DP + cc];
-                A = in_edge_factor(attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(Ph, Pl), is2, a.K), c);
-            }
-            // this owner's fired in-edges of the round: lanes [rel_lo, rel_hi) (in-edges are sorted by destination)
-            const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));
-            unsigned mine = 0;
-            if (hi_c > lo_c) mine = fired & ((0xffffffffu >> (32 - (hi_c - lo_c))) << lo_c);
-            rel_lo -= 32; rel_hi -= 32;
-            while (__any_sync(0xffffffffu, mine != 0)) {
-                const int b = mine ? __ffs(mine) - 1 : lane;
-                float t[DP];
-#pragma unroll
-                for (int cc = 0; cc < DP; cc++) t[cc] = __shfl_sync(0xffffffffu, ys[cc], b);
-                const float Ab = __shfl_sync(0xffffffffu, A, b);
-                if (mine) { apply_in_edge<DP>(y, t, Ab); mine &= mine - 1; }
-            }
-        }
-    } else {
-        uint32_t qcount = 0, seg_start = 0, seg_cnt = 0;           // queue fill (warp uniform); this owner's entries in it
-        auto flush = [&]() {
-            __syncwarp();
-            for (uint32_t t = seg_start, te = seg_start + seg_cnt; t < te; t++) {
-                float ys[DP];
-                float A;
-                if constexpr (DP == 2) {
-                    const float4 e4 = *reinterpret_cast<const float4 *>(s_q + t * QF);
-                    ys[0] = e4.x; ys[1] = e4.y; A = e4.z;
-                } else {
-    #pragma unroll
-                    for (int c = 0; c < DP; c += 4) {
-                        const float4 v = *reinterpret_cast<const float4 *>(s_q + t * QF + c);
-                        ys[c] = v.x; ys[c + 1] = v.y; ys[c + 2] = v.z; ys[c + 3] = v.w;
-                    }
-                    A = s_q[t * QF + DP];
-                }
-                apply_in_edge<DP>(y, ys, A);
-            }
-            __syncwarp();
-            qcount = 0; seg_cnt = 0;
-        };
-        uint4 rec_next = make_uint4(0, 0, 0, 0);
-        uint32_t own_next = 0;
-        if (lane < n_in) { rec_next = __ldcs(recp); own_next = __ldcs(ownp); }
-        __syncwarp();
-        for (uint64_t qb = Q0; qb < Q1; qb += 32) {
-            const uint4 rec = rec_next;
-            const uint32_t own = own_next;
-            const bool have = qb + lane < Q1;
-            if (qb + 32 + lane < Q1) {                             // prefetch the next round
-                rec_next = __ldcs(a.in_rec + (qb + 32 + lane - a.in_base));
-                own_next = __ldcs(a.in_own + (qb + 32 + lane - a.in_base));
-            }
-            int c = 0;
-            if (have) {
-                const float us = node_uniform(rec.x, a.epoch, a.k2);
-                c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
-            }
-            const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
-            if (c > 0) {
-                const uint32_t slot = qcount + __popc(fired & ((1u << lane) - 1u));
-                float ys[DP], yr[DP];
-                load_row<DP>(a.y_snap, rec.x, ys);
-    #pragma unroll
-                for (int cc = 0; cc < DP; cc++) yr[cc] = s_yref[own * DP + cc];
-                const float coef = attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(as_float(rec.z), as_float(rec.y)), as_float(rec.w), a.K);
-                const float A = in_edge_factor(coef, c);
-                if constexpr (DP == 2) {
-                    *reinterpret_cast<float4 *>(s_q + slot * QF) = make_float4(ys[0], ys[1], A, 0.0f);
-                } else {
-    #pragma unroll
-                    for (int cc = 0; cc < DP; cc++) s_q[slot * QF + cc] = ys[cc];
-                    s_q[slot * QF + DP] = A;
-                }
-            }
-            // which of this round's fired lanes belong to this owner (in-edges are sorted by destination)
-            {
-                const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));
-                if (hi_c > lo_c) {
-                    const unsigned range = (0xffffffffu >> (32 - (hi_c - lo_c))) << lo_c;
-                    const uint32_t mine = __popc(fired & range);
-                    if (mine) {
-                        if (seg_cnt == 0) seg_start = qcount + __popc(fired & ((1u << lo_c) - 1u));
-                        seg_cnt += mine;
-                    }
-                }
-                rel_lo -= 32; rel_hi -= 32;
-            }
-            qcount += __popc(fired);
-            if (qcount + 32 > EPOCH_QCAP) flush();
-        }
-        if (qcount) flush();
+        nown = own; nPl = as_float(rec.y); nPh = as_float(rec.z); nis2 = as_float(rec.w);
+        if (nc > 0) load_row<DP>(a.y_snap, rec.x, nys);
+    };
+    {
+        uint4 rec1 = make_uint4(0, 0, 0, 0);
+        uint32_t own1 = 0;
+        if (lane < n_in) { rec1 = __ldcs(recp); own1 = __ldcs(ownp); }
+        if (32 + lane < n_in) { rec2 = __ldcs(recp + 32); own2 = __ldcs(ownp + 32); }
+        prepare(rec1, own1, lane < n_in);
     }
-    if (valid) store_row<DP>(a.y_next, node, y);
-    unsigned int applied = (unsigned int)T;
+    for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
+        const int c = nc;
+        const uint32_t own = nown;
+        const float Pl = nPl, Ph = nPh, is2 = nis2;
+        float ys[DP];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) applied += __shfl_xor_sync(0xffffffffu, applied, o);
-    if (lane == 0 && applied) atomicAdd(sample_counter + (blockIdx.x & 255), (unsigned long long)applied);
+        for (int cc = 0; cc < DP; cc++) ys[cc] = nys[cc];
+        {   // prepare the next round (its records were loaded one iteration ago), fetch the records after it
+            const uint4 rec1 = rec2;
+            const uint32_t own1 = own2;
+            if (base_q + 64 + lane < n_in) { rec2 = __ldcs(recp + base_q + 64); own2 = __ldcs(ownp + base_q + 64); }
+            prepare(rec1, own1, base_q + 32 + lane < n_in);
+        }
+        // the affine map of this lane's in-edge: y -> alpha y + beta  (identity when it did not fire)
+        float alpha = 1.0f, beta[DP];
+#pragma unroll
+        for (int cc = 0; cc < DP; cc++) beta[cc] = 0.0f;
+        // reference position and segment start of this in-edge's owner
+        float yr[DP];
+#pragma unroll
+        for (int cc = 0; cc < DP; cc++) yr[cc] = __shfl_sync(0xffffffffu, y[cc], (int)own);
+        const int seg_lo = max(0, __shfl_sync(0xffffffffu, rel_lo, (int)own));
+        if (c > 0) {
+            const float A = in_edge_factor(attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(Ph, Pl), is2, a.K), c);
+            alpha = F_ADD(1.0f, A);
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) beta[cc] = F_MUL(-A, ys[cc]);
+        }
+        // segmented inclusive scan (composition in index order) over the lanes of each owner
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float ap = __shfl_up_sync(0xffffffffu, alpha, d);
+            float bp[DP];
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) bp[cc] = __shfl_up_sync(0xffffffffu, beta[cc], d);
+            if (lane - d >= seg_lo) {
+#pragma unroll
+                for (int cc = 0; cc < DP; cc++) beta[cc] = F_FMA(alpha, bp[cc], beta[cc]);
+                alpha = F_MUL(alpha, ap);
+            }
+        }
+        // owner: composite of its in-edges of this round sits in the last lane of its range
+        {
+            const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));
+            const bool mine = hi_c > lo_c;
+            const int src = mine ? hi_c - 1 : lane;
+            const float ar = __shfl_sync(0xffffffffu, alpha, src);
+            float br[DP];
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) br[cc] = __shfl_sync(0xffffffffu, beta[cc], src);
+            if (mine) {
+#pragma unroll
+                for (int cc = 0; cc < DP; cc++) beta_tot[cc] = F_FMA(ar, beta_tot[cc], br[cc]);
+                alpha_tot = F_MUL(ar, alpha_tot);
+            }
+            rel_lo -= 32; rel_hi -= 32;
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < DP; c++) y[c] = F_FMA(alpha_tot, y[c], beta_tot[c]);
+        store_row<DP>(a.y_next, node, y);
+    }
 }
 
 // K5: embedder.rs:1127-1163 + cauchy_edge_weight :1322-1345, fp64 like the reference
@@ -1308,16 +1278,13 @@ template <int DP, bool HUB, int KREG>
 static cudaError_t launch_tiled(annembed_cuda_ctx *ctx, const EpochArgs &a)
 {
     using TL = EpochTile<DP, KREG>;
-    static bool configured[64] = {false};
-    auto kern = k_epoch_tiled<DP, HUB, KREG>;
-    if (!configured[ctx->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM);
-        if (e != cudaSuccess) return e;
-        configured[ctx->device & 63] = true;
-    }
     const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;
     const unsigned int nb = (unsigned int)((tiles + TL::WARPS - 1) / TL::WARPS);
-    kern<<<nb, TL::WARPS * 32, TL::SMEM, ctx->stream>>>(a, ctx->counter.p);
+    k_epoch_out<DP, HUB, KREG><<<nb, TL::WARPS * 32, TL::SMEM, ctx->stream>>>(a, ctx->counter.p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const unsigned int nb2 = (unsigned int)((tiles + ANNEMBED_WARPS_IN - 1) / ANNEMBED_WARPS_IN);
+    k_epoch_in<DP><<<nb2, ANNEMBED_WARPS_IN * 32, 0, ctx->stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -1326,7 +1293,8 @@ static cudaError_t launch_epoch_dp(annembed_cuda_ctx *ctx, const EpochArgs &a)
 {
     if (a.hi <= a.lo) return cudaSuccess;
     const bool force_generic = (ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL) != 0;
-    const bool tiled_ok = !force_generic && ctx->prm.b == 1.0;     // the tiled kernel is specialised for b == 1
+    const bool tiled_ok = !force_generic && ctx->prm.b == 1.0;     // the tiled kernels are specialised for b == 1
+    ctx->last_epoch_kernels = (tiled_ok && ctx->kmax <= 16) ? 2 : 1;
     if (tiled_ok && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
     if (tiled_ok && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);
     k_epoch_generic<DP, HUB><<<nblocks(a.hi - a.lo, 256), 256, 0, ctx->stream>>>(a, ctx->counter.p);
@@ -1407,7 +1375,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
         if (ctx->nranks > 1) { CU(cudaEventElapsedTime(&t, ctx->ev[xoff + 2 * i], ctx->ev[xoff + 2 * i + 1])); xms += t; }
     }
     ctx->st.optimize_ms = ms; ctx->st.epoch_kernel_ms = kms; ctx->st.exchange_ms = xms;
-    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_launch;
+    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_launch * (ctx->last_epoch_kernels);
     ctx->st.positive_samples = cnt; ctx->st.edge_updates = 6 * cnt;
     ctx->st.model_bytes = (double)cnt * (12.0 + 36.0 * (double)ctx->prm.asked_dim);
     return ANNEMBED_OK;

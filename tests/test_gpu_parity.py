@@ -233,22 +233,24 @@ def test_epoch_kernel_matches_host_replay(d, hub):
 
 @pytest.mark.parametrize("d,kmax,hub", [(2, 6, False), (2, 14, True), (3, 8, False), (15, 10, False), (32, 5, False)])
 def test_tiled_epoch_kernel_equals_generic_kernel(d, kmax, hub):
-    """The warp-tiled K4 and the thread-per-node K4 run the same per-node program (same draws, same order)."""
+    """The warp-tiled K4 (k_epoch_out + k_epoch_in) and the thread-per-node K4 run the same per-node program: same
+    draws, same firings in the same order (bit-identical after the out-edge phase); the in-edge phase composes the
+    same affine maps with a warp scan instead of one after the other, so one mini-epoch agrees to fp32 rounding."""
     row_ptr, col, dist = random_graph(5000, 2, kmax, seed=72)
     y0 = np.random.default_rng(2).uniform(-1, 1, size=(5000, d)).astype(np.float32)
     outs = []
     for flags in (0, 1):                             # 1 = ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL
         ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=3, grad_step=1.0, seed=5, flags=flags,
-                      hubness_weighting=hub, mini_epochs_per_batch=4)
+                      hubness_weighting=hub, nb_sampling_by_edge=1, mini_epochs_per_batch=1)
         ctx.edge_weights(want_outputs=False)
         if hub:
             ctx.set_neg_weights(oracle.hubness_weights(row_ptr, col))
         ctx.set_embedding(y0)
-        ctx.optimize_batches(1, 1)
+        ctx.optimize_batches(1, 1)                   # exactly one mini-epoch
         outs.append((ctx.get_embedding(), ctx.get_stats()["positive_samples"]))
     assert outs[0][1] == outs[1][1]
-    # both kernels inline the same explicitly-rounded device functions in the same order: bit-identical layouts
-    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert np.abs(outs[0][0] - y0).max() > 1e-2
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=2e-5)
 
 
 def test_rows_longer_than_16_use_the_generic_kernel():
