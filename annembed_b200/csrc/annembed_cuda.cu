@@ -1248,6 +1248,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
     a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;
+    a.grouped_neg = (ctx->prm.flags & ANNEMBED_FLAG_GROUPED_NEGATIVES) ? 1u : 0u;
     a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);
     a.n = (uint32_t)ctx->n; a.lo = ctx->lo; a.hi = ctx->hi;
     a.epoch = epoch;

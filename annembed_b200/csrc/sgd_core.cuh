@@ -229,6 +229,7 @@ struct EpochArgs {
     const float *__restrict__ cum;       // v2: inclusive cumulative probability along each row (last entry exactly 1)
     uint32_t k2;                         // v2: Philox2x32 key of the per-node uniform
     uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
+    uint32_t grouped_neg;                // ANNEMBED_FLAG_GROUPED_NEGATIVES: 4 of the 5 negatives share one 32-byte sector
     uint32_t n, lo, hi;
     uint32_t epoch, k0, k1;
     float kappa;                        // expected firings of edge e in this mini-epoch = kappa * p_e
@@ -416,10 +417,15 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
         const Philox4 D = philox4x32_10(node, s, a.epoch, 4u, a.k0, a.k1);
         wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = D.x;
     }
+    // grouped mode (uniform sampler only): negatives 0..3 are the 4 nodes of one uniformly drawn 32-byte sector of
+    // the layout (ids 4g..4g+3), negative 4 is an independent draw.  Every node keeps marginal probability 1/n per
+    // slot; a rejected / out-of-range member is replaced by an independent redraw like any other negative.
+    const bool grouped = !HUB && a.grouped_neg != 0u;
+    const uint32_t gbase = grouped ? (below32(A.x, (a.n + 3u) >> 2) << 2) : 0u;
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-        uint32_t k = map_negative<HUB>(a, wi[q], wa[q]);
-        bool rej = rejected(k);
+        uint32_t k = (grouped && q < 4) ? gbase + (uint32_t)q : map_negative<HUB>(a, wi[q], wa[q]);
+        bool rej = k >= a.n || rejected(k);
         for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
             const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
             k = map_negative<HUB>(a, R.x, R.y);

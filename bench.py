@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--batches", type=int, default=40)
     ap.add_argument("--mini-epochs", type=int, default=0)
     ap.add_argument("--hubness", type=int, default=0)
+    ap.add_argument("--flags", type=int, default=0, help="ANNEMBED_FLAG_* bits (4 = grouped negatives, opt-in)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per bounded oracle sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -79,7 +80,7 @@ def params_for(a):
     import annembed_b200 as A
     return A.EmbedderParams(asked_dim=a.dim, dmap_init=False, beta=1.0, b=1.0, scale_rho=0.75, grad_step=1.0,
                             nb_sampling_by_edge=10, nb_grad_batch=a.batches, hubness_weighting=bool(a.hubness),
-                            mini_epochs_per_batch=a.mini_epochs, seed=0xB200)
+                            mini_epochs_per_batch=a.mini_epochs, seed=0xB200, flags=a.flags)
 
 
 class ClockSampler:
@@ -292,7 +293,7 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * elapsed_max / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "mini_epochs_per_batch": int(mini),
+            "config": {"workload": workload_name(a), "mini_epochs_per_batch": int(mini), "flags": a.flags,
                        "l2_persist_max_bytes": int(st["l2_persist_max_bytes"]), "l2_window_max_bytes": int(st["l2_window_max_bytes"]),
                        "l2": "inputs larger than L2 (graph + transposed index > 2 GB per pass); no flush needed",
                        "parallelism": f"node-sharded x{world}, replicated layout, all-gather per mini-epoch" if world > 1 else "single GPU",

@@ -11,6 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 Ms = [int(a) for a in sys.argv[3:]] or [0]
 RUNS, NBNG = 4, 50
+FLAGS = int(os.environ.get('ANNEMBED_FLAGS', '0'))
 x, _ = workloads.gaussian_mixture(n, 784, seed=0)
 idx, dist = workloads.knn_exact(x, k, device="cuda")
 row_ptr, col, dist = workloads.csr_from_knn(idx, dist)
@@ -29,7 +30,7 @@ summarize("oracle hogwild", ys, (time.time() - t) / RUNS)
 for M in Ms:
     ys = []; t = time.time()
     for s in range(RUNS):
-        ctx = A.CudaContext(A.EmbedderParams(nb_grad_batch=30, grad_step=1.0, seed=100 + s, mini_epochs_per_batch=M))
+        ctx = A.CudaContext(A.EmbedderParams(nb_grad_batch=30, grad_step=1.0, seed=100 + s, mini_epochs_per_batch=M, flags=FLAGS))
         ctx.set_graph_csr(row_ptr, col, dist); ctx.edge_weights(want_outputs=False); ctx.set_embedding(y0)
         ctx.optimize(want_ce=False); ys.append(ctx.get_embedding()); Meff = ctx.get_stats()["mini_epochs_per_batch"]; ctx.close()
-    summarize(f"cuda M={Meff}", ys, (time.time() - t) / RUNS)
+    summarize(f"cuda M={Meff} flags={FLAGS}", ys, (time.time() - t) / RUNS)
