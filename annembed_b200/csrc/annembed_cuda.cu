@@ -88,6 +88,9 @@ struct annembed_cuda_ctx {
     DevBuf<uint64_t> in_ptr_all;   // n+1, transposed index of the whole graph
     DevBuf<uint4> in_rec;          // in-edge records of the owned slice
     DevBuf<uint8_t> in_own;        // owner lane of each record in its warp tile
+    DevBuf<uint32_t> in_src, in_eid; // structure of the transposed index (graph only)
+    uint64_t in_cnt = 0;
+    bool have_struct = false;
     uint64_t in_base = 0;
     DevBuf<uint2> neg_alias;
     DevBuf<float> y[2], y0;
@@ -303,19 +306,31 @@ __global__ void k_in_ptr(uint64_t E, uint64_t n, const uint32_t *__restrict__ so
     for (uint64_t v = prev; v < curr; v++) in_ptr[v] = q;
 }
 
-__global__ void k_in_rec(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_t *__restrict__ sorted_eid,
-                         const uint32_t *__restrict__ sorted_dst, uint32_t lo, const uint64_t *__restrict__ row_ptr,
-                         const float *__restrict__ cum, const float *__restrict__ inv_s2, uint4 *__restrict__ rec,
-                         uint8_t *__restrict__ own)
+// structure of the transposed index (depends on the graph only): source node, edge id and owner lane of every
+// owned in-edge, in (destination, edge id) order
+__global__ void k_in_struct(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_t *__restrict__ sorted_eid,
+                            const uint32_t *__restrict__ sorted_dst, uint32_t lo, const uint64_t *__restrict__ row_ptr,
+                            uint32_t *__restrict__ in_src, uint32_t *__restrict__ in_eid, uint8_t *__restrict__ own)
 {
     const uint64_t q = q_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= q_hi) return;
     const uint32_t e = sorted_eid[q];
     uint64_t a = 0, b = n;                       // largest i with row_ptr[i] <= e
     while (b - a > 1) { const uint64_t mid = (a + b) >> 1; if (row_ptr[mid] <= e) a = mid; else b = mid; }
-    const float P_lo = (row_ptr[a] == e) ? 0.0f : cum[e - 1];
-    rec[q - q_lo] = make_uint4((uint32_t)a, __float_as_uint(P_lo), __float_as_uint(cum[e]), __float_as_uint(inv_s2[a]));
+    in_src[q - q_lo] = (uint32_t)a;
+    in_eid[q - q_lo] = e;
     own[q - q_lo] = (uint8_t)((sorted_dst[q] - lo) & 31u);
+}
+// payload (depends on the weights): {src, P_lo, P_hi, 1/s_src^2}
+__global__ void k_in_rec(uint64_t cnt, const uint32_t *__restrict__ in_src, const uint32_t *__restrict__ in_eid,
+                         const uint64_t *__restrict__ row_ptr, const float *__restrict__ cum,
+                         const float *__restrict__ inv_s2, uint4 *__restrict__ rec)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= cnt) return;
+    const uint32_t src = in_src[q], e = in_eid[q];
+    const float P_lo = (row_ptr[src] == e) ? 0.0f : cum[e - 1];
+    rec[q] = make_uint4(src, __float_as_uint(P_lo), __float_as_uint(cum[e]), __float_as_uint(inv_s2[src]));
 }
 
 __global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint32_t *__restrict__ out)
@@ -910,7 +925,7 @@ extern "C" int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, c
     REQUIRE(E < 0xFFFFFFFFull, ANNEMBED_ERR_UNSUPPORTED, "E >= 2^32-1 not supported");
     REQUIRE(E >= 1, ANNEMBED_ERR_EMPTY_ROW, "graph has no edge (node 0 has no neighbour)");
     CU(cudaSetDevice(ctx->device));
-    ctx->have_graph = ctx->have_weights = ctx->have_build = ctx->have_embedding = false;
+    ctx->have_graph = ctx->have_weights = ctx->have_build = ctx->have_embedding = ctx->have_struct = false;
     ctx->n = n; ctx->E = E;
     set_shard(ctx);
     CU(ctx->row_ptr.alloc(n + 1)); CU(ctx->col.alloc(E)); CU(ctx->dist.alloc(E)); CU(ctx->rho.alloc(n));
@@ -1062,47 +1077,68 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
 }
 
 // device context build: K2 + transposed index (≙ EntropyOptim::new, embedder.rs:964-1025)
+// transposed index of the graph (≙ nothing in the reference: its symmetric move writes y_j under a lock,
+// embedder.rs:1239).  Depends on the graph and the shard only; built once per set_graph_csr.
+static int ensure_struct(annembed_cuda_ctx *ctx)
+{
+    if (ctx->have_struct) return ANNEMBED_OK;
+    const uint64_t n = ctx->n, E = ctx->E;
+    int rc;
+    CU(ctx->in_ptr_all.alloc(n + 2));
+    DevBuf<uint32_t> eid, dst_sorted, eid_sorted;
+    DevBuf<unsigned char> tmp;
+    CU(eid.alloc(E)); CU(dst_sorted.alloc(E)); CU(eid_sorted.alloc(E));
+    k_iota<<<nblocks(E, 256), 256, 0, ctx->stream>>>(E, eid.p);
+    int bits = 1; while (bits < 32 && (1ull << bits) < n) bits++;
+    size_t tmp_bytes = 0;
+    // stable radix sort of (dst, edge id): in-edges of a node stay in edge-id order
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
+    CU(tmp.alloc(tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
+    k_in_ptr<<<nblocks(E + 1, 256), 256, 0, ctx->stream>>>(E, n, dst_sorted.p, ctx->in_ptr_all.p);
+    ctx->st.kernel_launches += 3;
+    uint64_t qr[2];
+    CU(cudaMemcpyAsync(&qr[0], ctx->in_ptr_all.p + ctx->lo, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&qr[1], ctx->in_ptr_all.p + ctx->hi, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = sync_stream(ctx))) return rc;
+    ctx->in_base = qr[0];
+    const uint64_t cnt = qr[1] - qr[0];
+    ctx->in_cnt = cnt;
+    CU(ctx->in_rec.alloc(std::max<uint64_t>(cnt, 1)));
+    CU(ctx->in_own.alloc(std::max<uint64_t>(cnt, 1)));
+    CU(ctx->in_src.alloc(std::max<uint64_t>(cnt, 1)));
+    CU(ctx->in_eid.alloc(std::max<uint64_t>(cnt, 1)));
+    if (cnt) {
+        k_in_struct<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, dst_sorted.p, ctx->lo, ctx->row_ptr.p,
+                                                                ctx->in_src.p, ctx->in_eid.p, ctx->in_own.p);
+        ctx->st.kernel_launches++;
+    }
+    if ((rc = sync_stream(ctx))) return rc;
+    ctx->have_struct = true;
+    return ANNEMBED_OK;
+}
+
+// device context build: K2 + cumulative row probabilities + in-edge payloads (≙ EntropyOptim::new, embedder.rs:964-1025)
 static int ensure_build(annembed_cuda_ctx *ctx)
 {
     if (ctx->have_build) return ANNEMBED_OK;
     REQUIRE(ctx->have_weights, ANNEMBED_ERR_STATE, "edge weights not computed (embedder.rs:802-808: initial_space not constructed)");
     const uint64_t n = ctx->n, E = ctx->E;
+    int rc;
     CU(cudaEventRecord(ctx->ev_a, ctx->stream));
-    CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); CU(ctx->in_ptr_all.alloc(n + 2)); CU(ctx->cum.alloc(E));
+    if ((rc = ensure_struct(ctx))) return rc;
+    if (ctx->emb_scale.n != n) { CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); }
+    if (ctx->cum.n != E) CU(ctx->cum.alloc(E));
     k_row_cumsum<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr.p, ctx->proba.p, ctx->cum.p);
     ctx->st.kernel_launches++;
-    int rc;
     // K2
     if ((rc = sum_f64(ctx, ctx->scale.p, n, ctx->partials.p + 4095))) return rc;
     k_embedded_scales<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->scale.p, ctx->partials.p + 4095, ctx->emb_scale.p, ctx->inv_s2.p);
     ctx->st.kernel_launches++;
-    // transposed index: stable radix sort of (dst, edge id)
-    {
-        DevBuf<uint32_t> eid, dst_sorted, eid_sorted;
-        DevBuf<unsigned char> tmp;
-        CU(eid.alloc(E)); CU(dst_sorted.alloc(E)); CU(eid_sorted.alloc(E));
-        k_iota<<<nblocks(E, 256), 256, 0, ctx->stream>>>(E, eid.p);
-        int bits = 1; while (bits < 32 && (1ull << bits) < n) bits++;
-        size_t tmp_bytes = 0;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
-        CU(tmp.alloc(tmp_bytes));
-        CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
-        k_in_ptr<<<nblocks(E + 1, 256), 256, 0, ctx->stream>>>(E, n, dst_sorted.p, ctx->in_ptr_all.p);
-        ctx->st.kernel_launches += 3;
-        uint64_t qr[2];
-        CU(cudaMemcpyAsync(&qr[0], ctx->in_ptr_all.p + ctx->lo, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(&qr[1], ctx->in_ptr_all.p + ctx->hi, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if ((rc = sync_stream(ctx))) return rc;
-        ctx->in_base = qr[0];
-        const uint64_t cnt = qr[1] - qr[0];
-        CU(ctx->in_rec.alloc(std::max<uint64_t>(cnt, 1)));
-        CU(ctx->in_own.alloc(std::max<uint64_t>(cnt, 1)));
-        if (cnt) {
-            k_in_rec<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, dst_sorted.p, ctx->lo, ctx->row_ptr.p,
-                                                                 ctx->cum.p, ctx->inv_s2.p, ctx->in_rec.p, ctx->in_own.p);
-            ctx->st.kernel_launches++;
-        }
-        if ((rc = sync_stream(ctx))) return rc;
+    if (ctx->in_cnt) {
+        k_in_rec<<<nblocks(ctx->in_cnt, 256), 256, 0, ctx->stream>>>(ctx->in_cnt, ctx->in_src.p, ctx->in_eid.p, ctx->row_ptr.p, ctx->cum.p,
+                                                                     ctx->inv_s2.p, ctx->in_rec.p);
+        ctx->st.kernel_launches++;
     }
     CU(cudaEventRecord(ctx->ev_b, ctx->stream));
     if ((rc = sync_stream(ctx))) return rc;
@@ -1118,14 +1154,10 @@ extern "C" int annembed_cuda_get_hubness_counts(annembed_cuda_ctx *ctx, uint32_t
     REQUIRE(counts, ANNEMBED_ERR_INVALID_ARG, "null output");
     REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "get_hubness_counts: graph not set");
     CU(cudaSetDevice(ctx->device));
-    // in-degree = histogram of col; independent of the weights: sort-free path through atomics is not needed,
-    // the transposed index gives it when built, else build a throw-away one.
-    if (!ctx->have_build) {
-        const bool hw = ctx->have_weights;
-        if (!hw) { CU(cudaMemsetAsync(ctx->scale.p, 0, ctx->n * sizeof(float), ctx->stream)); CU(cudaMemsetAsync(ctx->proba.p, 0, ctx->E * sizeof(float), ctx->stream)); ctx->have_weights = true; }
-        int rc = ensure_build(ctx);
-        if (!hw) { ctx->have_weights = false; ctx->have_build = false; }
-        if (rc) return rc;
+    // in-degree of every node = segment lengths of the transposed index (graph only)
+    {
+        int rc0 = ensure_struct(ctx);
+        if (rc0) return rc0;
     }
     DevBuf<uint32_t> t; CU(t.alloc(ctx->n));
     k_degree_u32<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->in_ptr_all.p, t.p);
