@@ -891,7 +891,9 @@ extern "C" int annembed_cuda_comm_unique_id(uint8_t unique_id[128])
 static void set_shard(annembed_cuda_ctx *ctx)
 {
     const uint64_t n = ctx->n;
-    ctx->n_pad = (uint32_t)((n + ctx->nranks - 1) / ctx->nranks);
+    // shards are whole warp tiles (32 nodes): every node then sits in the same tile, and its in-edges in the same
+    // sweep rounds, for any number of ranks -> bit-identical layouts for any R
+    ctx->n_pad = (uint32_t)((((n + ctx->nranks - 1) / ctx->nranks) + 31) / 32 * 32);
     ctx->lo = (uint32_t)std::min<uint64_t>(n, (uint64_t)ctx->rank * ctx->n_pad);
     ctx->hi = (uint32_t)std::min<uint64_t>(n, (uint64_t)(ctx->rank + 1) * ctx->n_pad);
 }

@@ -12,7 +12,7 @@ import numpy as np
 
 def shard_range(n: int, rank: int, nranks: int) -> tuple[int, int]:
     """Owned node range of `rank` -- must match set_shard() in csrc/annembed_cuda.cu."""
-    n_pad = (n + nranks - 1) // nranks
+    n_pad = ((n + nranks - 1) // nranks + 31) // 32 * 32          # whole warp tiles per shard
     return min(n, rank * n_pad), min(n, (rank + 1) * n_pad)
 
 

@@ -28,4 +28,4 @@ def test_unique_id_broadcast_and_shards(tmp_path):
     r0, r1 = (np.load(tmp_path / f"r{r}.npy") for r in range(world))
     np.testing.assert_array_equal(r0[:128], (np.arange(128) * 7 % 251))
     np.testing.assert_array_equal(r0[:128], r1[:128])
-    assert r0[128] == 0 and r0[129] == r1[128] == 501 and r1[129] == n
+    assert r0[128] == 0 and r0[129] == r1[128] == 512 and r1[129] == n

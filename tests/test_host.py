@@ -53,8 +53,8 @@ def test_shard_ranges_partition_nodes():
             ranges = [shard_range(n, k, r) for k in range(r)]
             assert ranges[0][0] == 0 and ranges[-1][1] == n
             assert all(ranges[i][1] == ranges[i + 1][0] for i in range(r - 1))
-            pad = (n + r - 1) // r
-            assert all(hi - lo <= pad for lo, hi in ranges)
+            pad = ((n + r - 1) // r + 31) // 32 * 32
+            assert all(hi - lo <= pad and (lo % 32 == 0 or lo == n) for lo, hi in ranges)
 
 
 def test_philox4x32_10_known_answers():
