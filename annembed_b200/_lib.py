@@ -50,6 +50,8 @@ SYMBOLS = [
     ("annembed_cuda_last_error", C.c_char_p, [_ctx]),
     ("annembed_cuda_comm_unique_id", C.c_int, [u8p]),
     ("annembed_cuda_comm_init", C.c_int, [_ctx, C.c_int, C.c_int, u8p]),
+    ("annembed_cuda_comm_export_layout", C.c_int, [_ctx, u8p]),
+    ("annembed_cuda_comm_import_layouts", C.c_int, [_ctx, u8p]),
     ("annembed_cuda_set_graph_csr", C.c_int, [_ctx, C.c_uint64, u64p, u32p, f32p]),
     ("annembed_cuda_edge_weights", C.c_int, [_ctx, f32p, f32p]),
     ("annembed_cuda_edge_weights_umap", C.c_int, [_ctx, C.c_float, f32p, f32p, u8p]),

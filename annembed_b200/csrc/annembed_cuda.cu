@@ -101,6 +101,9 @@ struct annembed_cuda_ctx {
     int rank = 0, nranks = 1;
     uint32_t lo = 0, hi = 0, n_pad = 0;
     ncclComm_t comm = nullptr;
+    float *peer_y[8][2] = {};      // fused exchange: the two layout buffers of every rank, opened through CUDA IPC
+    bool have_peers = false;
+    DevBuf<float> barrier_buf;
 
     // scratch
     DevBuf<double> partials;
@@ -111,6 +114,9 @@ struct annembed_cuda_ctx {
 
     annembed_cuda_stats st{};
 };
+
+static void close_peers(annembed_cuda_ctx *ctx);
+static int alloc_layout(annembed_cuda_ctx *ctx);
 
 #define CU(call)                                                                                     \
     do {                                                                                             \
@@ -604,7 +610,11 @@ k_epoch_in(EpochArgs a)
     // this owner's in-edge positions relative to the sweep cursor (advanced by 32 per round)
     int rel_lo = valid ? (int)(my_q0 - Q0) : 0x3fffffff, rel_hi = valid ? (int)(my_q1 - Q0) : 0x3fffffff;
     const uint32_t n_in = (uint32_t)(Q1 - Q0);                 // in-edges of the tile
-    if (n_in == 0) return;                                     // nothing to apply: y_next already holds the result
+    if (n_in == 0) {                                           // nothing to apply: y_next already holds the result
+        if (valid)
+            for (uint32_t pr = 0; pr < a.n_peers; pr++) store_row<DP>(a.peer_next[pr], node, y);
+        return;
+    }
     const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
     const uint8_t *ownp = a.in_own + (Q0 - a.in_base) + lane;
     float alpha_tot = 1.0f, beta_tot[DP];                      // composite of all rounds, applied once at the end
@@ -696,6 +706,9 @@ k_epoch_in(EpochArgs a)
 #pragma unroll
         for (int c = 0; c < DP; c++) y[c] = F_FMA(alpha_tot, y[c], beta_tot[c]);
         store_row<DP>(a.y_next, node, y);
+        // fused exchange: the owner writes its row straight into every peer's replica (NVLink P2P stores, coalesced
+        // 32 rows per warp) while other tiles are still computing; a tiny all-reduce closes the mini-epoch
+        for (uint32_t pr = 0; pr < a.n_peers; pr++) store_row<DP>(a.peer_next[pr], node, y);
     }
 }
 
@@ -868,6 +881,7 @@ extern "C" int annembed_cuda_destroy(annembed_cuda_ctx *ctx)
     if (!ctx) return ANNEMBED_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    close_peers(ctx);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (auto ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -915,6 +929,29 @@ extern "C" int annembed_cuda_comm_init(annembed_cuda_ctx *ctx, int rank, int nra
     return ANNEMBED_OK;
 }
 
+static void close_peers(annembed_cuda_ctx *ctx)
+{
+    if (!ctx->have_peers) return;
+    for (int r = 0; r < ctx->nranks && r < 8; r++)
+        for (int b = 0; b < 2; b++)
+            if (r != ctx->rank && ctx->peer_y[r][b]) { cudaIpcCloseMemHandle(ctx->peer_y[r][b]); ctx->peer_y[r][b] = nullptr; }
+    ctx->have_peers = false;
+}
+
+// the two layout buffers + the initial copy; sized for whole tiles per rank so that the all-gather is uniform
+static int alloc_layout(annembed_cuda_ctx *ctx)
+{
+    const uint64_t rows = (uint64_t)ctx->n_pad * ctx->nranks;
+    const size_t want = (size_t)rows * ctx->DP;
+    if (ctx->y[0].n == want) return ANNEMBED_OK;
+    close_peers(ctx);
+    CU(ctx->y[0].alloc(want)); CU(ctx->y[1].alloc(want)); CU(ctx->y0.alloc(want));
+    CU(cudaMemsetAsync(ctx->y[0].p, 0, want * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(ctx->y[1].p, 0, want * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(ctx->y0.p, 0, want * sizeof(float), ctx->stream));
+    return ANNEMBED_OK;
+}
+
 extern "C" int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, const uint64_t *row_ptr,
                                            const uint32_t *col, const float *dist)
 {
@@ -933,6 +970,7 @@ extern "C" int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, c
     CU(ctx->row_ptr.alloc(n + 1)); CU(ctx->col.alloc(E)); CU(ctx->dist.alloc(E)); CU(ctx->rho.alloc(n));
     CU(ctx->scale.alloc(n)); CU(ctx->proba.alloc(E));
     int rc;
+    if ((rc = alloc_layout(ctx))) return rc;
     if ((rc = h2d(ctx, ctx->row_ptr.p, row_ptr, (n + 1) * sizeof(uint64_t)))) return rc;
     if ((rc = h2d(ctx, ctx->col.p, col, E * sizeof(uint32_t)))) return rc;
     if ((rc = h2d(ctx, ctx->dist.p, dist, E * sizeof(float)))) return rc;
@@ -970,6 +1008,45 @@ extern "C" int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, c
     if ((rc = sync_stream(ctx))) return rc;
     ctx->have_graph = true;
     return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_comm_export_layout(annembed_cuda_ctx *ctx, uint8_t handles[128])
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(handles, ANNEMBED_ERR_INVALID_ARG, "null output");
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "comm_export_layout: graph not set (the layout buffers are sized by it)");
+    CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    for (int b = 0; b < 2; b++) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ctx->y[b].p));
+        memcpy(handles + 64 * b, &h, 64);
+    }
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_comm_import_layouts(annembed_cuda_ctx *ctx, const uint8_t *all_handles)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(all_handles, ANNEMBED_ERR_INVALID_ARG, "null handles");
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "comm_import_layouts: graph not set");
+    REQUIRE(ctx->nranks > 1 && ctx->comm, ANNEMBED_ERR_STATE, "comm_import_layouts: comm_init with nranks > 1 first");
+    REQUIRE(ctx->nranks <= 8, ANNEMBED_ERR_UNSUPPORTED, "fused exchange supports up to 8 ranks (one NVSwitch domain)");
+    CU(cudaSetDevice(ctx->device));
+    close_peers(ctx);
+    for (int r = 0; r < ctx->nranks; r++)
+        for (int b = 0; b < 2; b++) {
+            if (r == ctx->rank) { ctx->peer_y[r][b] = ctx->y[b].p; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + (size_t)r * 128 + 64 * b, 64);
+            void *p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->peer_y[r][b] = (float *)p;
+        }
+    CU(ctx->barrier_buf.alloc(4));
+    CU(cudaMemsetAsync(ctx->barrier_buf.p, 0, 4 * sizeof(float), ctx->stream));
+    ctx->have_peers = true;
+    return sync_stream(ctx);
 }
 
 extern "C" int annembed_cuda_edge_weights(annembed_cuda_ctx *ctx, float *scale_out, float *proba_out)
@@ -1175,15 +1252,10 @@ extern "C" int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *
     REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_embedding: graph not set");
     REQUIRE(y, ANNEMBED_ERR_INVALID_ARG, "null embedding");
     CU(cudaSetDevice(ctx->device));
-    const uint64_t n = ctx->n, rows = (uint64_t)ctx->n_pad * ctx->nranks;
+    const uint64_t n = ctx->n;
     const int d = (int)ctx->prm.asked_dim, DP = ctx->DP;
-    if (ctx->y[0].n != rows * DP) {
-        CU(ctx->y[0].alloc(rows * DP)); CU(ctx->y[1].alloc(rows * DP)); CU(ctx->y0.alloc(rows * DP));
-        CU(cudaMemsetAsync(ctx->y[0].p, 0, rows * DP * sizeof(float), ctx->stream));
-        CU(cudaMemsetAsync(ctx->y[1].p, 0, rows * DP * sizeof(float), ctx->stream));
-        CU(cudaMemsetAsync(ctx->y0.p, 0, rows * DP * sizeof(float), ctx->stream));
-    }
     int rc;
+    if ((rc = alloc_layout(ctx))) return rc;
     if (d == DP) {
         if ((rc = h2d(ctx, ctx->y0.p, y, n * d * sizeof(float)))) return rc;
     } else {
@@ -1283,6 +1355,8 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.cum = ctx->cum.p;
     a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;
     a.grouped_neg = (ctx->prm.flags & ANNEMBED_FLAG_GROUPED_NEGATIVES) ? 1u : 0u;
+    a.n_peers = 0;
+    for (int r = 0; r < 7; r++) a.peer_next[r] = nullptr;
     a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);
     a.n = (uint32_t)ctx->n; a.lo = ctx->lo; a.hi = ctx->hi;
     a.epoch = epoch;
@@ -1369,6 +1443,9 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     const uint32_t nb = ctx->prm.nb_grad_batch, M = eff_mini_epochs(ctx);
     const uint32_t last = std::min<uint64_t>((uint64_t)first_batch + n_batches, (uint64_t)nb + 1);   // exclusive
     const size_t n_launch = first_batch < last ? (size_t)(last - first_batch) * M : 0;
+    // fused exchange needs the tiled kernels (k_epoch_in does the peer stores)
+    const bool fused = ctx->nranks > 1 && ctx->have_peers && ctx->prm.b == 1.0 && ctx->kmax <= 16 &&
+                       !(ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL);
     while (ctx->ev.size() < 2 * n_launch + 2 * n_launch * (ctx->nranks > 1)) {
         cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
     }
@@ -1379,18 +1456,28 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     for (uint32_t iter = first_batch; iter < last; iter++) {
         const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
         for (uint32_t m = 0; m < M; m++, li++) {
-            const EpochArgs a = make_epoch_args(ctx, (iter - 1) * M + m, grad_step);
+            EpochArgs a = make_epoch_args(ctx, (iter - 1) * M + m, grad_step);
+            if (fused) {
+                for (int r = 0; r < ctx->nranks; r++)
+                    if (r != ctx->rank) a.peer_next[a.n_peers++] = ctx->peer_y[r][ctx->cur ^ 1];
+            }
             set_l2_window(ctx, a.y_snap, (size_t)ctx->n * ctx->DP * sizeof(float));
             CU(cudaEventRecord(ctx->ev[2 * li], ctx->stream));
             CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
             CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
             if (ctx->nranks > 1) {
-                // replicate the updated rows: in-place all-gather of the owned slice of y_next
-                float *buf = ctx->y[ctx->cur ^ 1].p;
-                const size_t cnt = (size_t)ctx->n_pad * ctx->DP;
                 CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
-                ncclResult_t r = g_nccl.AllGather(buf + (size_t)ctx->rank * cnt, buf, cnt, ncclFloat, ctx->comm, ctx->stream);
-                if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+                if (fused) {
+                    // the in-edge kernel already stored the owned rows into every replica: only a barrier is left
+                    ncclResult_t r = g_nccl.AllReduce(ctx->barrier_buf.p, ctx->barrier_buf.p + 1, 1, ncclFloat, ncclSum, ctx->comm, ctx->stream);
+                    if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce (barrier): ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+                } else {
+                    // replicate the updated rows: in-place all-gather of the owned slice of y_next
+                    float *buf = ctx->y[ctx->cur ^ 1].p;
+                    const size_t cnt = (size_t)ctx->n_pad * ctx->DP;
+                    ncclResult_t r = g_nccl.AllGather(buf + (size_t)ctx->rank * cnt, buf, cnt, ncclFloat, ctx->comm, ctx->stream);
+                    if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+                }
                 CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream));
             }
             ctx->cur ^= 1;

@@ -229,6 +229,8 @@ struct EpochArgs {
     const float *__restrict__ cum;       // v2: inclusive cumulative probability along each row (last entry exactly 1)
     uint32_t k2;                         // v2: Philox2x32 key of the per-node uniform
     uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
+    uint32_t n_peers;                    // fused exchange: replicas of y_next on the other ranks (peer memory over NVLink)
+    float *peer_next[7];
     uint32_t grouped_neg;                // ANNEMBED_FLAG_GROUPED_NEGATIVES: 4 of the 5 negatives share one 32-byte sector
     uint32_t n, lo, hi;
     uint32_t epoch, k0, k1;

@@ -38,3 +38,18 @@ def broadcast_unique_id(make_id, rank: int, nranks: int) -> np.ndarray | None:
         t.copy_(torch.from_numpy(uid))
     dist.broadcast(t, src=0)
     return t.cpu().numpy().copy()
+
+
+def exchange_layout_handles(ctx, rank: int, nranks: int) -> None:
+    """Fused exchange set-up: all-gather the CUDA IPC handles of every rank's layout buffers (2 x 64 bytes each)
+    through torch.distributed and open them in `ctx` (annembed_cuda_comm_import_layouts)."""
+    if nranks == 1:
+        return
+    import torch
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.from_numpy(ctx.export_layout()).to(dev)
+    allh = torch.zeros(nranks * 128, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine)
+    ctx.import_layouts(allh.cpu().numpy())

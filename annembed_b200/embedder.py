@@ -69,6 +69,15 @@ class CudaContext:
         uid = None if unique_id is None else np.ascontiguousarray(unique_id, np.uint8)
         self._ck(self.lib.annembed_cuda_comm_init(self.h, rank, nranks, ptr(uid, C.c_uint8)))
 
+    def export_layout(self) -> np.ndarray:
+        out = np.zeros(128, np.uint8)
+        self._ck(self.lib.annembed_cuda_comm_export_layout(self.h, ptr(out, C.c_uint8)))
+        return out
+
+    def import_layouts(self, all_handles: np.ndarray):
+        h = np.ascontiguousarray(all_handles, np.uint8).reshape(-1)
+        self._ck(self.lib.annembed_cuda_comm_import_layouts(self.h, ptr(h, C.c_uint8)))
+
     # --- graph / weights
     def set_graph_csr(self, row_ptr, col, dist):
         row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
@@ -188,7 +197,7 @@ class Embedder:
     """≙ `Embedder<'a, F>` (embedder.rs:84-100) restricted to the one-step path (`Embedder::new`, :107)."""
 
     def __init__(self, kgraph: KGraph, parameters: EmbedderParams, initial_embedding: np.ndarray | None = None,
-                 device: int = 0, comm: tuple | None = None):
+                 device: int = 0, comm: tuple | None = None, fused_exchange: bool = True):
         self.kgraph = kgraph                     # borrowed, like &'a KGraph<F>
         self.parameters = parameters             # copied by value in the reference (EmbedderParams: Copy)
         self.initial_embedding = None if initial_embedding is None else np.ascontiguousarray(initial_embedding, np.float32)
@@ -197,6 +206,7 @@ class Embedder:
         self.cross_entropy = (None, None)
         self.device = device
         self.comm = comm                          # (rank, nranks, unique_id) or None
+        self.fused_exchange = fused_exchange      # peer-memory stores from the epoch kernel instead of an all-gather
         self.stats = {}
 
     # --- parameter getters, embedder.rs:135-153
@@ -230,6 +240,9 @@ class Embedder:
                 ctx.comm_init(*self.comm)
             row_ptr, col, dist = self.kgraph.get_neighbours()
             ctx.set_graph_csr(row_ptr, col, dist)
+            if self.comm is not None and self.comm[1] > 1 and self.fused_exchange:
+                from .dist import exchange_layout_handles
+                exchange_layout_handles(ctx, self.comm[0], self.comm[1])
             ctx.edge_weights(want_outputs=False)                       # to_proba_edges, embedder.rs:351
             if p.hubness_weighting:                                    # embedder.rs:810-837
                 counts = ctx.get_hubness_counts()

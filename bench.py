@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-gather instead of the fused peer-store exchange")
     return ap.parse_args()
 
 
@@ -190,7 +191,7 @@ def run_reference(a):
 def run_ours(a):
     import torch.distributed as dist
     import annembed_b200 as A
-    from annembed_b200.dist import broadcast_unique_id, env_rank_world
+    from annembed_b200.dist import broadcast_unique_id, env_rank_world, exchange_layout_handles
 
     rank, world, local = env_rank_world()
     if world != a.gpus and world > 1:
@@ -211,6 +212,8 @@ def run_ours(a):
     uid = broadcast_unique_id(ctx.unique_id, rank, world)
     ctx.comm_init(rank, world, uid)
     ctx.set_graph_csr(row_ptr, col, distances)
+    if world > 1 and not a.no_fused:
+        exchange_layout_handles(ctx, rank, world)
     if a.hubness:
         ctx.edge_weights(want_outputs=False)
         cnt = ctx.get_hubness_counts()
@@ -272,7 +275,7 @@ def run_ours(a):
         e2e_t, e2e_samples, h2d, d2h = 0.0, 0, 0, 0
         for it in range(1 + a.steps):                 # first one is a warm-up
             uid = broadcast_unique_id(ctx.unique_id, rank, world)
-            emb = A.Embedder(g, params, initial_embedding=y0, device=local, comm=(rank, world, uid))
+            emb = A.Embedder(g, params, initial_embedding=y0, device=local, comm=(rank, world, uid), fused_exchange=not a.no_fused)
             barrier()
             t1 = time.perf_counter()
             emb.embed()
@@ -317,7 +320,8 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "mini_epochs_per_batch": int(mini), "flags": a.flags,
                        "l2_persist_max_bytes": int(st["l2_persist_max_bytes"]), "l2_window_max_bytes": int(st["l2_window_max_bytes"]),
                        "l2": "inputs larger than L2 (graph + transposed index > 2 GB per pass); no flush needed",
-                       "parallelism": f"node-sharded x{world}, replicated layout, all-gather per mini-epoch" if world > 1 else "single GPU",
+                       "parallelism": (f"node-sharded x{world}, replicated layout, " + ("NCCL all-gather per mini-epoch" if a.no_fused else
+                                       "fused exchange: peer-memory row stores from the in-edge kernel + 4-byte all-reduce per mini-epoch")) if world > 1 else "single GPU",
                        "positive_samples_per_step": samples / a.steps, "input_build_s": t_in,
                        "cross_entropy_last_step": list(ce)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

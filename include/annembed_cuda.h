@@ -105,6 +105,13 @@ const char *annembed_cuda_last_error(const annembed_cuda_ctx *ctx);
 int annembed_cuda_comm_unique_id(uint8_t unique_id[128]);
 int annembed_cuda_comm_init(annembed_cuda_ctx *ctx, int rank, int nranks, const uint8_t unique_id[128]);
 
+/* Fused exchange (optional; after set_graph_csr on every rank): instead of the all-gather, the in-edge kernel stores
+ * every owned row straight into all replicas over NVLink (peer memory opened through CUDA IPC) while the other tiles
+ * are still computing, and a 4-byte all-reduce closes the mini-epoch.  export: 2 x 64-byte cudaIpcMemHandle_t of this
+ * rank's two layout buffers; import: the handles of all ranks, rank-major (nranks x 128 bytes). */
+int annembed_cuda_comm_export_layout(annembed_cuda_ctx *ctx, uint8_t handles[128]);
+int annembed_cuda_comm_import_layouts(annembed_cuda_ctx *ctx, const uint8_t *all_handles);
+
 /* ≙ the KGraph hand-off, kgraph.rs:108-120 + get_neighbours :157.  Rows sorted ascending by distance
  * (kgraph.rs:508-509), no self edges, every row non-empty.  row_ptr has n+1 entries. */
 int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, const uint64_t *row_ptr,

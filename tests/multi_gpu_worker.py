@@ -10,11 +10,11 @@ import torch
 import torch.distributed as dist
 
 import annembed_b200 as A
-from annembed_b200.dist import broadcast_unique_id, env_rank_world
+from annembed_b200.dist import broadcast_unique_id, env_rank_world, exchange_layout_handles
 from tests.conftest import random_graph
 
 
-def main(out_path, n, d):
+def main(out_path, n, d, fused):
     rank, world, local = env_rank_world()
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -25,6 +25,8 @@ def main(out_path, n, d):
     uid = broadcast_unique_id(ctx.unique_id, rank, world)
     ctx.comm_init(rank, world, uid)
     ctx.set_graph_csr(row_ptr, col, dst)
+    if fused:
+        exchange_layout_handles(ctx, rank, world)
     ctx.edge_weights(want_outputs=False)
     ctx.set_embedding(y0)
     ce0, ce1 = ctx.optimize()
@@ -40,4 +42,4 @@ def main(out_path, n, d):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))
+    main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) != 0)
