@@ -6,8 +6,8 @@ call without the CUDA library and a GPU raises.
 """
 from .embedparams import EmbedderParams
 from .kgraph import KGraph, read_csr, write_csr
-from .embedder import CudaContext, Embedder, EmbedError
+from .embedder import CudaContext, Embedder, EmbedError, KGraphProjection
 from ._lib import AnnembedCudaError, load
 
-__all__ = ["EmbedderParams", "KGraph", "read_csr", "write_csr", "CudaContext", "Embedder", "EmbedError",
+__all__ = ["EmbedderParams", "KGraph", "read_csr", "write_csr", "CudaContext", "Embedder", "EmbedError", "KGraphProjection",
            "AnnembedCudaError", "load"]

@@ -61,6 +61,7 @@ SYMBOLS = [
     ("annembed_cuda_get_hubness_counts", C.c_int, [_ctx, u32p]),
     ("annembed_cuda_set_embedding", C.c_int, [_ctx, f32p]),
     ("annembed_cuda_reset_embedding", C.c_int, [_ctx]),
+    ("annembed_cuda_set_embedding_from_projection", C.c_int, [_ctx, C.c_uint64, f32p, u32p, f32p, C.c_float]),
     ("annembed_cuda_get_embedded_scales", C.c_int, [_ctx, f32p]),
     ("annembed_cuda_step_fixed", C.c_int, [_ctx, C.c_uint64, u64p, u32p, C.c_double]),
     ("annembed_cuda_optimize", C.c_int, [_ctx, f64p, f64p]),

@@ -345,6 +345,39 @@ __global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint3
     if (i < n) out[i] = (uint32_t)(ptr[i + 1] - ptr[i]);
 }
 
+// N1: second-step initial layout of the hierarchical embedding, embedder.rs:245-269.  One thread per node.
+// Gaussian noise: Box-Muller on Philox4x32-10 words keyed (seed; node, coordinate block, 0, tag 0x51).
+__global__ void k_project_init(uint64_t n, uint64_t n_small, int d, int DP, const float *__restrict__ first,
+                               const uint32_t *__restrict__ proj_node, const float *__restrict__ proj_dist,
+                               float median_dist, uint32_t k0, uint32_t k1, float *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float *o = out + i * DP;
+    if (i < n_small) {                                                            // :249-253
+        for (int j = 0; j < DP; j++) o[j] = j < d ? first[i * d + j] : 0.0f;
+        return;
+    }
+    const float ratio = proj_dist[i] / median_dist;                               // :262
+    const float correction = sqrtf(ratio / (float)d);                             // :263
+    const float *src = first + (uint64_t)proj_node[i] * d;
+    for (int j0 = 0; j0 < DP; j0 += 4) {
+        const Philox4 w = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)(j0 >> 2), 0x51u, k0, k1);
+        // two Box-Muller pairs -> four standard normals
+        const float u1 = ((float)(w.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(w.y >> 8) * (1.0f / 16777216.0f);
+        const float u3 = ((float)(w.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u4 = (float)(w.w >> 8) * (1.0f / 16777216.0f);
+        const float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u3));
+        float z[4];
+        sincospif(2.0f * u2, &z[1], &z[0]); z[0] *= r1; z[1] *= r1;
+        sincospif(2.0f * u4, &z[3], &z[2]); z[2] *= r2; z[3] *= r2;
+        for (int t = 0; t < 4 && j0 + t < DP; t++) {
+            const int j = j0 + t;
+            const float c = fminf(fmaxf(correction * z[t], -2.0f), 2.0f);         // clip(.., 2.) tools/clip.rs:5-18
+            o[j] = j < d ? src[j] + c : 0.0f;                                     // :265-267
+        }
+    }
+}
+
 __global__ void k_pad_rows(uint64_t n, int d, int DP, const float *__restrict__ in, float *__restrict__ out)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1265,6 +1298,34 @@ extern "C" int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *
         ctx->st.kernel_launches++;
         if ((rc = sync_stream(ctx))) return rc;
     }
+    ctx->have_embedding = true;
+    return annembed_cuda_reset_embedding(ctx);
+}
+
+extern "C" int annembed_cuda_set_embedding_from_projection(annembed_cuda_ctx *ctx, uint64_t n_small, const float *first,
+                                                           const uint32_t *proj_node, const float *proj_dist, float median_dist)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_embedding_from_projection: graph not set");
+    REQUIRE(first && proj_node && proj_dist, ANNEMBED_ERR_INVALID_ARG, "null argument");
+    REQUIRE(n_small >= 1 && n_small <= ctx->n, ANNEMBED_ERR_INVALID_ARG, "n_small must be in 1..n");
+    REQUIRE(median_dist > 0.0f && std::isfinite(median_dist), ANNEMBED_ERR_INVALID_ARG, "median projection distance must be > 0");
+    for (uint64_t i = n_small; i < ctx->n; i++)
+        REQUIRE(proj_node[i] < n_small, ANNEMBED_ERR_INVALID_ARG, "projection target is not a node of the small graph");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->n;
+    const int d = (int)ctx->prm.asked_dim, DP = ctx->DP;
+    int rc;
+    if ((rc = alloc_layout(ctx))) return rc;
+    DevBuf<float> dfirst, ddist; DevBuf<uint32_t> dnode;
+    CU(dfirst.alloc(n_small * d)); CU(ddist.alloc(n)); CU(dnode.alloc(n));
+    if ((rc = h2d(ctx, dfirst.p, first, n_small * d * sizeof(float)))) return rc;
+    if ((rc = h2d(ctx, dnode.p, proj_node, n * sizeof(uint32_t)))) return rc;
+    if ((rc = h2d(ctx, ddist.p, proj_dist, n * sizeof(float)))) return rc;
+    k_project_init<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, n_small, d, DP, dfirst.p, dnode.p, ddist.p, median_dist,
+                                                             (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu), (uint32_t)(ctx->prm.seed >> 32), ctx->y0.p);
+    ctx->st.kernel_launches++;
+    if ((rc = sync_stream(ctx))) return rc;
     ctx->have_embedding = true;
     return annembed_cuda_reset_embedding(ctx);
 }

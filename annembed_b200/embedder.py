@@ -136,6 +136,15 @@ class CudaContext:
             raise ValueError(f"initial embedding must be ({self.n}, {self.params.asked_dim}), got {y.shape}")
         self._ck(self.lib.annembed_cuda_set_embedding(self.h, ptr(y, C.c_float)))
 
+    def set_embedding_from_projection(self, first, proj_node, proj_dist, median_dist: float):
+        first = np.ascontiguousarray(first, np.float32)
+        proj_node = np.ascontiguousarray(proj_node, np.uint32)
+        proj_dist = np.ascontiguousarray(proj_dist, np.float32)
+        assert first.shape[1] == self.params.asked_dim and len(proj_node) == self.n == len(proj_dist)
+        self._ck(self.lib.annembed_cuda_set_embedding_from_projection(self.h, first.shape[0], ptr(first, C.c_float),
+                                                                      ptr(proj_node, C.c_uint32), ptr(proj_dist, C.c_float),
+                                                                      median_dist))
+
     def reset_embedding(self):
         self._ck(self.lib.annembed_cuda_reset_embedding(self.h))
 
@@ -189,6 +198,31 @@ class CudaContext:
         return counts, negs
 
 
+class KGraphProjection:
+    """≙ `KGraphProjection<F>` (fromhnsw/kgproj.rs:35-44) as flat arrays: a small graph on the upper HNSW layers, the
+    whole (large) graph whose first `small_graph.get_nb_nodes()` nodes ARE the small graph's nodes (kgproj.rs:106-124),
+    and for every other node its projection = nearest small-graph node and the distance to it (proj_data)."""
+
+    def __init__(self, small_graph: KGraph, large_graph: KGraph, proj_node, proj_dist, layer: int = 1):
+        self.layer = layer
+        self.small_graph = small_graph
+        self.large_graph = large_graph
+        self.proj_node = np.ascontiguousarray(proj_node, np.uint32)
+        self.proj_dist = np.ascontiguousarray(proj_dist, np.float32)
+        n, ns = large_graph.get_nb_nodes(), small_graph.get_nb_nodes()
+        if len(self.proj_node) != n or len(self.proj_dist) != n or ns > n:
+            raise ValueError("projection arrays must have one entry per node of the large graph")
+
+    def get_small_graph(self) -> KGraph: return self.small_graph          # kgproj.rs:388
+    def get_large_graph(self) -> KGraph: return self.large_graph          # :393
+    def get_projection_by_nodeidx(self, i: int): return int(self.proj_node[i]), float(self.proj_dist[i])   # :376
+
+    def get_projection_distance_median(self) -> float:
+        """≙ get_projection_distance_quant().query(0.5) (kgproj.rs:403-410; exact median instead of CKMS)."""
+        ns = self.small_graph.get_nb_nodes()
+        return float(np.median(self.proj_dist[ns:])) if len(self.proj_dist) > ns else 1.0
+
+
 class EmbedError(RuntimeError):
     """≙ `Err(1)` of Embedder::embed (embedder.rs:183,366-369)."""
 
@@ -209,6 +243,48 @@ class Embedder:
         self.fused_exchange = fused_exchange      # peer-memory stores from the epoch kernel instead of an all-gather
         self.stats = {}
 
+    @classmethod
+    def from_hkgraph(cls, graph_projection: KGraphProjection, parameters: EmbedderParams,
+                     initial_embedding: np.ndarray | None = None, device: int = 0):
+        """≙ Embedder::from_hkgraph (embedder.rs:120-133): two-step embedding.  `initial_embedding` is the initial
+        layout of the SMALL graph (the reference computes a diffusion-map layout for it)."""
+        e = cls(graph_projection.get_large_graph(), parameters, initial_embedding, device)
+        e.hkgraph = graph_projection
+        return e
+
+    def h_embed(self) -> int:
+        """≙ h_embed (embedder.rs:194-295)."""
+        import dataclasses
+        proj, p = self.hkgraph, self.parameters
+        first_params = dataclasses.replace(p, nb_grad_batch=p.grad_factor * p.nb_grad_batch, grad_step=1.0,
+                                           hierarchy_layer=0)                       # embedder.rs:203-209
+        first = Embedder(proj.get_small_graph(), first_params, self.initial_embedding, self.device)
+        first.embed()                                                               # :213
+        first_embedding = first.get_embedded()
+        self.first_step_stats = first.stats
+        ctx = None
+        try:
+            large = proj.get_large_graph()
+            ctx = CudaContext(p, self.device)
+            ctx.set_graph_csr(*large.get_neighbours())
+            ctx.edge_weights(want_outputs=False)                                    # :226-230
+            if p.hubness_weighting:
+                counts = ctx.get_hubness_counts()
+                self.hubness_counts = counts
+                ctx.set_neg_weights(np.clip(counts.astype(np.float32), 1.0, float(len(counts))))
+            ctx.set_embedding_from_projection(first_embedding, proj.proj_node, proj.proj_dist,
+                                              proj.get_projection_distance_median())   # :245-269
+            self.initial_embedding = ctx.get_embedding()
+            self.cross_entropy = ctx.optimize(want_ce=True)                         # :275
+            self.embedding = ctx.get_embedding()
+            self.stats = ctx.get_stats()
+        except AnnembedCudaError as e:
+            raise EmbedError(str(e)) from e
+        finally:
+            if ctx is not None:
+                ctx.close()
+        return 1
+
     # --- parameter getters, embedder.rs:135-153
     def get_asked_dimension(self) -> int: return self.parameters.asked_dim
     def get_scale_rho(self) -> float: return self.parameters.scale_rho
@@ -228,6 +304,8 @@ class Embedder:
     def embed(self) -> int:
         """≙ embed -> one_step_embed (embedder.rs:183,298-371).  Returns 1 (`Ok(1)`); raises EmbedError (`Err(1)`)."""
         p = self.parameters
+        if getattr(self, "hkgraph", None) is not None:
+            return self.h_embed()                                                   # embedder.rs:186-190
         if self.initial_embedding is None:
             if p.dmap_init:
                 raise EmbedError("dmap_init=true needs an explicit initial_embedding: the diffusion-map layout "

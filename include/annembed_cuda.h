@@ -140,6 +140,14 @@ int annembed_cuda_get_hubness_counts(annembed_cuda_ctx *ctx, uint32_t *counts /*
  * embedder.rs:794-798).  A device-resident copy is kept for annembed_cuda_reset_embedding. */
 int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *y);
 int annembed_cuda_reset_embedding(annembed_cuda_ctx *ctx);
+/* Hierarchical embedding, second-step initial layout ≙ h_embed (embedder.rs:245-269): nodes < n_small keep `first`
+ * (the first-step layout of the small graph, n_small x asked_dim); every other node i starts at
+ * first[proj_node[i]] + clip(sqrt((proj_dist[i] / median_dist) / asked_dim) * N(0,1), 2) per coordinate, where
+ * (proj_node, proj_dist) ≙ KGraphProjection::get_projection_by_nodeidx (fromhnsw/kgproj.rs:376) and median_dist
+ * ≙ get_projection_distance_quant().query(0.5) (:403).  Entries of proj_* below n_small are ignored. */
+int annembed_cuda_set_embedding_from_projection(annembed_cuda_ctx *ctx, uint64_t n_small, const float *first /*[n_small*d]*/,
+                                                const uint32_t *proj_node /*[n]*/, const float *proj_dist /*[n]*/,
+                                                float median_dist);
 /* K2 ≙ estimate_embedded_scales_from_initial_scales (embedder.rs:1356-1373). */
 int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *out /*[n]*/);
 

@@ -74,3 +74,11 @@ def test_no_cpu_fallback():
     emb = A.Embedder(g, A.EmbedderParams(dmap_init=False))
     with pytest.raises(A.EmbedError):
         emb.embed()
+
+
+def test_cpp_host_mirror_compiles_against_the_header():
+    """The C++ mirror of `Embedder` (include/annembed_embedder.hpp) builds and links against the C ABI (no GPU needed)."""
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    subprocess.run(["make", "-C", here, "-s", "-B"], check=True)
+    assert os.path.exists(os.path.join(here, "test_embedder"))

@@ -360,3 +360,14 @@ def test_embedder_mirror_end_to_end():
     assert emb.get_hubness().sum() == len(col)
     with pytest.raises(A.EmbedError):
         A.Embedder(g, A.EmbedderParams(dmap_init=True)).embed()
+
+
+def test_cpp_driver_of_the_host_mirror():
+    """T9: the C++ host mirror (include/annembed_embedder.hpp) driven from a C++ program: the reference's
+    mini_embed_full (embedder.rs:1435-1467) restated + error behaviour."""
+    import subprocess
+    here = os.path.join(os.path.dirname(__file__), "cpp")
+    subprocess.run(["make", "-C", here, "-s"], check=True)
+    out = subprocess.run([os.path.join(here, "test_embedder"), "500"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "test_embedder ok" in out.stdout
