@@ -123,3 +123,18 @@ def test_negative_uniformity_chi2():
         expect += 5 * allowed[fired].sum(0)
     chi2 = ((hist - expect) ** 2 / expect).sum()
     assert chi2 < n + 6 * np.sqrt(2 * n), chi2          # chi2(63): mean 63, sd 11
+
+
+def test_csv_output_matches_rust_lower_exp_format(tmp_path):
+    """N4: `{:.5e}` of Rust (tools/io.rs:35,59): 1.23457e0 / -9.87654e-3, no '+', no padded exponent."""
+    from annembed_b200.io import rust_lower_exp, write_csv_array2, write_csv_labeled_array2
+    assert rust_lower_exp(1.234567) == "1.23457e0"
+    assert rust_lower_exp(-0.00987654) == "-9.87654e-3"
+    assert rust_lower_exp(0.0) == "0.00000e0"
+    assert rust_lower_exp(123456.7) == "1.23457e5"
+    m = np.array([[1.5, -2.25e-4], [3e10, 0.0]], np.float32)
+    p = str(tmp_path / "e.csv")
+    assert write_csv_array2(p, m) == 1
+    assert open(p).read() == "1.50000e0,-2.25000e-4\n3.00000e10,0.00000e0\n"
+    write_csv_labeled_array2(p, [7, 9], m)
+    assert open(p).read().splitlines()[1] == "9,3.00000e10,0.00000e0"
