@@ -437,38 +437,6 @@ __global__ void __launch_bounds__(256) k_epoch_generic(EpochArgs a, unsigned lon
 //               segmented warp scan and lets the owner lane apply the composite: y_next <- alpha * y_next + beta.
 //  Splitting keeps both register footprints small (k_epoch_in: ~48 registers) so that enough warps are resident to
 //  hide the random-gather latency.
-// 8- or 16-byte asynchronous global->shared copy of one layout row (LDGSTS), and its shared-memory read back
-template <int DP>
-__device__ __forceinline__ void cp_async_row(float *smem_dst, const float *gsrc)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if constexpr (DP == 2) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
-    } else {
-#pragma unroll
-        for (int c = 0; c < DP; c += 4)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 4u * c), "l"(gsrc + c) : "memory");
-    }
-}
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-template <int DP>
-__device__ __forceinline__ void lds_row(const float *smem_src, float (&v)[DP])
-{
-    if constexpr (DP == 2) {
-        const float2 t = *reinterpret_cast<const float2 *>(smem_src);
-        v[0] = t.x; v[1] = t.y;
-    } else {
-#pragma unroll
-        for (int c = 0; c < DP; c += 4) {
-            const float4 t = *reinterpret_cast<const float4 *>(smem_src + c);
-            v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
-        }
-    }
-}
-
 template <int DP, int KREG>
 struct EpochTile {
 #ifndef ANNEMBED_WARPS_OUT
@@ -480,9 +448,7 @@ struct EpochTile {
     static constexpr int WARPS = DP <= 4 ? ANNEMBED_WARPS_OUT : (DP <= 16 ? 4 : 2);
     static constexpr int MINB = DP <= 4 ? ANNEMBED_MINB_OUT : (DP <= 8 ? 2 : 1);  // blocks/SM the register budget aims at
     static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
-    static constexpr int CH = DP <= 2 ? 4 : (DP <= 4 ? 2 : 0);                   // firings whose gathers are in flight together
-    static constexpr int GATHER_BYTES = CH * 6 * 32 * DP * 4;                    // cp.async landing buffer [CH][6][32][DP]
-    static constexpr int PER_WARP = ((GATHER_BYTES + 32 * RS * (4 + 4 + 2) + 15) / 16) * 16;   // + col, cum, ceil counts (u16)
+    static constexpr int PER_WARP = ((32 * RS * (4 + 4 + 2) + 15) / 16) * 16;    // col, cum, ceil counts (u16)
     static constexpr int SMEM = WARPS * PER_WARP;
 };
 
@@ -498,8 +464,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
     const uint64_t n0 = (uint64_t)a.lo + tile * 32;
     if (n0 >= a.hi) return;                                    // whole warp leaves together
     unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
-    float *s_g = reinterpret_cast<float *>(base);                               // [CH][6][32][DP]  (16-byte aligned)
-    uint32_t *s_col = reinterpret_cast<uint32_t *>(base + TL::GATHER_BYTES);    // [32][RS]
+    uint32_t *s_col = reinterpret_cast<uint32_t *>(base);                       // [32][RS]
     float *s_cum = reinterpret_cast<float *>(s_col + 32 * RS);                  // [32][RS]
     unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_cum + 32 * RS); // [32][RS]
 
@@ -554,62 +519,61 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
     }
     // ---------------- the node's own firings
     if constexpr (DP <= 4) {
-        // Chunks of CH firings.  Pass 1 (ALU only): pick the edge, draw and filter the negatives, and issue the 6 row
-        // gathers of every firing of the chunk as cp.async global->shared copies (no registers, up to 24 in flight per
-        // lane).  Pass 2: wait once, then run the sequential arithmetic out of shared memory.
-        constexpr int CH = TL::CH;
+        // software pipelined: the 6 row gathers of firing s+1 are in flight during the arithmetic of firing s
         int m = 0;                       // edge cursor of the systematic sampler
         int m_cur = -1;                  // edge whose partner copy yj is live (pair simulation across firings)
         float yj[DP];
         Philox4 B;
-        for (int s0 = 0; s0 < T; s0 += CH) {
-            const int nf = min(CH, T - s0);
-            unsigned mpack = 0, usepack = 0;
-            for (int f = 0; f < nf; f++) {
-                const int s = s0 + f;
-                while ((int)s_ch[lane * RS + m] <= s) m++;      // ch[k-1] == T > s
-                mpack |= (unsigned)m << (4 * f);
-                const uint32_t j = s_col[lane * RS + m];
-                float *dst = s_g + ((size_t)(f * 6) * 32 + lane) * DP;
-                cp_async_row<DP>(dst, a.y_snap + (size_t)j * DP);
-                const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
-                if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
-                auto rej = [&](uint32_t kk) -> bool {
-                    bool r = (kk == node) | (kk == j);
+        int nm = -1;                     // prefetched firing
+        float npe = 0.0f;
+        float nyj[DP], nyk[ANNEMBED_NB_NEG][DP];
+        unsigned nuse = 0;
+        auto prepare = [&](int s) {
+            while ((int)s_ch[lane * RS + m] <= s) m++;          // ch[k-1] == T > s
+            nm = m;
+            const uint32_t j = s_col[lane * RS + m];
+            const float P_hi = s_cum[lane * RS + m];
+            const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
+            npe = F_SUB(P_hi, P_lo);
+            load_row<DP>(a.y_snap, j, nyj);
+            const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
+            if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
+            auto rej = [&](uint32_t kk) -> bool {
+                bool r = (kk == node) | (kk == j);
 #pragma unroll
-                    for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
-                    return r;
-                };
-                uint32_t negs[ANNEMBED_NB_NEG];
-                draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
+                for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
+                return r;
+            };
+            uint32_t negs[ANNEMBED_NB_NEG];
+            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
+            nuse = 0;
 #pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-                    const bool ok = negs[q] != ANNEMBED_NO_NODE;
-                    usepack |= (ok ? 1u : 0u) << (5 * f + q);
-                    cp_async_row<DP>(dst + (size_t)(q + 1) * 32 * DP, a.y_snap + (size_t)(ok ? negs[q] : node) * DP);
-                }
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+                const bool ok = negs[q] != ANNEMBED_NO_NODE;
+                nuse |= ok ? (1u << q) : 0u;
+                load_row<DP>(a.y_snap, ok ? negs[q] : node, nyk[q]);
             }
-            cp_async_wait_all();
-            for (int f = 0; f < nf; f++) {
-                const int mf = (int)((mpack >> (4 * f)) & 15u);
-                const float P_hi = s_cum[lane * RS + mf];
-                const float P_lo = mf ? s_cum[lane * RS + mf - 1] : 0.0f;
-                const float pe = F_SUB(P_hi, P_lo);
-                const float *src = s_g + ((size_t)(f * 6) * 32 + lane) * DP;
-                if (mf != m_cur) {
-                    lds_row<DP>(src, yj);
-                    m_cur = mf;
-                }
+        };
+        if (T > 0) prepare(0);
+        for (int s = 0; s < T; s++) {
+            float yk[ANNEMBED_NB_NEG][DP];
+            const float pe = npe;
+            const unsigned use = nuse;
+            if (nm != m_cur) {
 #pragma unroll
-                for (int c = 0; c < DP; c++) g[c] = 0.0f;
-                attract<DP, true>(y, yj, g, pe, inv_s2, a.K);
-#pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-                    float yk[DP];
-                    lds_row<DP>(src + (size_t)(q + 1) * 32 * DP, yk);
-                    repulse<DP, true>(y, yk, g, inv_s2, a.K, (usepack >> (5 * f + q)) & 1u);
-                }
+                for (int c = 0; c < DP; c++) yj[c] = nyj[c];
+                m_cur = nm;
             }
+#pragma unroll
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+#pragma unroll
+                for (int c = 0; c < DP; c++) yk[q][c] = nyk[q][c];
+            if (s + 1 < T) prepare(s + 1);
+#pragma unroll
+            for (int c = 0; c < DP; c++) g[c] = 0.0f;
+            attract<DP, true>(y, yj, g, pe, inv_s2, a.K);
+#pragma unroll
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, yk[q], g, inv_s2, a.K, (use >> q) & 1u);
         }
     } else {
         // wide rows: the prefetch registers do not fit, plain sequential firings
@@ -741,9 +705,13 @@ k_epoch_in(EpochArgs a)
 #pragma unroll
             for (int cc = 0; cc < DP; cc++) beta[cc] = F_MUL(-A, ys[cc]);
         }
-        // segmented inclusive scan (composition in index order) over the lanes of each owner
+        // segmented inclusive scan (composition in index order) over the lanes of each owner; log2(longest segment of
+        // the round) steps are enough
+        const int my_len = max(0, min(32, rel_hi)) - max(0, min(32, rel_lo));
+        const int max_len = __reduce_max_sync(0xffffffffu, my_len);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
+            if (d >= max_len) break;
             const float ap = __shfl_up_sync(0xffffffffu, alpha, d);
             float bp[DP];
 #pragma unroll
