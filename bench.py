@@ -24,6 +24,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The CPU arm (oracle, OpenMP) must see all host cores: torchrun exports OMP_NUM_THREADS=1 and libgomp reads it when
+# it is first loaded (by numpy/torch), so fix it before those imports.  Only the process that runs the CPU arm needs it.
+if ("reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1) and int(os.environ.get("RANK", "0")) == 0:
+    _cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(_cores)
+
 import numpy as np
 import torch
 
@@ -145,15 +151,16 @@ def cpu_arm(a, row_ptr, col, dist, y0, seconds, label):
     scale, p = oracle.edge_weights(row_ptr, col, dist, 0.75, 1.0)
     es = oracle.embedded_scales(scale)
     t_w = time.time() - t0
-    cores = oracle.num_threads()
+    # all host cores (torchrun exports OMP_NUM_THREADS=1; the oracle sets its own thread count)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     E = len(col)
     # calibrate on a tiny slice, then size the sample for ~`seconds` of work (first batch: full gradient step)
     _, done, secs = oracle.optimize(row_ptr, col, p, es, y0[:, :a.dim], 1.0, 1.0, 10, a.batches, seed=1, first_batch=1,
-                                    n_batches=1, sample_fraction=max(2e-4, 2e5 / (10.0 * E)), timing=True)
+                                    n_batches=1, sample_fraction=max(2e-4, 2e5 / (10.0 * E)), timing=True, n_threads=cores)
     rate = done / max(secs, 1e-6)
     frac = min(1.0, rate * seconds / (10.0 * E))
     _, done, secs = oracle.optimize(row_ptr, col, p, es, y0[:, :a.dim], 1.0, 1.0, 10, a.batches, seed=2, first_batch=1,
-                                    n_batches=1, sample_fraction=frac, timing=True)
+                                    n_batches=1, sample_fraction=frac, timing=True, n_threads=cores)
     return {"value": 6.0 * done / secs, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{label}: {done} positive samples = {frac:.4f} of one batch (of {a.batches}) of the same graph, "
                       f"sampling loop only ({secs:.1f} s); K1 weights + scales took {t_w:.1f} s on the host and are not included",
