@@ -69,6 +69,9 @@ struct annembed_cuda_ctx {
     annembed_cuda_params prm{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;              // second stream: staggered sub-ranges when the exchange is fused
+    cudaStream_t launch_stream = nullptr;        // stream the epoch kernels are launched on (stream or stream2)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int n_sm = 148;
     int last_epoch_kernels = 1;                  // kernels per mini-epoch of the path in use (tiled: 2, generic: 1)
@@ -899,6 +902,10 @@ extern "C" int annembed_cuda_create(annembed_cuda_ctx **out, const annembed_cuda
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    ctx->launch_stream = ctx->stream;
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, device);
     cudaDeviceGetAttribute(&ctx->l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, device);
@@ -923,6 +930,9 @@ extern "C" int annembed_cuda_destroy(annembed_cuda_ctx *ctx)
     for (auto ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ANNEMBED_OK;
@@ -1365,6 +1375,10 @@ static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
     return (uint32_t)std::max<double>(1.0, std::ceil(per_node / ANNEMBED_FIRINGS_PER_MINI_EPOCH));
 }
 
+#ifndef ANNEMBED_FUSED_CHUNKS
+#define ANNEMBED_FUSED_CHUNKS 4
+#endif
+
 static SgdConst make_const(const annembed_cuda_ctx *ctx, double grad_step)
 {
     SgdConst K;
@@ -1446,6 +1460,7 @@ static void set_l2_window(annembed_cuda_ctx *ctx, const void *ptr, size_t bytes)
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaStreamSetAttribute(ctx->stream2, cudaStreamAttributeAccessPolicyWindow, &v);
 }
 
 template <int DP, bool HUB, int KREG>
@@ -1454,11 +1469,11 @@ static cudaError_t launch_tiled(annembed_cuda_ctx *ctx, const EpochArgs &a)
     using TL = EpochTile<DP, KREG>;
     const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;
     const unsigned int nb = (unsigned int)((tiles + TL::WARPS - 1) / TL::WARPS);
-    k_epoch_out<DP, HUB, KREG><<<nb, TL::WARPS * 32, TL::SMEM, ctx->stream>>>(a, ctx->counter.p);
+    k_epoch_out<DP, HUB, KREG><<<nb, TL::WARPS * 32, TL::SMEM, ctx->launch_stream>>>(a, ctx->counter.p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const unsigned int nb2 = (unsigned int)((tiles + ANNEMBED_WARPS_IN - 1) / ANNEMBED_WARPS_IN);
-    k_epoch_in<DP><<<nb2, ANNEMBED_WARPS_IN * 32, 0, ctx->stream>>>(a);
+    k_epoch_in<DP><<<nb2, ANNEMBED_WARPS_IN * 32, 0, ctx->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -1471,7 +1486,7 @@ static cudaError_t launch_epoch_dp(annembed_cuda_ctx *ctx, const EpochArgs &a)
     ctx->last_epoch_kernels = (tiled_ok && ctx->kmax <= 16) ? 2 : 1;
     if (tiled_ok && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
     if (tiled_ok && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);
-    k_epoch_generic<DP, HUB><<<nblocks(a.hi - a.lo, 256), 256, 0, ctx->stream>>>(a, ctx->counter.p);
+    k_epoch_generic<DP, HUB><<<nblocks(a.hi - a.lo, 256), 256, 0, ctx->launch_stream>>>(a, ctx->counter.p);
     return cudaGetLastError();
 }
 
@@ -1528,7 +1543,28 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
             }
             set_l2_window(ctx, a.y_snap, (size_t)ctx->n * ctx->DP * sizeof(float));
             CU(cudaEventRecord(ctx->ev[2 * li], ctx->stream));
-            CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
+            if (fused) {
+                // Staggered sub-ranges on two streams: the peer stores of one sub-range's in-edge kernel travel over
+                // NVLink while the next sub-range's out-edge kernel computes (the rows only become final in k_epoch_in).
+                const uint32_t tiles = (ctx->hi - ctx->lo + 31) / 32;
+                const uint32_t per = ((tiles + ANNEMBED_FUSED_CHUNKS - 1) / ANNEMBED_FUSED_CHUNKS) * 32;
+                CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                for (int c = 0; c < ANNEMBED_FUSED_CHUNKS; c++) {
+                    EpochArgs ac = a;
+                    ac.lo = std::min<uint32_t>(ctx->hi, ctx->lo + (uint32_t)c * per);
+                    ac.hi = std::min<uint32_t>(ctx->hi, ac.lo + per);
+                    if (ac.hi <= ac.lo) continue;
+                    ac.in_ptr = ctx->in_ptr_all.p + ac.lo;
+                    ctx->launch_stream = (c & 1) ? ctx->stream2 : ctx->stream;
+                    CU(hub ? launch_epoch<true>(ctx, ac) : launch_epoch<false>(ctx, ac));
+                }
+                ctx->launch_stream = ctx->stream;
+                CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+            } else {
+                CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
+            }
             CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
             if (ctx->nranks > 1) {
                 CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
@@ -1562,7 +1598,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
         if (ctx->nranks > 1) { CU(cudaEventElapsedTime(&t, ctx->ev[xoff + 2 * i], ctx->ev[xoff + 2 * i + 1])); xms += t; }
     }
     ctx->st.optimize_ms = ms; ctx->st.epoch_kernel_ms = kms; ctx->st.exchange_ms = xms;
-    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_launch * (ctx->last_epoch_kernels);
+    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_launch * (ctx->last_epoch_kernels) * (fused ? ANNEMBED_FUSED_CHUNKS : 1);
     ctx->st.positive_samples = cnt; ctx->st.edge_updates = 6 * cnt;
     ctx->st.model_bytes = (double)cnt * (12.0 + 36.0 * (double)ctx->prm.asked_dim);
     return ANNEMBED_OK;
