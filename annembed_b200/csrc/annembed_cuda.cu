@@ -1376,7 +1376,7 @@ static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
 }
 
 #ifndef ANNEMBED_FUSED_CHUNKS
-#define ANNEMBED_FUSED_CHUNKS 4
+#define ANNEMBED_FUSED_CHUNKS 1   // >1 staggers sub-ranges on two streams (measured: no gain at 8 GPUs, profiles/r01_bench_8gpu_*)
 #endif
 
 static SgdConst make_const(const annembed_cuda_ctx *ctx, double grad_step)
