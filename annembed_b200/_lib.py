@@ -38,6 +38,11 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Quality(C.Structure):
+    _fields_ = [("nb_without_match", C.c_uint64), ("mean_nbmatch", C.c_double), ("knn_preservation", C.c_double),
+                ("mean_ratio", C.c_double), ("radius_quantiles", C.c_double * 6), ("ratio_quantiles", C.c_double * 6)]
+
+
 STATUS = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "EMPTY_ROW", 4: "UNSORTED_ROW", 5: "STATE", 6: "UNSUPPORTED",
           7: "COMM", 8: "NO_NEGATIVE"}
 
@@ -68,6 +73,7 @@ SYMBOLS = [
     ("annembed_cuda_optimize_batches", C.c_int, [_ctx, C.c_uint32, C.c_uint32]),
     ("annembed_cuda_cross_entropy", C.c_int, [_ctx, f64p]),
     ("annembed_cuda_get_embedding", C.c_int, [_ctx, f32p]),
+    ("annembed_cuda_quality_estimate", C.c_int, [_ctx, C.c_uint32, C.POINTER(Quality), f32p, f32p, f32p]),
     ("annembed_cuda_get_stats", C.c_int, [_ctx, C.POINTER(Stats)]),
     ("annembed_cuda_reset_stats", C.c_int, [_ctx]),
     ("annembed_cuda_debug_draws", C.c_int, [_ctx, C.c_uint32, u32p, u32p]),

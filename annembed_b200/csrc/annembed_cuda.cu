@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "sgd_core.cuh"
+#include "quality.cuh"
 
 using namespace annembed;
 
@@ -1682,6 +1683,159 @@ extern "C" int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx)
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
     memset(&ctx->st, 0, sizeof(ctx->st));
     return ANNEMBED_OK;
+}
+
+// =====================================================================================================
+// N3: quality estimate (embedder.rs:620-753) on the device
+// =====================================================================================================
+__device__ __forceinline__ int float_to_ordered(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+static inline float ordered_to_float(int i) { i ^= ((i >> 31) & 0x7fffffff); float f; memcpy(&f, &i, 4); return f; }
+
+__global__ void k_bbox(uint64_t n, int DP, const float *__restrict__ Y, int *__restrict__ box /* xmin, xmax, ymin, ymax (ordered ints) */)
+{
+    int xmin = 0x7fffffff, xmax = -0x7fffffff - 1, ymin = 0x7fffffff, ymax = -0x7fffffff - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int x = float_to_ordered(Y[i * DP]), y = float_to_ordered(DP > 1 ? Y[i * DP + 1] : 0.0f);
+        xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(box, xmin); atomicMax(box + 1, xmax); atomicMin(box + 2, ymin); atomicMax(box + 3, ymax); }
+}
+
+// per-block partials {sum of matches, nodes without match} over nodes and {sum of finite ratios, number of finite ratios} over edges
+__global__ void __launch_bounds__(256)
+k_quality_reduce(uint64_t n, uint64_t E, const uint32_t *__restrict__ nodes_match, const float *__restrict__ ratio,
+                 double *__restrict__ partials /* [gridDim.x][4] */)
+{
+    double a = 0, b = 0, c = 0, d = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        a += (double)nodes_match[i]; b += nodes_match[i] == 0 ? 1.0 : 0.0;
+    }
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (uint64_t)gridDim.x * blockDim.x) {
+        const float r = ratio[e];
+        if (isfinite(r)) { c += (double)r; d += 1.0; }
+    }
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    a = BR(tmp).Sum(a); __syncthreads();
+    b = BR(tmp).Sum(b); __syncthreads();
+    c = BR(tmp).Sum(c); __syncthreads();
+    d = BR(tmp).Sum(d);
+    if (threadIdx.x == 0) { partials[4 * blockIdx.x] = a; partials[4 * blockIdx.x + 1] = b; partials[4 * blockIdx.x + 2] = c; partials[4 * blockIdx.x + 3] = d; }
+}
+
+// quantiles (numpy "linear" definition) of the first m entries of an ascending device array
+static int device_quantiles(annembed_cuda_ctx *ctx, const float *sorted, uint64_t m, double out[6])
+{
+    static const double qs[6] = {0.05, 0.25, 0.5, 0.75, 0.85, 0.95};
+    for (int i = 0; i < 6; i++) out[i] = std::nan("");
+    if (m == 0) return ANNEMBED_OK;
+    for (int i = 0; i < 6; i++) {
+        const double pos = qs[i] * (double)(m - 1);
+        const uint64_t lo = (uint64_t)std::floor(pos), hi = std::min<uint64_t>(lo + 1, m - 1);
+        float v[2];
+        CU(cudaMemcpyAsync(&v[0], sorted + lo, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&v[1], sorted + hi, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        out[i] = (double)v[0] + (pos - (double)lo) * ((double)v[1] - (double)v[0]);
+    }
+    return ANNEMBED_OK;
+}
+
+template <int DP>
+static int quality_impl(annembed_cuda_ctx *ctx, uint32_t nbng, annembed_cuda_quality *out, float *radius_out,
+                        float *first_dist_out, float *node_ratio_out)
+{
+    const uint64_t n = ctx->n, E = ctx->E;
+    const float *Y = ctx->y[ctx->cur].p;
+    int rc;
+    DevBuf<float> t, radius, ratio, node_ratio, first_dist, sorted;
+    DevBuf<uint32_t> nodes_match, cell, idx, cell_s, idx_s, cell_start;
+    DevBuf<int> box;
+    DevBuf<unsigned char> tmp;
+    CU(t.alloc(E)); CU(radius.alloc(n)); CU(ratio.alloc(E)); CU(node_ratio.alloc(n)); CU(first_dist.alloc(n));
+    CU(nodes_match.alloc(n)); CU(cell.alloc(n)); CU(idx.alloc(n)); CU(cell_s.alloc(n)); CU(idx_s.alloc(n)); CU(box.alloc(4));
+    // embedder.rs:478-522
+    k_transformed_kgraph<DP><<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr.p, ctx->col.p, Y, t.p);
+    // bounding box of coordinates (0,1) and the grid: about 2 points per cell
+    const int init[4] = {0x7fffffff, -0x7fffffff - 1, 0x7fffffff, -0x7fffffff - 1};
+    CU(cudaMemcpyAsync(box.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    k_bbox<<<std::min<unsigned int>(1024u, nblocks(n, 256)), 256, 0, ctx->stream>>>(n, DP, Y, box.p);
+    int hb[4];
+    CU(cudaMemcpyAsync(hb, box.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = sync_stream(ctx))) return rc;
+    const float xmin = ordered_to_float(hb[0]), xmax = ordered_to_float(hb[1]), ymin = ordered_to_float(hb[2]), ymax = ordered_to_float(hb[3]);
+    REQUIRE(std::isfinite(xmin) && std::isfinite(xmax) && std::isfinite(ymin) && std::isfinite(ymax), ANNEMBED_ERR_INVALID_ARG,
+            "quality_estimate: the embedding holds non-finite coordinates");
+    GridParams gp;
+    gp.G = (int)std::min<double>(8192.0, std::max(1.0, std::ceil(std::sqrt((double)n / 2.0))));
+    const float width = std::max(std::max(xmax - xmin, ymax - ymin), 1e-30f);
+    gp.h = width / (float)gp.G * 1.0001f;
+    gp.inv_h = 1.0f / gp.h;
+    gp.x0 = xmin; gp.y0 = ymin;
+    const uint64_t ncell = (uint64_t)gp.G * gp.G;
+    CU(cell_start.alloc(ncell + 2));
+    k_cell_of_point<DP><<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, Y, gp, cell.p, idx.p);
+    int bits = 1; while (bits < 32 && (1ull << bits) < ncell) bits++;
+    size_t tmp_bytes = 0, tb2 = 0, tb3 = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, cell.p, cell_s.p, idx.p, idx_s.p, (int64_t)n, 0, bits, ctx->stream));
+    CU(sorted.alloc(std::max(n, E)));
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tb2, radius.p, sorted.p, (int64_t)n, 0, 32, ctx->stream));
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tb3, ratio.p, sorted.p, (int64_t)E, 0, 32, ctx->stream));
+    CU(tmp.alloc(std::max(tmp_bytes, std::max(tb2, tb3))));
+    tmp_bytes = tmp.n;
+    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, cell.p, cell_s.p, idx.p, idx_s.p, (int64_t)n, 0, bits, ctx->stream));
+    k_cell_start<<<nblocks(n + 1, 256), 256, 0, ctx->stream>>>(n, ncell, cell_s.p, cell_start.p);
+    // embedder.rs:527-554 (exact instead of HNSW): distance to the nbng-th nearest embedded neighbour
+    k_knn_radius<DP><<<nblocks(n, 4), 128, 0, ctx->stream>>>(n, nbng, Y, gp, idx_s.p, cell_s.p, cell_start.p, radius.p);
+    // embedder.rs:646-674
+    k_quality_per_node<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr.p, t.p, radius.p, nodes_match.p, ratio.p, node_ratio.p, first_dist.p);
+    const unsigned int nb = std::min<unsigned int>(1023u, std::max(1u, nblocks(std::max(n, E), 256)));
+    k_quality_reduce<<<nb, 256, 0, ctx->stream>>>(n, E, nodes_match.p, ratio.p, ctx->partials.p);
+    ctx->st.kernel_launches += 8;
+    std::vector<double> hp(4 * nb);
+    CU(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = sync_stream(ctx))) return rc;
+    double sum_match = 0, n_zero = 0, sum_ratio = 0, n_finite = 0;
+    for (unsigned int i = 0; i < nb; i++) { sum_match += hp[4 * i]; n_zero += hp[4 * i + 1]; sum_ratio += hp[4 * i + 2]; n_finite += hp[4 * i + 3]; }
+    out->nb_without_match = (uint64_t)n_zero;                                                   // :676-678
+    out->mean_nbmatch = sum_match / std::max(1.0, (double)n - n_zero);                          // :679-680
+    out->knn_preservation = sum_match / (double)E;
+    out->mean_ratio = n_finite > 0 ? sum_ratio / n_finite : std::nan("");                       // :721-726
+    size_t tbx = tmp.n;
+    CU(cub::DeviceRadixSort::SortKeys(tmp.p, tbx, radius.p, sorted.p, (int64_t)n, 0, 32, ctx->stream));
+    if ((rc = device_quantiles(ctx, sorted.p, n, out->radius_quantiles))) return rc;           // :681-690
+    tbx = tmp.n;
+    CU(cub::DeviceRadixSort::SortKeys(tmp.p, tbx, ratio.p, sorted.p, (int64_t)E, 0, 32, ctx->stream));
+    if ((rc = device_quantiles(ctx, sorted.p, (uint64_t)n_finite, out->ratio_quantiles))) return rc;   // :695-714
+    ctx->st.kernel_launches += 2;
+    if (radius_out && (rc = d2h(ctx, radius_out, radius.p, n * sizeof(float)))) return rc;
+    if (first_dist_out && (rc = d2h(ctx, first_dist_out, first_dist.p, n * sizeof(float)))) return rc;   // first_dist.csv :729-735
+    if (node_ratio_out && (rc = d2h(ctx, node_ratio_out, node_ratio.p, n * sizeof(float)))) return rc;   // continuity_ratio.csv :737-743
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_quality_estimate(annembed_cuda_ctx *ctx, uint32_t nbng, annembed_cuda_quality *out,
+                                              float *radius_out, float *first_dist_out, float *node_ratio_out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(out, ANNEMBED_ERR_INVALID_ARG, "null output");
+    REQUIRE(ctx->have_graph && ctx->have_embedding, ANNEMBED_ERR_STATE, "quality_estimate: graph / embedding not set (embedder.rs:629-632)");
+    REQUIRE(nbng >= 1 && (uint64_t)nbng < ctx->n, ANNEMBED_ERR_INVALID_ARG, "nbng must be in 1..n-1");
+    REQUIRE(ctx->nranks == 1, ANNEMBED_ERR_UNSUPPORTED, "quality_estimate runs on one GPU");
+    CU(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    switch (ctx->DP) {
+    case 2: return quality_impl<2>(ctx, nbng, out, radius_out, first_dist_out, node_ratio_out);
+    case 4: return quality_impl<4>(ctx, nbng, out, radius_out, first_dist_out, node_ratio_out);
+    case 8: return quality_impl<8>(ctx, nbng, out, radius_out, first_dist_out, node_ratio_out);
+    case 16: return quality_impl<16>(ctx, nbng, out, radius_out, first_dist_out, node_ratio_out);
+    default: return quality_impl<32>(ctx, nbng, out, radius_out, first_dist_out, node_ratio_out);
+    }
 }
 
 extern "C" int annembed_cuda_debug_draws(annembed_cuda_ctx *ctx, uint32_t epoch, uint32_t *counts_out, uint32_t *neg_out)

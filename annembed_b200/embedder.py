@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AnnembedCudaError, Params, Stats, ptr
+from ._lib import AnnembedCudaError, Params, Quality, Stats, ptr
 from .embedparams import EmbedderParams
 from .kgraph import KGraph
 
@@ -183,6 +183,21 @@ class CudaContext:
         self._ck(self.lib.annembed_cuda_get_embedding(self.h, ptr(out, C.c_float)))
         return out
 
+    def quality_estimate(self, nbng: int, want_arrays: bool = False) -> dict:
+        q = Quality()
+        radius = np.empty(self.n, np.float32) if want_arrays else None
+        first = np.empty(self.n, np.float32) if want_arrays else None
+        nratio = np.empty(self.n, np.float32) if want_arrays else None
+        self._ck(self.lib.annembed_cuda_quality_estimate(self.h, nbng, C.byref(q), ptr(radius, C.c_float),
+                                                         ptr(first, C.c_float), ptr(nratio, C.c_float)))
+        out = {"nb_without_match": int(q.nb_without_match), "mean_nbmatch": q.mean_nbmatch,
+               "knn_preservation": q.knn_preservation, "mean_ratio": q.mean_ratio,
+               "radius_quantiles": list(q.radius_quantiles), "ratio_quantiles": list(q.ratio_quantiles),
+               "median_ratio": q.ratio_quantiles[2]}
+        if want_arrays:
+            out.update(radius=radius, first_dist=first, ratio_by_node=nratio)
+        return out
+
     def get_stats(self) -> dict:
         s = Stats()
         self._ck(self.lib.annembed_cuda_get_stats(self.h, C.byref(s)))
@@ -241,6 +256,7 @@ class Embedder:
         self.device = device
         self.comm = comm                          # (rank, nranks, unique_id) or None
         self.fused_exchange = fused_exchange      # peer-memory stores from the epoch kernel instead of an all-gather
+        self.write_quality_csv = False            # the reference dumps first_dist.csv / continuity_ratio.csv (embedder.rs:729-743)
         self.stats = {}
 
     @classmethod
@@ -337,6 +353,27 @@ class Embedder:
             if ctx is not None:
                 ctx.close()
         return 1
+
+    def get_quality_estimate_from_edge_length(self, nbng: int) -> dict:
+        """≙ embedder.rs:620-753 on the device (annembed_cuda_quality_estimate).  Returns the statistics the reference
+        prints (it returns Some(0.) itself) and writes first_dist.csv / continuity_ratio.csv in the CWD like it does."""
+        if self.embedding is None:
+            raise RuntimeError("cannot ask for embedded quality before embedding (embedder.rs:629-632)")
+        from .io import write_csv_labeled_array2
+        ctx = CudaContext(self.parameters, self.device)
+        try:
+            ctx.set_graph_csr(*self.kgraph.get_neighbours())
+            ctx.set_embedding(self.embedding)
+            q = ctx.quality_estimate(nbng, want_arrays=True)
+        except AnnembedCudaError as e:
+            raise EmbedError(str(e)) from e
+        finally:
+            ctx.close()
+        if self.write_quality_csv:
+            re = self.get_embedded_reindexed()
+            write_csv_labeled_array2("first_dist.csv", q["first_dist"], re)
+            write_csv_labeled_array2("continuity_ratio.csv", q["ratio_by_node"], re)
+        return q
 
     # --- results, embedder.rs:378-453
     def get_embedded(self):

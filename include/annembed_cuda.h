@@ -169,6 +169,22 @@ int annembed_cuda_cross_entropy(annembed_cuda_ctx *ctx, double *out);
  * DataId order exactly as get_embedded_reindexed does (embedder.rs:384-405). */
 int annembed_cuda_get_embedding(annembed_cuda_ctx *ctx, float *y_out);
 
+/* N3 ≙ Embedder::get_quality_estimate_from_edge_length(nbng) (embedder.rs:620-753) on the current layout:
+ * neighbourhood conservation statistics.  The radius (distance to the nbng-th nearest embedded neighbour) is exact
+ * (uniform-grid search) where the reference rebuilds an HNSW on the embedded points (embedder.rs:527-554); quantiles
+ * are exact where the reference uses CKMS(0.01).  Optional per-node outputs ≙ the csv dumps at :729-743. */
+typedef struct annembed_cuda_quality {
+    uint64_t nb_without_match;     /* neighbourhoods without a match, :676-678 */
+    double   mean_nbmatch;         /* mean number of neighbours conserved when match, :679-680 */
+    double   knn_preservation;     /* sum of matches / number of edges */
+    double   mean_ratio;           /* mean of edge length / radius, :721-726 */
+    double   radius_quantiles[6];  /* 0.05 0.25 0.5 0.75 0.85 0.95 of the embedded radii, :681-690 */
+    double   ratio_quantiles[6];   /* same quantiles of edge length / radius, :695-714 */
+} annembed_cuda_quality;
+int annembed_cuda_quality_estimate(annembed_cuda_ctx *ctx, uint32_t nbng, annembed_cuda_quality *out,
+                                   float *radius_out /*[n] nullable*/, float *first_dist_out /*[n] nullable*/,
+                                   float *node_ratio_out /*[n] nullable*/);
+
 int annembed_cuda_get_stats(annembed_cuda_ctx *ctx, annembed_cuda_stats *stats);
 int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx);
 
