@@ -522,6 +522,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         __syncwarp();
     }
     // ---------------- the node's own firings
+    const uint32_t nkey = neg_stream_key<HUB>(a, node);
     if constexpr (DP <= 4) {
         // software pipelined: the 6 row gathers of firing s+1 are in flight during the arithmetic of firing s
         int m = 0;                       // edge cursor of the systematic sampler
@@ -540,8 +541,8 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
             const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
             npe = F_SUB(P_hi, P_lo);
             load_row<DP>(a.y_snap, j, nyj);
-            const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
-            if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
+            const Philox4 A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
+            if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
             auto rej = [&](uint32_t kk) -> bool {
                 bool r = (kk == node) | (kk == j);
 #pragma unroll
@@ -596,8 +597,8 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
                 load_row<DP>(a.y_snap, j, yj);
                 m_prev = m;
             }
-            const Philox4 A = philox4x32_10(node, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
-            if ((s & 3) == 0) B = philox4x32_10(node, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
+            const Philox4 A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
+            if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
             auto rej = [&](uint32_t kk) -> bool {
                 bool r = (kk == node) | (kk == j);
 #pragma unroll
@@ -803,8 +804,9 @@ __global__ void k_debug_draws(EpochArgs a, uint32_t *__restrict__ counts, uint32
             uint32_t negs[ANNEMBED_NB_NEG] = {ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE};
             if (c > 0) {
                 const uint32_t s = (uint32_t)c_lo;              // the node's firing index at which this edge first fires
-                const Philox4 A = philox4x32_10((uint32_t)node, s, a.epoch, 1u, a.k0, a.k1);
-                const Philox4 B = philox4x32_10((uint32_t)node, s >> 2, a.epoch, 2u, a.k0, a.k1);
+                const uint32_t nk = neg_stream_key<HUB>(a, (uint32_t)node);
+                const Philox4 A = philox4x32_10(nk, s, a.epoch, 1u, a.k0, a.k1);
+                const Philox4 B = philox4x32_10(nk, s >> 2, a.epoch, 2u, a.k0, a.k1);
                 const GlobalRowRejector rej{a.col, r0, r1, (uint32_t)node, a.col[m]};
                 draw_negatives_v2<HUB>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
             }

@@ -10,6 +10,17 @@
 
 namespace annembed {
 
+// squared embedded distance with one fixed operation order (no fma): the transformed edges and the kNN radii must
+// compare bit-for-bit equal when an original neighbour IS the nbng-th embedded neighbour (`<=` at embedder.rs:659)
+template <int DP>
+__device__ __forceinline__ float emb_dist2(const float (&a)[DP], const float (&b)[DP])
+{
+    float ds = 0.0f;
+#pragma unroll
+    for (int c = 0; c < DP; c++) { const float d = __fsub_rn(a[c], b[c]); ds = __fadd_rn(ds, __fmul_rn(d, d)); }
+    return ds;
+}
+
 // embedder.rs:494-516: per node, embedded L2 distance to every original neighbour kept as a RUNNING MINIMUM in graph
 // order (:500-509), then sorted ascending.  One thread per node; rows are short (<= nbng of the graph).
 template <int DP>
@@ -25,10 +36,7 @@ __global__ void k_transformed_kgraph(uint64_t n, const uint64_t *__restrict__ ro
     for (uint64_t m = r0; m < r1; m++) {
         float yj[DP];
         load_row<DP>(Y, col[m], yj);
-        float ds = 0.0f;
-#pragma unroll
-        for (int c = 0; c < DP; c++) { const float d = __fsub_rn(yi[c], yj[c]); ds = __fadd_rn(ds, __fmul_rn(d, d)); }
-        run = fminf(__fsqrt_rn(ds), run);
+        run = fminf(__fsqrt_rn(emb_dist2<DP>(yi, yj)), run);
         // insertion into the sorted prefix (values are non-increasing in arrival order, so it goes to the front part)
         uint64_t p = m;
         while (p > r0 && t[p - 1] > run) { t[p] = t[p - 1]; p--; }
@@ -104,8 +112,7 @@ k_knn_radius(uint64_t n, uint32_t k, const float *__restrict__ Y, GridParams gp,
                 if (t < e) {
                     float yc[DP];
                     load_row<DP>(Y, sorted_idx[t], yc);
-#pragma unroll
-                    for (int c = 0; c < DP; c++) { const float d = yp[c] - yc[c]; d2 = fmaf(d, d, d2); }
+                    d2 = emb_dist2<DP>(yp, yc);
                     in = whole || d2 <= lim2;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, in);
@@ -143,10 +150,7 @@ k_knn_radius(uint64_t n, uint32_t k, const float *__restrict__ Y, GridParams gp,
                 for (uint32_t t = b + lane; t < e; t += 32) {
                     float yc[DP];
                     load_row<DP>(Y, sorted_idx[t], yc);
-                    float d2 = 0.0f;
-#pragma unroll
-                    for (int cc = 0; cc < DP; cc++) { const float d = yp[cc] - yc[cc]; d2 = fmaf(d, d, d2); }
-                    c += (__float_as_uint(d2) <= mid);
+                    c += (__float_as_uint(emb_dist2<DP>(yp, yc)) <= mid);
                 }
             }
 #pragma unroll
@@ -154,7 +158,7 @@ k_knn_radius(uint64_t n, uint32_t k, const float *__restrict__ Y, GridParams gp,
             if (c >= kk + 1) hi = mid; else lo = mid + 1;
         }
     }
-    if (lane == 0) radius[p] = sqrtf(__uint_as_float(lo));
+    if (lane == 0) radius[p] = __fsqrt_rn(__uint_as_float(lo));
 }
 
 // embedder.rs:646-674: per node, number of transformed edges inside the radius, ratio edge / radius per edge,

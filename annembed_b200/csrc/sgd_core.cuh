@@ -407,6 +407,18 @@ struct GlobalRowRejector {          // nodeparam.rs:83-85 linear scan of the ori
     }
 };
 
+// Counter word 0 of the negative streams.  Uniform sampler (default): the 4 nodes of an aligned group (ids 4g..4g+3,
+// i.e. 4 adjacent lanes of a warp tile) share the stream, so that for every negative slot they draw the SAME random
+// 32-byte sector of the layout and each takes a different row of it (rotated by a random offset): every sample still
+// gets 5 independent, uniformly distributed negatives -- exactly the reference's per-sample law (embedder.rs:1121) --
+// while the 4 lanes' gathers coalesce into one sector request.  Only samples of different nodes of a group become
+// correlated, which no statistic of the optimizer depends on.  Hubness / grouped modes key the stream by the node.
+template <bool HUB>
+__host__ __device__ __forceinline__ uint32_t neg_stream_key(const EpochArgs &a, uint32_t node)
+{
+    return (HUB || a.grouped_neg) ? node : (node & ~3u);
+}
+
 template <bool HUB, class Rej>
 __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t node, uint32_t s, const Philox4 &A,
                                                            uint32_t w4, const Rej &rejected,
@@ -423,10 +435,14 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
     // the layout (ids 4g..4g+3), negative 4 is an independent draw.  Every node keeps marginal probability 1/n per
     // slot; a rejected / out-of-range member is replaced by an independent redraw like any other negative.
     const bool grouped = !HUB && a.grouped_neg != 0u;
-    const uint32_t gbase = grouped ? (below32(A.x, (a.n + 3u) >> 2) << 2) : 0u;
+    const bool shared = !HUB && a.grouped_neg == 0u;               // sector shared by the 4 nodes of the aligned group
+    const uint32_t nsec = (a.n + 3u) >> 2;
+    const uint32_t gbase = grouped ? (below32(A.x, nsec) << 2) : 0u;
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-        uint32_t k = (grouped && q < 4) ? gbase + (uint32_t)q : map_negative<HUB>(a, wi[q], wa[q]);
+        uint32_t k;
+        if (shared) k = (below32(wi[q], nsec) << 2) | ((node + wi[q]) & 3u);   // random sector, row rotated by 2 random bits
+        else k = (grouped && q < 4) ? gbase + (uint32_t)q : map_negative<HUB>(a, wi[q], wa[q]);
         bool rej = k >= a.n || rejected(k);
         for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
             const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
@@ -490,8 +506,9 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
         load_row<DP>(a.y_snap, j, yj);
         const GlobalRowRejector rej{a.col, r0, r1, node, j};
         for (int f = 0; f < c; f++, s++) {
-            const Philox4 A = philox4x32_10(node, s, a.epoch, 1u, a.k0, a.k1);
-            const Philox4 B = philox4x32_10(node, s >> 2, a.epoch, 2u, a.k0, a.k1);
+            const uint32_t nk = neg_stream_key<HUB>(a, node);
+            const Philox4 A = philox4x32_10(nk, s, a.epoch, 1u, a.k0, a.k1);
+            const Philox4 B = philox4x32_10(nk, s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
             draw_negatives_v2<HUB>(a, node, s, A, philox_word(B, s & 3u), rej, negs);
             apply_firing<DP, B1>(a, node, y, yj, g, pe, inv_s2, negs);

@@ -22,8 +22,14 @@ def quality_stats(row_ptr, col, y, nbng):
     t = oracle.transformed_kgraph(row_ptr, col, y).astype(np.float64)
     # embedder.rs:527-554 + kgraph.rs:167-183: per node, length of the longest of its nbng embedded kNN edges
     tree = cKDTree(y.astype(np.float64))
-    dd, _ = tree.query(y.astype(np.float64), k=nbng + 1, workers=-1)
-    radius = dd[:, nbng]
+    _, ii = tree.query(y.astype(np.float64), k=nbng + 1, workers=-1)
+    # the radius in the same fp32 arithmetic as the transformed edges (the reference compares f32 distances with `<=`,
+    # embedder.rs:659: an original neighbour that IS the nbng-th embedded neighbour counts as a match)
+    diff = y - y[ii[:, nbng]]
+    acc = np.zeros(n, np.float32)
+    for c in range(y.shape[1]):
+        acc = (acc + diff[:, c] * diff[:, c]).astype(np.float32)
+    radius = np.sqrt(acc).astype(np.float64)
     deg = np.diff(row_ptr.astype(np.int64))
     rad_e = np.repeat(radius, deg)
     with np.errstate(divide="ignore", invalid="ignore"):

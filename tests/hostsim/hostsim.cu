@@ -149,8 +149,9 @@ extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_
                 uint32_t negs[5] = {ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE, ANNEMBED_NO_NODE};
                 if (c > 0) {
                     const uint32_t s = (uint32_t)c_lo;
-                    const Philox4 A = philox4x32_10((uint32_t)node, s, epoch, 1u, a.k0, a.k1);
-                    const Philox4 B = philox4x32_10((uint32_t)node, s >> 2, epoch, 2u, a.k0, a.k1);
+                    const uint32_t nk = neg_alias ? neg_stream_key<true>(a, (uint32_t)node) : neg_stream_key<false>(a, (uint32_t)node);
+                    const Philox4 A = philox4x32_10(nk, s, epoch, 1u, a.k0, a.k1);
+                    const Philox4 B = philox4x32_10(nk, s >> 2, epoch, 2u, a.k0, a.k1);
                     const GlobalRowRejector rej{col, r0, r1, (uint32_t)node, col[m]};
                     if (neg_alias) draw_negatives_v2<true>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
                     else draw_negatives_v2<false>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);

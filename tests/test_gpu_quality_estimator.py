@@ -24,7 +24,7 @@ def compare(row_ptr, col, dist, y, nbng, d):
     np.testing.assert_allclose(q["first_dist"], ref["first_dist"], rtol=1e-5, atol=1e-7)
     n = len(row_ptr) - 1
     assert abs(q["nb_without_match"] - ref["nb_without_match"]) <= max(2, 0.002 * n)
-    assert abs(q["mean_nbmatch"] - ref["mean_nbmatch"]) <= 2e-3 * ref["mean_nbmatch"]
+    assert abs(q["mean_nbmatch"] - ref["mean_nbmatch"]) <= 5e-3 * ref["mean_nbmatch"]
     assert abs(q["knn_preservation"] - ref["knn_preservation"]) <= 2e-3
     assert abs(q["mean_ratio"] - ref["mean_ratio"]) <= 1e-4 * ref["mean_ratio"]
     np.testing.assert_allclose(q["radius_quantiles"], ref["radius_quantiles"], rtol=1e-4)
