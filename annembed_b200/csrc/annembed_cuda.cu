@@ -1436,7 +1436,6 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
     a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;
-    a.grouped_neg = (ctx->prm.flags & ANNEMBED_FLAG_GROUPED_NEGATIVES) ? 1u : 0u;
     a.n_peers = 0;
     for (int r = 0; r < 7; r++) a.peer_next[r] = nullptr;
     a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);

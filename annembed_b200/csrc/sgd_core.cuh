@@ -231,7 +231,6 @@ struct EpochArgs {
     uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
     uint32_t n_peers;                    // fused exchange: replicas of y_next on the other ranks (peer memory over NVLink)
     float *peer_next[7];
-    uint32_t grouped_neg;                // ANNEMBED_FLAG_GROUPED_NEGATIVES: 4 of the 5 negatives share one 32-byte sector
     uint32_t n, lo, hi;
     uint32_t epoch, k0, k1;
     float kappa;                        // expected firings of edge e in this mini-epoch = kappa * p_e
@@ -412,11 +411,11 @@ struct GlobalRowRejector {          // nodeparam.rs:83-85 linear scan of the ori
 // 32-byte sector of the layout and each takes a different row of it (rotated by a random offset): every sample still
 // gets 5 independent, uniformly distributed negatives -- exactly the reference's per-sample law (embedder.rs:1121) --
 // while the 4 lanes' gathers coalesce into one sector request.  Only samples of different nodes of a group become
-// correlated, which no statistic of the optimizer depends on.  Hubness / grouped modes key the stream by the node.
+// correlated, which no statistic of the optimizer depends on.  The hubness sampler keys the stream by the node.
 template <bool HUB>
 __host__ __device__ __forceinline__ uint32_t neg_stream_key(const EpochArgs &a, uint32_t node)
 {
-    return (HUB || a.grouped_neg) ? node : (node & ~3u);
+    return HUB ? node : (node & ~3u);
 }
 
 template <bool HUB, class Rej>
@@ -431,18 +430,12 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
         const Philox4 D = philox4x32_10(node, s, a.epoch, 4u, a.k0, a.k1);
         wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = D.x;
     }
-    // grouped mode (uniform sampler only): negatives 0..3 are the 4 nodes of one uniformly drawn 32-byte sector of
-    // the layout (ids 4g..4g+3), negative 4 is an independent draw.  Every node keeps marginal probability 1/n per
-    // slot; a rejected / out-of-range member is replaced by an independent redraw like any other negative.
-    const bool grouped = !HUB && a.grouped_neg != 0u;
-    const bool shared = !HUB && a.grouped_neg == 0u;               // sector shared by the 4 nodes of the aligned group
     const uint32_t nsec = (a.n + 3u) >> 2;
-    const uint32_t gbase = grouped ? (below32(A.x, nsec) << 2) : 0u;
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
         uint32_t k;
-        if (shared) k = (below32(wi[q], nsec) << 2) | ((node + wi[q]) & 3u);   // random sector, row rotated by 2 random bits
-        else k = (grouped && q < 4) ? gbase + (uint32_t)q : map_negative<HUB>(a, wi[q], wa[q]);
+        if constexpr (HUB) k = map_negative<HUB>(a, wi[q], wa[q]);
+        else k = (below32(wi[q], nsec) << 2) | ((node + wi[q]) & 3u);          // random sector, row rotated by 2 random bits
         bool rej = k >= a.n || rejected(k);
         for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
             const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);

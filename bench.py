@@ -49,11 +49,11 @@ def parse():
     ap.add_argument("--batches", type=int, default=40)
     ap.add_argument("--mini-epochs", type=int, default=0)
     ap.add_argument("--hubness", type=int, default=0)
-    ap.add_argument("--flags", type=int, default=0, help="ANNEMBED_FLAG_* bits (4 = grouped negatives, opt-in)")
+    ap.add_argument("--flags", type=int, default=0, help="ANNEMBED_FLAG_* bits")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per bounded oracle sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="(kept for command-line compatibility; no variants are measured)")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-gather instead of the fused peer-store exchange")
     return ap.parse_args()
 
@@ -254,26 +254,6 @@ def run_ours(a):
     launches = st["kernel_launches"]
     mini = st["mini_epochs_per_batch"]
 
-    # ---- opt-in variant: grouped negatives (ANNEMBED_FLAG_GROUPED_NEGATIVES), reported beside the default, never as it
-    variant = None
-    if world == 1 and not a.flags and not a.no_variants:
-        import dataclasses
-        vctx = A.CudaContext(dataclasses.replace(params, flags=4), device=local)
-        vctx.set_graph_csr(row_ptr, col, distances)
-        vctx.set_embedding(y0)
-        for it in range(2):                              # one warm-up, one timed
-            vctx.reset_embedding()
-            torch.cuda.synchronize()
-            tv = time.perf_counter()
-            vctx.edge_weights(want_outputs=False)
-            vctx.optimize(want_ce=True)
-            tv = time.perf_counter() - tv
-        vs = vctx.get_stats()
-        variant = {"flags": 4, "what": "4 of the 5 negatives of a sample share one 32-byte sector (same marginals)",
-                   "value": 6.0 * vs["positive_samples"] / tv, "unit": UNIT, "ms_per_step": 1e3 * tv,
-                   "avg_epoch_ms": vs["epoch_kernel_ms"] / max(1, vs["epoch_launches"])}
-        vctx.close()
-
     # ---- end to end through the public host API (pinned host buffers -> embed() -> host result)
     e2e = None
     if not a.no_e2e:
@@ -341,8 +321,6 @@ def run_ours(a):
             "gpu_launches": int(launches_all),
             "clocks": clk,
         }
-        if variant is not None:
-            line["variants"] = {"grouped_negatives": variant}
         if e2e is not None:
             line["e2e"] = {"value": 6.0 * e2e_s / e2e_tmax, "unit": UNIT, "h2d_bytes_per_step": int(e2e[2]),
                            "d2h_bytes_per_step": int(e2e[3]), "ms_per_step": 1e3 * e2e_tmax / a.steps,

@@ -66,8 +66,6 @@ typedef struct annembed_cuda_params {
 #define ANNEMBED_FLAG_NONE 0u
 #define ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL 1u   /* force the thread-per-node epoch kernel (cross-check of the tiled one) */
 #define ANNEMBED_FLAG_NO_L2_PERSIST 2u
-#define ANNEMBED_FLAG_GROUPED_NEGATIVES 4u       /* opt-in: 4 of the 5 negatives of a sample are the nodes of one uniformly drawn
-                                                   32-byte sector of the layout (ids 4g..4g+3): same marginals, 1 gather for 4 */            /* do not pin the layout snapshot in L2 (A/B measurements) */
 
 typedef struct annembed_cuda_stats {
     double   edge_weights_ms;      /* K0+K1 device time, last call */

@@ -28,8 +28,6 @@ struct HostCtx {
 };
 static int g_version = 2;   // 2 = the product's systematic sampler; 1 = first design (per-edge counts), kept for studies
 extern "C" void hostsim_set_version(int v) { g_version = v; }
-static int g_grouped = 0;
-extern "C" void hostsim_set_grouped(int v) { g_grouped = v; }
 extern "C" void hostsim_philox2(const uint32_t ctr[2], uint32_t key, uint32_t out[2])
 {
     Philox2 r = philox2x32_10(ctr[0], ctr[1], key);
@@ -106,7 +104,7 @@ extern "C" int64_t hostsim_optimize(uint64_t n, uint32_t d, const uint64_t *row_
             a.row_ptr = row_ptr; a.col = col; a.p = p; a.inv_s2 = h.inv_s2.data();
             a.in_ptr = h.in_ptr.data(); a.in_rec = h.in_rec.data(); a.in_base = 0; a.in_own = nullptr;
             a.neg_alias = (const uint2 *)neg_alias;
-            a.regular_k = 0; a.grouped_neg = (uint32_t)g_grouped; a.cum = h.cum.data(); a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+            a.regular_k = 0; a.cum = h.cum.data(); a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
             a.n = (uint32_t)n; a.lo = 0; a.hi = (uint32_t)n;
             a.epoch = (iter - 1) * M + m; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
             a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
@@ -134,7 +132,7 @@ extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_
     EpochArgs a;
     memset(&a, 0, sizeof a);
     a.row_ptr = row_ptr; a.col = col; a.p = p; a.neg_alias = (const uint2 *)neg_alias; a.cum = cum.data();
-    a.n = (uint32_t)n; a.epoch = epoch; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32); a.grouped_neg = (uint32_t)g_grouped;
+    a.n = (uint32_t)n; a.epoch = epoch; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
     a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
     a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
     for (uint64_t node = 0; node < n; node++) {

@@ -26,10 +26,6 @@ def set_version(v):
     lib().hostsim_set_version(C.c_int(v))
 
 
-def set_grouped(v):
-    lib().hostsim_set_grouped(C.c_int(v))
-
-
 def philox2(ctr, key):
     ctr = np.asarray(ctr, np.uint32); out = np.zeros(2, np.uint32)
     lib().hostsim_philox2(_p(ctr, C.c_uint32), C.c_uint32(key), _p(out, C.c_uint32))
