@@ -431,18 +431,30 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
         wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = D.x;
     }
     const uint32_t nsec = (a.n + 3u) >> 2;
+    // first draw of the 5 negatives, branch-free; the redraws (probability ~ (deg+2)/n per negative) are a rare path
+    bool any_rej = false;
+    bool rej[ANNEMBED_NB_NEG];
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
         uint32_t k;
         if constexpr (HUB) k = map_negative<HUB>(a, wi[q], wa[q]);
         else k = (below32(wi[q], nsec) << 2) | ((node + wi[q]) & 3u);          // random sector, row rotated by 2 random bits
-        bool rej = k >= a.n || rejected(k);
-        for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
-            const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
-            k = map_negative<HUB>(a, R.x, R.y);
-            rej = rejected(k);
+        rej[q] = k >= a.n || rejected(k);
+        any_rej |= rej[q];
+        negs[q] = k;
+    }
+    if (any_rej) {
+#pragma unroll
+        for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+            uint32_t k = negs[q];
+            bool r = rej[q];
+            for (uint32_t t = 0; r && t < ANNEMBED_MAX_REDRAW; t++) {
+                const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
+                k = map_negative<HUB>(a, R.x, R.y);
+                r = rejected(k);
+            }
+            negs[q] = r ? ANNEMBED_NO_NODE : k;
         }
-        negs[q] = rej ? ANNEMBED_NO_NODE : k;
     }
 }
 
