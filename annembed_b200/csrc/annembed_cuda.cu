@@ -655,6 +655,8 @@ k_epoch_in(EpochArgs a)
     }
     const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
     const uint8_t *ownp = a.in_own + (Q0 - a.in_base) + lane;
+    // log2(longest in-edge segment of the tile, capped at a round) scan steps compose any owner's maps of a round
+    const int max_len = __reduce_max_sync(0xffffffffu, valid ? (int)min((uint64_t)32, my_q1 - my_q0) : 0);
     float alpha_tot = 1.0f, beta_tot[DP];                      // composite of all rounds, applied once at the end
 #pragma unroll
     for (int c = 0; c < DP; c++) beta_tot[c] = 0.0f;
@@ -682,6 +684,9 @@ k_epoch_in(EpochArgs a)
         if (32 + lane < n_in) { rec2 = __ldcs(recp + 32); own2 = __ldcs(ownp + 32); }
         prepare(rec1, own1, lane < n_in);
     }
+    const uint4 *recp2 = recp + 32;                            // slot of this lane in the round after next
+    const uint8_t *ownp2 = ownp + 32;
+    int left = (int)n_in - 32 - lane;                          // > 0 iff that slot holds an in-edge
     for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
         const int c = nc;
         const uint32_t own = nown;
@@ -692,8 +697,9 @@ k_epoch_in(EpochArgs a)
         {   // prepare the next round (its records were loaded one iteration ago), fetch the records after it
             const uint4 rec1 = rec2;
             const uint32_t own1 = own2;
-            if (base_q + 64 + lane < n_in) { rec2 = __ldcs(recp + base_q + 64); own2 = __ldcs(ownp + base_q + 64); }
-            prepare(rec1, own1, base_q + 32 + lane < n_in);
+            recp2 += 32; ownp2 += 32; left -= 32;               // `left` = in-edges from this lane's slot two rounds ahead
+            if (left > 0) { rec2 = __ldcs(recp2); own2 = __ldcs(ownp2); }
+            prepare(rec1, own1, left + 32 > 0);
         }
         // the affine map of this lane's in-edge: y -> alpha y + beta  (identity when it did not fire)
         float alpha = 1.0f, beta[DP];
@@ -710,10 +716,7 @@ k_epoch_in(EpochArgs a)
 #pragma unroll
             for (int cc = 0; cc < DP; cc++) beta[cc] = F_MUL(-A, ys[cc]);
         }
-        // segmented inclusive scan (composition in index order) over the lanes of each owner; log2(longest segment of
-        // the round) steps are enough
-        const int my_len = max(0, min(32, rel_hi)) - max(0, min(32, rel_lo));
-        const int max_len = __reduce_max_sync(0xffffffffu, my_len);
+        // segmented inclusive scan (composition in index order) over the lanes of each owner
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             if (d >= max_len) break;
