@@ -533,7 +533,31 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         float npe = 0.0f;
         float nyj[DP], nyk[ANNEMBED_NB_NEG][DP];
         unsigned nuse = 0;
-        auto prepare = [&](int s) {
+        // The 4 lanes of an aligned group share their negative streams (neg_stream_key): with at most 3 firings per
+        // node they need 4 Philox blocks in all (firings 0..2 and the block of the fifth words) -- one per lane,
+        // exchanged by shuffles -- instead of 4 blocks per lane.  The loop trip count is made warp-uniform for that.
+        const int Tmax = __reduce_max_sync(0xffffffffu, T);
+        const bool share = !HUB && Tmax <= 3;
+        Philox4 blk;
+        blk.x = blk.y = blk.z = blk.w = 0u;
+        if (share) {
+            const uint32_t r = (uint32_t)lane & 3u;
+            blk = (r < 3u) ? philox4x32_10(nkey, r, a.epoch, 1u, a.k0, a.k1) : philox4x32_10(nkey, 0u, a.epoch, 2u, a.k0, a.k1);
+        }
+        auto fetch = [&](int s, Philox4 &A, uint32_t &w4) {     // executed by the whole warp
+            if (share) {
+                const int src = (lane & ~3) + s;
+                A.x = __shfl_sync(0xffffffffu, blk.x, src); A.y = __shfl_sync(0xffffffffu, blk.y, src);
+                A.z = __shfl_sync(0xffffffffu, blk.z, src); A.w = __shfl_sync(0xffffffffu, blk.w, src);
+                const uint32_t comp = s == 0 ? blk.x : (s == 1 ? blk.y : blk.z);
+                w4 = __shfl_sync(0xffffffffu, comp, (lane & ~3) + 3);
+            } else {
+                A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
+                if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
+                w4 = philox_word(B, (uint32_t)s & 3u);
+            }
+        };
+        auto prepare = [&](int s, const Philox4 &A, uint32_t w4) {
             while ((int)s_ch[lane * RS + m] <= s) m++;          // ch[k-1] == T > s
             nm = m;
             const uint32_t j = s_col[lane * RS + m];
@@ -541,8 +565,6 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
             const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
             npe = F_SUB(P_hi, P_lo);
             load_row<DP>(a.y_snap, j, nyj);
-            const Philox4 A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
-            if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
             auto rej = [&](uint32_t kk) -> bool {
                 bool r = (kk == node) | (kk == j);
 #pragma unroll
@@ -550,7 +572,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
                 return r;
             };
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
+            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, w4, rej, negs);
             nuse = 0;
 #pragma unroll
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
@@ -559,26 +581,33 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
                 load_row<DP>(a.y_snap, ok ? negs[q] : node, nyk[q]);
             }
         };
-        if (T > 0) prepare(0);
-        for (int s = 0; s < T; s++) {
-            float yk[ANNEMBED_NB_NEG][DP];
-            const float pe = npe;
-            const unsigned use = nuse;
-            if (nm != m_cur) {
+        Philox4 An;
+        uint32_t w4n = 0;
+        An.x = An.y = An.z = An.w = 0u;
+        if (Tmax > 0) fetch(0, An, w4n);
+        if (T > 0) prepare(0, An, w4n);
+        for (int s = 0; s < Tmax; s++) {
+            if (s + 1 < Tmax) fetch(s + 1, An, w4n);
+            if (s < T) {
+                float yk[ANNEMBED_NB_NEG][DP];
+                const float pe = npe;
+                const unsigned use = nuse;
+                if (nm != m_cur) {
 #pragma unroll
-                for (int c = 0; c < DP; c++) yj[c] = nyj[c];
-                m_cur = nm;
+                    for (int c = 0; c < DP; c++) yj[c] = nyj[c];
+                    m_cur = nm;
+                }
+#pragma unroll
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
+#pragma unroll
+                    for (int c = 0; c < DP; c++) yk[q][c] = nyk[q][c];
+                if (s + 1 < T) prepare(s + 1, An, w4n);
+#pragma unroll
+                for (int c = 0; c < DP; c++) g[c] = 0.0f;
+                attract<DP, true>(y, yj, g, pe, inv_s2, a.K);
+#pragma unroll
+                for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, yk[q], g, inv_s2, a.K, (use >> q) & 1u);
             }
-#pragma unroll
-            for (int q = 0; q < ANNEMBED_NB_NEG; q++)
-#pragma unroll
-                for (int c = 0; c < DP; c++) yk[q][c] = nyk[q][c];
-            if (s + 1 < T) prepare(s + 1);
-#pragma unroll
-            for (int c = 0; c < DP; c++) g[c] = 0.0f;
-            attract<DP, true>(y, yj, g, pe, inv_s2, a.K);
-#pragma unroll
-            for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, yk[q], g, inv_s2, a.K, (use >> q) & 1u);
         }
     } else {
         // wide rows: the prefetch registers do not fit, plain sequential firings
