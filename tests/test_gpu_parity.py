@@ -262,7 +262,7 @@ def test_tiled_epoch_kernel_equals_generic_kernel(d, kmax, hub, M):
 
 def test_rows_longer_than_16_use_the_generic_kernel():
     row_ptr, col, dist = random_graph(3000, 17, 40, seed=73)
-    ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=3, grad_step=1.0)
+    ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=3, grad_step=1.0, mini_epochs_per_batch=60)
     scale, p = ctx.edge_weights()
     es = ctx.get_embedded_scales()
     y0 = np.random.default_rng(2).uniform(-1, 1, size=(3000, 2)).astype(np.float32)
