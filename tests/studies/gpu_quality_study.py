@@ -33,4 +33,4 @@ for M in Ms:
         ctx = A.CudaContext(A.EmbedderParams(nb_grad_batch=30, grad_step=1.0, seed=100 + s, mini_epochs_per_batch=M, flags=FLAGS))
         ctx.set_graph_csr(row_ptr, col, dist); ctx.edge_weights(want_outputs=False); ctx.set_embedding(y0)
         ctx.optimize(want_ce=False); ys.append(ctx.get_embedding()); Meff = ctx.get_stats()["mini_epochs_per_batch"]; ctx.close()
-    summarize(f"cuda M={Meff} flags={FLAGS}", ys, (time.time() - t) / RUNS)
+    summarize(f"cuda M={M if M else 'graded(' + str(Meff) + ')'} flags={FLAGS}", ys, (time.time() - t) / RUNS)

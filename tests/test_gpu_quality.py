@@ -12,16 +12,13 @@ from oracle import oracle, quality
 
 pytestmark = pytest.mark.gpu
 
-N, K, NBNG, RUNS = 20000, 10, 50, 3
+N, NBNG, RUNS = 20000, 50, 3
 
 
 @pytest.fixture(scope="module")
-def problem():
+def data():
     x, _ = workloads.gaussian_mixture(N, 784, seed=0)
-    idx, dist = workloads.knn_exact(x, K, device="cuda")
-    row_ptr, col, dist = workloads.csr_from_knn(idx, dist)
-    y0 = workloads.pca_init(x, 2)
-    return row_ptr, col, dist, y0
+    return x, workloads.pca_init(x, 2)
 
 
 def mean_stats(stats):
@@ -29,17 +26,25 @@ def mean_stats(stats):
     return {k: float(np.mean([s[k] for s in stats])) for k in keys}
 
 
-def test_quality_statistics_within_one_percent_of_oracle(problem):
-    row_ptr, col, dist, y0 = problem
-    scale, p = oracle.edge_weights(row_ptr, col, dist, 1.0, 1.0)
+# (kNN, scale_rho, batches, hubness): examples/mnist_digits.rs:92-100 and examples/higgs.rs:204-211,234
+@pytest.mark.parametrize("k,scale_rho,nb_batch,hub", [(10, 1.0, 30, False), (6, 0.75, 40, True)])
+def test_quality_statistics_within_one_percent_of_oracle(data, k, scale_rho, nb_batch, hub):
+    x, y0 = data
+    idx, dist = workloads.knn_exact(x, k, device="cuda")
+    row_ptr, col, dist = workloads.csr_from_knn(idx, dist)
+    scale, p = oracle.edge_weights(row_ptr, col, dist, scale_rho, 1.0)
     es = oracle.embedded_scales(scale)
+    neg_w = oracle.hubness_weights(row_ptr, col) if hub else None
     ref, ours = [], []
     for seed in range(RUNS):
-        y, _ = oracle.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, 10, 30, seed=seed + 1)
+        y, _ = oracle.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, 10, nb_batch, neg_w=neg_w, seed=seed + 1)
         ref.append(quality.quality_stats(row_ptr, col, y, NBNG))
-        ctx = A.CudaContext(A.EmbedderParams(nb_grad_batch=30, grad_step=1.0, seed=100 + seed))
+        ctx = A.CudaContext(A.EmbedderParams(nb_grad_batch=nb_batch, grad_step=1.0, scale_rho=scale_rho, seed=100 + seed,
+                                             hubness_weighting=hub))
         ctx.set_graph_csr(row_ptr, col, dist)
         ctx.edge_weights(want_outputs=False)
+        if hub:
+            ctx.set_neg_weights(np.clip(ctx.get_hubness_counts().astype(np.float32), 1.0, float(N)))
         ctx.set_embedding(y0)
         ce0, ce1 = ctx.optimize()
         ours.append(quality.quality_stats(row_ptr, col, ctx.get_embedding(), NBNG))
