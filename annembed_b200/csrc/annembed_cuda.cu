@@ -1399,15 +1399,24 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
     return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
 }
 
-#define ANNEMBED_FIRINGS_PER_MINI_EPOCH 3.0
-// Mini-epochs per reference batch.  The finest level is about 3 own firings per node per mini-epoch
-// (nb_sampling_by_edge * mean degree / 3), where the bulk-synchronous layout statistics meet the serial reference's
-// within 1 % (tests/studies/semantics_study.py).
+// Mini-epochs per reference batch.  What governs the fidelity of the bulk-synchronous loop is how much of a batch is
+// applied against one snapshot, i.e. samples per edge per mini-epoch (nb_sampling_by_edge / M), not the node degree:
+// at ~0.3 samples per edge per mini-epoch (M = 34 for the default 10 samples per edge) the layout statistics are
+// within 1 % of the serial reference's for kNN 6 and 10, with and without the hubness sampler
+// (tests/studies/gpu_quality_study.py); they converge monotonically to the reference's as M grows.
+#ifndef ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH
+#define ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH 0.3
+#endif
+static double study_env(const char *name, double dflt)      // knobs of the design studies; not part of the ABI
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atof(v) : dflt;
+}
 static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
 {
     if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;
-    const double per_node = (double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)std::max<uint64_t>(ctx->n, 1));
-    return (uint32_t)std::max<double>(1.0, std::ceil(per_node / ANNEMBED_FIRINGS_PER_MINI_EPOCH));
+    const double spe = study_env("ANNEMBED_STUDY_SAMPLES_PER_EDGE", ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH);
+    return (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge / spe));
 }
 // Default (mini_epochs_per_batch == 0) schedule: graded.  The final statistics are set by the last, small-step batches
 // (tests/studies/adaptive_kappa_study.py: coarse-early / fine-late schedules land as close to the serial oracle as the
@@ -1418,8 +1427,9 @@ static uint32_t mini_epochs_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter
     const uint32_t base = eff_mini_epochs(ctx);
     if (ctx->prm.mini_epochs_per_batch) return base;
     const uint32_t nb = ctx->prm.nb_grad_batch;
-    const uint32_t div = (3 * iter <= nb) ? 4u : ((3 * iter <= 2 * nb) ? 2u : 1u);
-    return std::max(1u, (base + div - 1) / div);
+    const uint32_t d1 = (uint32_t)study_env("ANNEMBED_STUDY_DIV1", 4.0), d2 = (uint32_t)study_env("ANNEMBED_STUDY_DIV2", 2.0);
+    const uint32_t div = (3 * iter <= nb) ? d1 : ((3 * iter <= 2 * nb) ? d2 : 1u);
+    return std::max(1u, (base + div - 1) / std::max(div, 1u));
 }
 // global index of the first mini-epoch of batch `iter` (counter word of the Philox streams)
 static uint32_t first_epoch_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter)

@@ -18,7 +18,7 @@ class EmbedderParams:
     hierarchy_layer: int = 0         # :100,118
     hubness_weighting: bool = False  # :102,119
     # device-side additions (the reference's RNG is unseeded; see include/annembed_cuda.h)
-    mini_epochs_per_batch: int = 0   # 0 -> graded schedule (finest: ceil(nb_sampling_by_edge * E/n / 3))
+    mini_epochs_per_batch: int = 0   # 0 -> graded schedule (finest: ceil(nb_sampling_by_edge / 0.3))
     seed: int = 0x5EED
     flags: int = 0
 

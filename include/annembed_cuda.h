@@ -57,7 +57,7 @@ typedef struct annembed_cuda_params {
     uint32_t hubness_weighting;    /* :102 default 0: negatives uniform; 1: alias over set_neg_weights */
     /* ---- device-side additions (no reference counterpart: its RNG is unseeded, embedder.rs:1182) ---- */
     uint32_t mini_epochs_per_batch;/* bulk-synchronous sub-steps per reference batch;
-                                      0 -> graded: ceil(nb_sampling_by_edge * E/n / 3) (~3 firings per node per sub-step)
+                                      0 -> graded: ceil(nb_sampling_by_edge / 0.3) (0.3 samples per edge per sub-step)
                                       in the last third of the batches, 2x / 4x fewer sub-steps in the 2nd / 1st third */
     uint64_t seed;                 /* Philox4x32-10 key */
     uint32_t flags;                /* ANNEMBED_FLAG_* */
