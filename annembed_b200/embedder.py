@@ -246,7 +246,8 @@ class Embedder:
     """≙ `Embedder<'a, F>` (embedder.rs:84-100) restricted to the one-step path (`Embedder::new`, :107)."""
 
     def __init__(self, kgraph: KGraph, parameters: EmbedderParams, initial_embedding: np.ndarray | None = None,
-                 device: int = 0, comm: tuple | None = None, fused_exchange: bool = True):
+                 device: int = 0, comm: tuple | None = None, fused_exchange: bool = True,
+                 context: CudaContext | None = None):
         self.kgraph = kgraph                     # borrowed, like &'a KGraph<F>
         self.parameters = parameters             # copied by value in the reference (EmbedderParams: Copy)
         self.initial_embedding = None if initial_embedding is None else np.ascontiguousarray(initial_embedding, np.float32)
@@ -256,6 +257,8 @@ class Embedder:
         self.device = device
         self.comm = comm                          # (rank, nranks, unique_id) or None
         self.fused_exchange = fused_exchange      # peer-memory stores from the epoch kernel instead of an all-gather
+        self.context = context                    # optional long-lived device context (keeps its NCCL communicator and
+                                                  # peer mappings across embeds); by default embed() creates and destroys one
         self.write_quality_csv = False            # the reference dumps first_dist.csv / continuity_ratio.csv (embedder.rs:729-743)
         self.stats = {}
 
@@ -327,14 +330,16 @@ class Embedder:
                 raise EmbedError("dmap_init=true needs an explicit initial_embedding: the diffusion-map layout "
                                  "(embedder.rs:308-345) is outside this library's hot path")
             self.initial_embedding = self._get_random_init(1.0)       # embedder.rs:348
-        ctx = None
+        ctx = self.context
+        own_ctx = ctx is None
         try:
-            ctx = CudaContext(p, self.device)
-            if self.comm is not None:
-                ctx.comm_init(*self.comm)
+            if own_ctx:
+                ctx = CudaContext(p, self.device)
+                if self.comm is not None:
+                    ctx.comm_init(*self.comm)
             row_ptr, col, dist = self.kgraph.get_neighbours()
             ctx.set_graph_csr(row_ptr, col, dist)
-            if self.comm is not None and self.comm[1] > 1 and self.fused_exchange:
+            if own_ctx and self.comm is not None and self.comm[1] > 1 and self.fused_exchange:
                 from .dist import exchange_layout_handles
                 exchange_layout_handles(ctx, self.comm[0], self.comm[1])
             ctx.edge_weights(want_outputs=False)                       # to_proba_edges, embedder.rs:351
@@ -350,7 +355,7 @@ class Embedder:
         except AnnembedCudaError as e:
             raise EmbedError(str(e)) from e
         finally:
-            if ctx is not None:
+            if own_ctx and ctx is not None:
                 ctx.close()
         return 1
 
