@@ -554,7 +554,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         // node they need 4 Philox blocks in all (firings 0..2 and the block of the fifth words) -- one per lane,
         // exchanged by shuffles -- instead of 4 blocks per lane.  The loop trip count is made warp-uniform for that.
         const int Tmax = __reduce_max_sync(0xffffffffu, T);
-        const bool share = !HUB && Tmax <= 3;
+        const bool share = Tmax <= 3;
         Philox4 blk;
         blk.x = blk.y = blk.z = blk.w = 0u;
         if (share) {

@@ -411,11 +411,14 @@ struct GlobalRowRejector {          // nodeparam.rs:83-85 linear scan of the ori
 // 32-byte sector of the layout and each takes a different row of it (rotated by a random offset): every sample still
 // gets 5 independent, uniformly distributed negatives -- exactly the reference's per-sample law (embedder.rs:1121) --
 // while the 4 lanes' gathers coalesce into one sector request.  Only samples of different nodes of a group become
-// correlated, which no statistic of the optimizer depends on.  The hubness sampler keys the stream by the node.
+// correlated, which no statistic of the optimizer depends on.  The hubness (alias) sampler does the same one level up:
+// the group draws one random sector of the ALIAS TABLE, each lane reads a different entry of it and then accepts it or
+// follows its alias (embedder.rs:909-931): per sample, 5 independent draws from the hubness law.
 template <bool HUB>
 __host__ __device__ __forceinline__ uint32_t neg_stream_key(const EpochArgs &a, uint32_t node)
 {
-    return HUB ? node : (node & ~3u);
+    (void)a;
+    return node & ~3u;
 }
 
 template <bool HUB, class Rej>
@@ -426,9 +429,10 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
     uint32_t wi[ANNEMBED_NB_NEG] = {A.x, A.y, A.z, A.w, w4};
     uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
     if constexpr (HUB) {
-        const Philox4 C = philox4x32_10(node, s, a.epoch, 3u, a.k0, a.k1);
-        const Philox4 D = philox4x32_10(node, s, a.epoch, 4u, a.k0, a.k1);
-        wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = D.x;
+        const uint32_t gk = neg_stream_key<HUB>(a, node);
+        const Philox4 C = philox4x32_10(gk, s, a.epoch, 3u, a.k0, a.k1);
+        const Philox4 D = philox4x32_10(gk, s >> 2, a.epoch, 4u, a.k0, a.k1);
+        wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = philox_word(D, s & 3u);
     }
     const uint32_t nsec = (a.n + 3u) >> 2;
     // first draw of the 5 negatives, branch-free; the redraws (probability ~ (deg+2)/n per negative) are a rare path
@@ -436,10 +440,15 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
     bool rej[ANNEMBED_NB_NEG];
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-        uint32_t k;
-        if constexpr (HUB) k = map_negative<HUB>(a, wi[q], wa[q]);
-        else k = (below32(wi[q], nsec) << 2) | ((node + wi[q]) & 3u);          // random sector, row rotated by 2 random bits
-        rej[q] = k >= a.n || rejected(k);
+        uint32_t k = (below32(wi[q], nsec) << 2) | ((node + wi[q]) & 3u);      // random sector, row rotated by 2 random bits
+        bool out_of_range = k >= a.n;
+        if constexpr (HUB) {
+            if (!out_of_range) {                                               // alias method on the shared sector's entry
+                const uint2 t = a.neg_alias[k];
+                if (!(u01_24(wa[q]) < as_float(t.x))) k = t.y;
+            }
+        }
+        rej[q] = out_of_range || rejected(k);
         any_rej |= rej[q];
         negs[q] = k;
     }

@@ -138,3 +138,46 @@ def test_csv_output_matches_rust_lower_exp_format(tmp_path):
     assert open(p).read() == "1.50000e0,-2.25000e-4\n3.00000e10,0.00000e0\n"
     write_csv_labeled_array2(p, [7, 9], m)
     assert open(p).read().splitlines()[1] == "9,3.00000e10,0.00000e0"
+
+
+def _vose_alias(w):
+    n = len(w)
+    q = np.asarray(w, np.float64) * n / np.sum(w)
+    prob = np.ones(n, np.float32); alias = np.arange(n, dtype=np.uint32)
+    small = [i for i in range(n) if q[i] < 1.0]; large = [i for i in range(n) if q[i] >= 1.0]
+    while small and large:
+        s_, l_ = small.pop(), large.pop()
+        prob[s_] = q[s_]; alias[s_] = l_
+        q[l_] = (q[l_] + q[s_]) - 1.0
+        (small if q[l_] < 1.0 else large).append(l_)
+    tab = np.empty((n, 2), np.uint32)
+    tab[:, 0] = prob.view(np.uint32); tab[:, 1] = alias
+    return tab
+
+
+def test_hubness_sampler_follows_the_weights():
+    """K6: negatives drawn through the alias table (shared-sector lookups) follow clamp(in-degree,1,n)/sum
+    (embedder.rs:826-833,909-931), up to the rejection of {i, j} U N(i)."""
+    n = 256
+    row_ptr, col, dist = random_graph(n, 3, 6, seed=8)
+    scale, p = oracle.edge_weights(row_ptr, col, dist)
+    w = oracle.hubness_weights(row_ptr, col).astype(np.float64)
+    w[:8] *= 6.0                                       # a few pronounced hubs
+    tab = _vose_alias(w)
+    src = np.repeat(np.arange(n), np.diff(row_ptr.astype(np.int64)))
+    allowed = np.tile(w, (len(col), 1))
+    for e in range(len(col)):
+        i = src[e]
+        allowed[e, i] = 0
+        allowed[e, col[int(row_ptr[i]):int(row_ptr[i + 1])]] = 0
+    allowed /= allowed.sum(1, keepdims=True)
+    hist = np.zeros(n); expect = np.zeros(n)
+    for epoch in range(150):
+        c, negs = hs.draws(row_ptr, col, p, 10, 1, seed=3, epoch=epoch, neg_alias=tab)
+        fired = c > 0
+        hist += np.bincount(negs[fired].reshape(-1), minlength=n)
+        expect += 5 * allowed[fired].sum(0)
+    assert hist.sum() == expect.sum().round()
+    chi2 = ((hist - expect) ** 2 / expect).sum()
+    assert chi2 < n + 6 * np.sqrt(2 * n), chi2
+    assert np.corrcoef(hist, w)[0, 1] > 0.98
