@@ -210,10 +210,7 @@ __host__ __device__ __forceinline__ void fixed_sample(float *Y, uint32_t i, uint
     store_row<DP>(Y, i, yi);                                                      // :1301
 }
 
-// ---- the counter-based sampler ------------------------------------------------------------------
-// Sub-stream layout of counter word 3 for (edge, epoch):
-//   3s, 3s+1, 3s+2          firing s (word x of sub-stream 0 decides the firing count)
-//   0x80000000|s<<8|q<<5|t  redraw attempt t of negative q of firing s (rejection, embedder.rs:1246-1252)
+// ---- arguments of one mini-epoch ------------------------------------------------------------------------------
 struct EpochArgs {
     const float *__restrict__ y_snap;   // layout at the start of the mini-epoch (replicated, n x DP)
     float *__restrict__ y_next;         // layout after it; only rows [lo,hi) are written here
@@ -226,8 +223,8 @@ struct EpochArgs {
     uint64_t in_base;
     const uint8_t *__restrict__ in_own;  // (dst - lo) & 31 of every owned in-edge: its owner lane in the warp tile
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
-    const float *__restrict__ cum;       // v2: inclusive cumulative probability along each row (last entry exactly 1)
-    uint32_t k2;                         // v2: Philox2x32 key of the per-node uniform
+    const float *__restrict__ cum;       // inclusive cumulative probability along each row (last entry exactly 1)
+    uint32_t k2;                         // Philox2x32 key of the per-node uniform
     uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
     uint32_t n_peers;                    // fused exchange: replicas of y_next on the other ranks (peer memory over NVLink)
     float *peer_next[7];
@@ -236,14 +233,6 @@ struct EpochArgs {
     float kappa;                        // expected firings of edge e in this mini-epoch = kappa * p_e
     SgdConst K;
 };
-
-// firing count of an edge: floor(kappa*p + u), u ~ U[0,1) from word x of sub-stream 0.
-// E[count] = kappa*p = nb_sampling_by_edge * E * (p_e/N) / mini_epochs, the reference's expectation
-// (alias draw over all edges with weights p_e, embedder.rs:987,1182; each row sums to 1).
-__host__ __device__ __forceinline__ int firing_count(float p, float kappa, uint32_t word)
-{
-    return (int)fmaf(p, kappa, u01_24(word));
-}
 
 template <bool HUB>
 __host__ __device__ __forceinline__ uint32_t map_negative(const EpochArgs &a, uint32_t w_idx, uint32_t w_acc)
@@ -256,117 +245,8 @@ __host__ __device__ __forceinline__ uint32_t map_negative(const EpochArgs &a, ui
     return k;
 }
 
-__host__ __device__ __forceinline__ bool negative_rejected(const EpochArgs &a, uint32_t k, uint32_t node, uint32_t j,
-                                                           uint64_t r0, uint64_t r1)
-{
-    if (k == node || k == j) return true;                                         // :1246-1247
-    for (uint64_t m = r0; m < r1; m++)                                            // nodeparam.rs:83-85
-        if (a.col[m] == k) return true;
-    return false;
-}
-
-// the 5 accepted negatives of firing s of edge e (A = sub-stream 3s, already drawn by the caller)
-template <bool HUB>
-__host__ __device__ __forceinline__ void draw_negatives(const EpochArgs &a, uint32_t e, uint32_t s, const Philox4 &A,
-                                                        uint32_t node, uint32_t j, uint64_t r0, uint64_t r1,
-                                                        uint32_t (&negs)[ANNEMBED_NB_NEG])
-{
-    const Philox4 B = philox4x32_10(e, 0u, a.epoch, 3u * s + 1u, a.k0, a.k1);
-    uint32_t wi[ANNEMBED_NB_NEG] = {A.y, A.z, A.w, B.x, B.y};
-    uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
-    if constexpr (HUB) {
-        const Philox4 C = philox4x32_10(e, 0u, a.epoch, 3u * s + 2u, a.k0, a.k1);
-        wa[0] = B.z; wa[1] = B.w; wa[2] = C.x; wa[3] = C.y; wa[4] = C.z;
-    }
-#pragma unroll
-    for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-        uint32_t k = map_negative<HUB>(a, wi[q], wa[q]);
-        bool rej = negative_rejected(a, k, node, j, r0, r1);
-        for (uint32_t t = 0; rej && t < ANNEMBED_MAX_REDRAW; t++) {
-            const Philox4 R = philox4x32_10(e, 0u, a.epoch, 0x80000000u | (s << 8) | ((uint32_t)q << 5) | t, a.k0, a.k1);
-            k = map_negative<HUB>(a, R.x, R.y);
-            rej = negative_rejected(a, k, node, j, r0, r1);
-        }
-        negs[q] = rej ? ANNEMBED_NO_NODE : k;
-    }
-}
-
-// ---- one node, one mini-epoch (owner computes; no atomics on the layout) -------------------------
-// Sequential over the node's own firings (Gauss-Seidel inside the node) against the snapshot of every
-// other node (Jacobi across nodes).  Both ends of a positive edge move in the reference (:1237-1239):
-// the origin's owner applies -g here (phase A), the destination's owner replays the same counter-based
-// draw and applies +g (phase B).  When an edge fires c>1 times in a mini-epoch both owners simulate the
-// pair's c sequential attractions on local copies, which is what the serial reference would do to the pair.
-template <int DP, bool HUB>
-__host__ __device__ __forceinline__ unsigned int epoch_node(const EpochArgs &a, uint32_t node)
-{
-    float y[DP], g[DP];
-    load_row<DP>(a.y_snap, node, y);
-    const float inv_s2 = a.inv_s2[node];
-    const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
-    unsigned int applied = 0;
-    // phase A: out-edges (node is the origin i)
-    for (uint64_t m = r0; m < r1; m++) {
-        const uint32_t e = (uint32_t)m;
-        Philox4 A = philox4x32_10(e, 0u, a.epoch, 0u, a.k0, a.k1);
-        const float pe = a.p[m];
-        const int c = firing_count(pe, a.kappa, A.x);
-        if (c == 0) continue;
-        const uint32_t j = a.col[m];
-        float yj[DP];
-        load_row<DP>(a.y_snap, j, yj);
-        for (int s = 0; s < c; s++) {
-            if (s > 0) A = philox4x32_10(e, 0u, a.epoch, 3u * (uint32_t)s, a.k0, a.k1);
-            uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives<HUB>(a, e, (uint32_t)s, A, node, j, r0, r1, negs);
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
-            if constexpr (DP <= 4) {
-                // issue the five gathers before the dependent arithmetic
-                float yk[ANNEMBED_NB_NEG][DP];
-#pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
-                    load_row<DP>(a.y_snap, negs[q] == ANNEMBED_NO_NODE ? node : negs[q], yk[q]);
-                attract<DP>(y, yj, g, pe, inv_s2, a.K);
-#pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
-                    if (negs[q] != ANNEMBED_NO_NODE) repulse<DP>(y, yk[q], g, inv_s2, a.K);
-            } else {
-                attract<DP>(y, yj, g, pe, inv_s2, a.K);
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-                    if (negs[q] == ANNEMBED_NO_NODE) continue;
-                    float yk[DP];
-                    load_row<DP>(a.y_snap, negs[q], yk);
-                    repulse<DP>(y, yk, g, inv_s2, a.K);
-                }
-            }
-        }
-        applied += (unsigned int)c;
-    }
-    // phase B: in-edges (node is the destination j of src -> node)
-    const uint64_t q0 = a.in_ptr[node - a.lo], q1 = a.in_ptr[node - a.lo + 1];
-    for (uint64_t q = q0; q < q1; q++) {
-        const uint4 rec = a.in_rec[q - a.in_base];
-        const Philox4 A = philox4x32_10(rec.y, 0u, a.epoch, 0u, a.k0, a.k1);
-        const float pe = as_float(rec.z);
-        const int c = firing_count(pe, a.kappa, A.x);
-        if (c == 0) continue;
-        float ys[DP];
-        load_row<DP>(a.y_snap, rec.x, ys);
-        const float inv_s2_src = as_float(rec.w);
-        for (int s = 0; s < c; s++) {
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) g[cc] = 0.0f;
-            attract<DP>(ys, y, g, pe, inv_s2_src, a.K);
-        }
-    }
-    store_row<DP>(a.y_next, node, y);
-    return applied;
-}
-
-
 // =====================================================================================================
-// v2 sampler: systematic (low-variance) sampling per node.
+// the sampler: systematic (low-variance) sampling per node.
 // Node i owns one uniform u_i(epoch) (Philox2x32-10 of (node, epoch)).  Its sample points are s + u_i,
 // s = 0,1,..; edge m of the row covers [kappa*P_{m-1}, kappa*P_m) where P is the cumulative edge probability
 // of the row (row sums are 1), so  count_m = ceil(kappa*P_m - u) - ceil(kappa*P_{m-1} - u),
@@ -495,7 +375,7 @@ __host__ __device__ __forceinline__ void apply_firing(const EpochArgs &a, uint32
     }
 }
 
-// in_rec (v2): {src node, bits(P_lo), bits(P_hi), bits(inv_s2[src])}; p_e is taken as P_hi - P_lo on both sides.
+// in_rec: {src node, bits(P_lo), bits(P_hi), bits(inv_s2[src])}; p_e is taken as P_hi - P_lo on both sides.
 template <int DP, bool HUB, bool B1 = false>
 __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &a, uint32_t node)
 {

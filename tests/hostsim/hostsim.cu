@@ -26,8 +26,6 @@ struct HostCtx {
     std::vector<float> inv_s2;
     std::vector<float> cum;
 };
-static int g_version = 2;   // 2 = the product's systematic sampler; 1 = first design (per-edge counts), kept for studies
-extern "C" void hostsim_set_version(int v) { g_version = v; }
 extern "C" void hostsim_philox2(const uint32_t ctr[2], uint32_t key, uint32_t out[2])
 {
     Philox2 r = philox2x32_10(ctr[0], ctr[1], key);
@@ -53,8 +51,7 @@ static void build(HostCtx &h, uint64_t n, const uint64_t *row_ptr, const uint32_
     for (uint64_t i = 0; i < n; i++)
         for (uint64_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) {   // ascending edge id inside each destination
             uint4 r; r.x = (uint32_t)i; r.w = as_uint(h.inv_s2[i]);
-            if (g_version == 1) { r.y = (uint32_t)e; r.z = as_uint(p[e]); }
-            else { r.y = as_uint(e == row_ptr[i] ? 0.0f : h.cum[e - 1]); r.z = as_uint(h.cum[e]); }
+            r.y = as_uint(e == row_ptr[i] ? 0.0f : h.cum[e - 1]); r.z = as_uint(h.cum[e]);
             h.in_rec[fill[col[e]]++] = r;
         }
 }
@@ -65,7 +62,7 @@ static uint64_t run_epoch(const EpochArgs &a)
     uint64_t tot = 0;
 #pragma omp parallel for schedule(dynamic, 1024) reduction(+ : tot)
     for (int64_t i = (int64_t)a.lo; i < (int64_t)a.hi; i++)
-        tot += g_version == 1 ? epoch_node<DP, HUB>(a, (uint32_t)i) : epoch_node_v2<DP, HUB>(a, (uint32_t)i);
+        tot += epoch_node_v2<DP, HUB>(a, (uint32_t)i);
     return tot;
 }
 

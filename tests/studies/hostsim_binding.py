@@ -22,10 +22,6 @@ def _p(a, t):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
-def set_version(v):
-    lib().hostsim_set_version(C.c_int(v))
-
-
 def philox2(ctr, key):
     ctr = np.asarray(ctr, np.uint32); out = np.zeros(2, np.uint32)
     lib().hostsim_philox2(_p(ctr, C.c_uint32), C.c_uint32(key), _p(out, C.c_uint32))

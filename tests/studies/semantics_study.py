@@ -10,8 +10,7 @@ from tests.studies import hostsim_binding as hs
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 Ms = [int(a) for a in sys.argv[3:]] or [10]
-import os as _os
-hs.set_version(int(_os.environ.get('HOSTSIM_VERSION', '2')))
+
 nb_batch, nbs, gs = 30, 10, 1.0
 x, labels = workloads.gaussian_mixture(n, 784, seed=0)
 t = time.time(); idx, dist = workloads.knn_exact(x, k); print("knn", time.time() - t)

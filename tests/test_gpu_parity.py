@@ -378,3 +378,35 @@ def test_cpp_driver_of_the_host_mirror():
     out = subprocess.run([os.path.join(here, "test_embedder"), "500"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "test_embedder ok" in out.stdout
+
+
+def test_in_edge_scan_across_many_rounds_for_a_hub():
+    """A node with thousands of in-edges: its affine maps span ~100 sweep rounds of k_epoch_in; the composite carried
+    across rounds must equal the one-after-the-other application of the thread-per-node kernel."""
+    n, k = 3000, 5
+    rng = np.random.default_rng(5)
+    row_ptr = np.arange(0, (n + 1) * k, k, dtype=np.uint64)
+    col = np.empty((n, k), np.uint32)
+    for i in range(n):
+        others = rng.choice(n - 2, size=k - 1, replace=False) + 1          # 1..n-2
+        others = np.where(others >= i, others + 1, others)
+        others = others[others != 7][:k - 1]
+        while len(others) < k - 1:
+            c = int(rng.integers(1, n))
+            if c != i and c != 7 and c not in others:
+                others = np.append(others, c)
+        col[i] = np.concatenate([[7 if i != 7 else 8], others])             # everybody's first neighbour is node 7
+    dist = np.sort(rng.gamma(2.0, 1.0, size=(n, k)).astype(np.float32), axis=1)
+    y0 = rng.uniform(-1, 1, size=(n, 2)).astype(np.float32)
+    outs = []
+    for flags in (0, 1):
+        ctx = ctx_for(row_ptr, col.reshape(-1), dist.reshape(-1), nb_grad_batch=3, grad_step=1.0, seed=9, flags=flags,
+                      nb_sampling_by_edge=1, mini_epochs_per_batch=1)
+        ctx.edge_weights(want_outputs=False)
+        assert ctx.get_hubness_counts()[7] == n - 1
+        ctx.set_embedding(y0)
+        ctx.optimize_batches(1, 1)
+        outs.append(ctx.get_embedding())
+    assert np.abs(outs[0][7] - y0[7]).max() > 1e-3                          # the hub moved
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-4, atol=1e-4)      # ~3000 composed maps: fp32 rounding only
+    np.testing.assert_allclose(np.delete(outs[0], 7, axis=0), np.delete(outs[1], 7, axis=0), rtol=1e-5, atol=2e-5)
