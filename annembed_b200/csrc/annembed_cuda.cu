@@ -467,11 +467,25 @@ struct EpochTile {
 #define ANNEMBED_MINB_OUT 5
 #endif
     static constexpr int WARPS = DP <= 4 ? ANNEMBED_WARPS_OUT : (DP <= 16 ? 4 : 2);
-    static constexpr int MINB = DP <= 4 ? ANNEMBED_MINB_OUT : (DP <= 8 ? 2 : 1);  // blocks/SM the register budget aims at
+    static constexpr int MINB = DP <= 2 ? ANNEMBED_MINB_OUT : (DP <= 4 ? 4 : (DP <= 8 ? 2 : 1));  // blocks/SM the register budget aims at
     static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
-    static constexpr int PER_WARP = ((32 * RS * (4 + 4 + 2) + 15) / 16) * 16;    // col, cum, ceil counts (u16)
+    static constexpr int PER_WARP = ((32 * RS * (4 + 4) + 15) / 16) * 16;        // col, cum
     static constexpr int SMEM = WARPS * PER_WARP;
+    static constexpr int MAX_FIRINGS = 126;                                      // per node and mini-epoch (byte counters)
 };
+
+// Number of edges of the row whose cumulative firing count is <= s, i.e. the edge firing s lands on.  The counts
+// ceil(kappa P_m - u) of the row are kept as bytes (<= 126; 0x7f pads the row) in registers: byte-wise
+// (0x80 | s) - ch never borrows and leaves bit 7 set exactly when ch <= s.
+template <int KREG>
+__device__ __forceinline__ int edge_of_firing(const uint32_t (&chb)[KREG / 4], int s)
+{
+    const uint32_t S = (uint32_t)s * 0x01010101u | 0x80808080u;
+    int m = 0;
+#pragma unroll
+    for (int w = 0; w < KREG / 4; w++) m += __popc((S - chb[w]) & 0x80808080u);
+    return m;
+}
 
 template <int DP, bool HUB, int KREG>
 __global__ void __launch_bounds__(EpochTile<DP, KREG>::WARPS * 32, EpochTile<DP, KREG>::MINB)
@@ -487,33 +501,34 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
     unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
     uint32_t *s_col = reinterpret_cast<uint32_t *>(base);                       // [32][RS]
     float *s_cum = reinterpret_cast<float *>(s_col + 32 * RS);                  // [32][RS]
-    unsigned short *s_ch = reinterpret_cast<unsigned short *>(s_cum + 32 * RS); // [32][RS]
 
     const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
     const uint32_t node = (uint32_t)n0 + lane;
     const bool valid = lane < nvalid;
     float y[DP], g[DP];
     uint32_t rc[KREG];
+    uint32_t chb[KREG / 4];
     float inv_s2 = 1.0f;
     int T = 0;
     // ---------------- stage the tile's rows: coalesced global reads, [lane][m] layout with odd stride in smem
     {
-        uint64_t rp = a.row_ptr[valid ? node : (uint32_t)n0];
-        uint64_t rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
-        if (lane == nvalid - 1) rp_next = a.row_ptr[node + 1];
-        const uint64_t R0 = __shfl_sync(0xffffffffu, rp, 0);
-        const uint64_t R1 = __shfl_sync(0xffffffffu, rp_next, nvalid - 1);
-        const int k = valid ? (int)(rp_next - rp) : 0;
-        const uint32_t tile_edges = (uint32_t)(R1 - R0);
+        int k;
         if (a.regular_k) {
-            // every row has exactly regular_k entries: edge e of the tile belongs to lane e / k
+            // every row has exactly regular_k entries: no row_ptr round trip, edge e of the tile belongs to lane e / k
             const uint32_t kk = a.regular_k, inv_k = (65536u + kk - 1u) / kk;
+            const uint64_t R0 = n0 * kk;
+            const uint32_t tile_edges = (uint32_t)nvalid * kk;
+            k = valid ? (int)kk : 0;
             for (uint32_t e = lane; e < tile_edges; e += 32) {
                 const uint32_t nl = (e * inv_k) >> 16, m = e - nl * kk;
                 s_col[nl * RS + m] = __ldcs(a.col + R0 + e);
                 s_cum[nl * RS + m] = __ldcs(a.cum + R0 + e);
             }
         } else {
+            const uint64_t rp = a.row_ptr[valid ? node : (uint32_t)n0];
+            uint64_t rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+            if (lane == nvalid - 1) rp_next = a.row_ptr[node + 1];
+            k = valid ? (int)(rp_next - rp) : 0;
             for (int m = 0; m < k; m++) {
                 s_col[lane * RS + m] = a.col[rp + m];
                 s_cum[lane * RS + m] = a.cum[rp + m];
@@ -522,119 +537,132 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < KREG; m++) rc[m] = ANNEMBED_NO_NODE;
+#pragma unroll
+        for (int w = 0; w < KREG / 4; w++) chb[w] = 0x7f7f7f7fu;
         if (valid) {
             load_row<DP>(a.y_snap, node, y);
             inv_s2 = __ldcs(a.inv_s2 + node);
-            const float u = node_uniform(node, a.epoch, a.k2);
+            const float u = node_uniform(node, a.ukey);
 #pragma unroll
             for (int m = 0; m < KREG; m++) {
                 if (m < k) {
                     rc[m] = s_col[lane * RS + m];
                     const int ch = cum_ceil(a.kappa, s_cum[lane * RS + m], u);
-                    s_ch[lane * RS + m] = (unsigned short)ch;
+                    chb[m >> 2] = (chb[m >> 2] & ~(0xffu << (8 * (m & 3)))) | ((uint32_t)ch << (8 * (m & 3)));
                     T = ch;
                 }
             }
         }
-        __syncwarp();
     }
     // ---------------- the node's own firings
     const uint32_t nkey = neg_stream_key<HUB>(a, node);
+    auto rejector = [&](uint32_t j) {
+        return [&, j](uint32_t kk) -> bool {
+            bool r = (kk == node) | (kk == j);
+#pragma unroll
+            for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
+            return r;
+        };
+    };
     if constexpr (DP <= 4) {
-        // software pipelined: the 6 row gathers of firing s+1 are in flight during the arithmetic of firing s
-        int m = 0;                       // edge cursor of the systematic sampler
-        int m_cur = -1;                  // edge whose partner copy yj is live (pair simulation across firings)
-        float yj[DP];
-        Philox4 B;
-        int nm = -1;                     // prefetched firing
-        float npe = 0.0f;
-        float nyj[DP], nyk[ANNEMBED_NB_NEG][DP];
-        unsigned nuse = 0;
-        // The 4 lanes of an aligned group share their negative streams (neg_stream_key): with at most 3 firings per
-        // node they need 4 Philox blocks in all (firings 0..2 and the block of the fifth words) -- one per lane,
-        // exchanged by shuffles -- instead of 4 blocks per lane.  The loop trip count is made warp-uniform for that.
+        // Software pipelined over two register sets: the 6 row gathers (y_j + 5 negatives) of firings s+1 and s+2 are
+        // in flight during the arithmetic of firing s.
+        struct Pre {
+            int m;                       // edge of the firing
+            float pe;
+            unsigned use;                // negatives that found an acceptable node
+            float yj[DP], yk[ANNEMBED_NB_NEG][DP];
+        };
+        // The 4 lanes of an aligned group share their negative streams (neg_stream_key): a chunk of 4 consecutive
+        // firings needs 5 Philox blocks per group (one per firing and the block of the fifth words).  Lane r computes the
+        // block of firing 4c+r and they are exchanged by shuffles; the fifth-words block is computed by lane 3 when the
+        // chunk has at most 3 firings (the common case: 1 block per lane and mini-epoch), else by every lane.
+        // The loop trip count is made warp-uniform for the shuffles.
         const int Tmax = __reduce_max_sync(0xffffffffu, T);
-        const bool share = Tmax <= 3;
+        const uint32_t r4 = (uint32_t)lane & 3u;
         Philox4 blk;
+        uint32_t bw = 0;                 // word r4 of the chunk's fifth-words block
         blk.x = blk.y = blk.z = blk.w = 0u;
-        if (share) {
-            const uint32_t r = (uint32_t)lane & 3u;
-            blk = (r < 3u) ? philox4x32_10(nkey, r, a.epoch, 1u, a.k0, a.k1) : philox4x32_10(nkey, 0u, a.epoch, 2u, a.k0, a.k1);
-        }
-        auto fetch = [&](int s, Philox4 &A, uint32_t &w4) {     // executed by the whole warp
-            if (share) {
-                const int src = (lane & ~3) + s;
-                A.x = __shfl_sync(0xffffffffu, blk.x, src); A.y = __shfl_sync(0xffffffffu, blk.y, src);
-                A.z = __shfl_sync(0xffffffffu, blk.z, src); A.w = __shfl_sync(0xffffffffu, blk.w, src);
-                const uint32_t comp = s == 0 ? blk.x : (s == 1 ? blk.y : blk.z);
-                w4 = __shfl_sync(0xffffffffu, comp, (lane & ~3) + 3);
-            } else {
-                A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
-                if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
-                w4 = philox_word(B, (uint32_t)s & 3u);
-            }
-        };
-        auto prepare = [&](int s, const Philox4 &A, uint32_t w4) {
-            while ((int)s_ch[lane * RS + m] <= s) m++;          // ch[k-1] == T > s
-            nm = m;
-            const uint32_t j = s_col[lane * RS + m];
-            const float P_hi = s_cum[lane * RS + m];
-            const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
-            npe = F_SUB(P_hi, P_lo);
-            load_row<DP>(a.y_snap, j, nyj);
-            auto rej = [&](uint32_t kk) -> bool {
-                bool r = (kk == node) | (kk == j);
-#pragma unroll
-                for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
-                return r;
-            };
-            uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, w4, rej, negs);
-            nuse = 0;
-#pragma unroll
-            for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-                const bool ok = negs[q] != ANNEMBED_NO_NODE;
-                nuse |= ok ? (1u << q) : 0u;
-                load_row<DP>(a.y_snap, ok ? negs[q] : node, nyk[q]);
-            }
-        };
         Philox4 An;
         uint32_t w4n = 0;
         An.x = An.y = An.z = An.w = 0u;
-        if (Tmax > 0) fetch(0, An, w4n);
-        if (T > 0) prepare(0, An, w4n);
-        for (int s = 0; s < Tmax; s++) {
-            if (s + 1 < Tmax) fetch(s + 1, An, w4n);
-            if (s < T) {
-                float yk[ANNEMBED_NB_NEG][DP];
-                const float pe = npe;
-                const unsigned use = nuse;
-                if (nm != m_cur) {
-#pragma unroll
-                    for (int c = 0; c < DP; c++) yj[c] = nyj[c];
-                    m_cur = nm;
+        auto fetch = [&](int s) {        // executed by the whole warp, s warp-uniform
+            if ((s & 3) == 0) {
+                const uint32_t c = (uint32_t)s >> 2;
+                if (Tmax - s <= 3) {
+                    const bool fifth = r4 == 3u;
+                    blk = philox4x32_10(nkey, fifth ? c : (uint32_t)s + r4, a.epoch, fifth ? 2u : 1u, a.k0, a.k1);
+                    // lane r keeps word r of the fifth-words block held by lane 3 (firings 4c .. 4c+2 only)
+                    const uint32_t b0 = __shfl_sync(0xffffffffu, blk.x, (lane & ~3) + 3);
+                    const uint32_t b1 = __shfl_sync(0xffffffffu, blk.y, (lane & ~3) + 3);
+                    const uint32_t b2 = __shfl_sync(0xffffffffu, blk.z, (lane & ~3) + 3);
+                    bw = r4 == 0u ? b0 : (r4 == 1u ? b1 : b2);
+                } else {
+                    blk = philox4x32_10(nkey, (uint32_t)s + r4, a.epoch, 1u, a.k0, a.k1);
+                    const Philox4 B5 = philox4x32_10(nkey, c, a.epoch, 2u, a.k0, a.k1);
+                    bw = philox_word(B5, r4);
                 }
-#pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++)
-#pragma unroll
-                    for (int c = 0; c < DP; c++) yk[q][c] = nyk[q][c];
-                if (s + 1 < T) prepare(s + 1, An, w4n);
-#pragma unroll
-                for (int c = 0; c < DP; c++) g[c] = 0.0f;
-                attract<DP, true>(y, yj, g, pe, inv_s2, a.K);
-#pragma unroll
-                for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, yk[q], g, inv_s2, a.K, (use >> q) & 1u);
             }
+            const int src = (lane & ~3) + (s & 3);
+            An.x = __shfl_sync(0xffffffffu, blk.x, src); An.y = __shfl_sync(0xffffffffu, blk.y, src);
+            An.z = __shfl_sync(0xffffffffu, blk.z, src); An.w = __shfl_sync(0xffffffffu, blk.w, src);
+            w4n = __shfl_sync(0xffffffffu, bw, src);
+        };
+        auto prepare = [&](int s, Pre &P) {
+            const int m = edge_of_firing<KREG>(chb, s);        // < k because ch[k-1] == T > s
+            P.m = m;
+            const uint32_t j = s_col[lane * RS + m];
+            const float P_hi = s_cum[lane * RS + m];
+            const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
+            P.pe = F_SUB(P_hi, P_lo);
+            load_row<DP>(a.y_snap, j, P.yj);
+            uint32_t negs[ANNEMBED_NB_NEG];
+            draw_negatives_v2<HUB>(a, node, (uint32_t)s, An, w4n, rejector(j), negs);
+            P.use = 0;
+#pragma unroll
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+                const bool ok = negs[q] != ANNEMBED_NO_NODE;
+                P.use |= ok ? (1u << q) : 0u;
+                load_row<DP>(a.y_snap, ok ? negs[q] : node, P.yk[q]);
+            }
+        };
+        int m_last = -1;                 // edge whose partner copy yl is live (pair simulation across firings)
+        float yl[DP];
+#pragma unroll
+        for (int c = 0; c < DP; c++) yl[c] = 0.0f;
+        auto apply = [&](Pre &P) {
+            if (P.m == m_last) {
+#pragma unroll
+                for (int c = 0; c < DP; c++) P.yj[c] = yl[c];
+            }
+#pragma unroll
+            for (int c = 0; c < DP; c++) g[c] = 0.0f;
+            attract<DP, true>(y, P.yj, g, P.pe, inv_s2, a.K);
+#pragma unroll
+            for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, P.yk[q], g, inv_s2, a.K, (P.use >> q) & 1u);
+            m_last = P.m;
+#pragma unroll
+            for (int c = 0; c < DP; c++) yl[c] = P.yj[c];
+        };
+        Pre PA, PB;
+        PA.m = PB.m = -1; PA.pe = PB.pe = 0.0f; PA.use = PB.use = 0u;
+        if (Tmax > 0) { fetch(0); if (T > 0) prepare(0, PA); }
+        if (Tmax > 1) { fetch(1); if (T > 1) prepare(1, PB); }
+        for (int s = 0; s < Tmax; s += 2) {
+            if (s < T) apply(PA);
+            if (s + 2 < Tmax) { fetch(s + 2); if (s + 2 < T) prepare(s + 2, PA); }
+            if (s + 1 < T) apply(PB);
+            if (s + 3 < Tmax) { fetch(s + 3); if (s + 3 < T) prepare(s + 3, PB); }
         }
     } else {
         // wide rows: the prefetch registers do not fit, plain sequential firings
-        int m = 0, m_prev = -1;
+        int m_prev = -1;
         uint32_t j = 0;
         float pe = 0.0f;
         float yj[DP];
         Philox4 B;
         for (int s = 0; s < T; s++) {
-            while ((int)s_ch[lane * RS + m] <= s) m++;
+            const int m = edge_of_firing<KREG>(chb, s);
             if (m != m_prev) {
                 j = s_col[lane * RS + m];
                 const float P_hi = s_cum[lane * RS + m];
@@ -645,14 +673,8 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
             }
             const Philox4 A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
             if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
-            auto rej = [&](uint32_t kk) -> bool {
-                bool r = (kk == node) | (kk == j);
-#pragma unroll
-                for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
-                return r;
-            };
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rej, negs);
+            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rejector(j), negs);
             apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
@@ -669,14 +691,32 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
 #ifndef ANNEMBED_MINB_IN
 #define ANNEMBED_MINB_IN 10
 #endif
+// shared memory of one k_epoch_in warp: a ring of fired in-edges (SoA, 64 slots) and the running composite per owner
+template <int DP>
+struct InTile {
+    static constexpr int QCAP = 64;                              // >= 31 left over + 32 new entries
+    static constexpr int WORDS = QCAP * (3 + DP) + 32 * (1 + DP);
+    static constexpr int PER_WARP = WORDS * 4;
+    static constexpr int SMEM = ANNEMBED_WARPS_IN * PER_WARP;
+};
+
 template <int DP>
 __global__ void __launch_bounds__(ANNEMBED_WARPS_IN * 32, (DP <= 4 ? ANNEMBED_MINB_IN : (DP <= 8 ? 6 : (DP <= 16 ? 4 : 2))))
 k_epoch_in(EpochArgs a)
 {
+    using TL = InTile<DP>;
+    constexpr int QCAP = TL::QCAP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t tile = (uint64_t)blockIdx.x * ANNEMBED_WARPS_IN + wib;
     const uint64_t n0 = (uint64_t)a.lo + tile * 32;
     if (n0 >= a.hi) return;
+    uint32_t *q_oc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)wib * TL::PER_WARP);   // own | count << 8
+    float *q_pe = reinterpret_cast<float *>(q_oc + QCAP);
+    float *q_is2 = q_pe + QCAP;
+    float *q_ys = q_is2 + QCAP;                                  // [DP][QCAP]
+    float *t_alpha = q_ys + DP * QCAP;                           // [32]      running composite of each owner:
+    float *t_beta = t_alpha + 32;                                // [DP][32]  y -> t_alpha * y + t_beta
     const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
     const uint32_t node = (uint32_t)n0 + lane;
     const bool valid = lane < nvalid;
@@ -686,83 +726,55 @@ k_epoch_in(EpochArgs a)
 #pragma unroll
     for (int c = 0; c < DP; c++) y[c] = 0.0f;
     if (valid) load_row<DP>(a.y_next, node, y);
-    uint64_t my_q0 = a.in_ptr[(valid ? node : (uint32_t)n0) - a.lo];
-    uint64_t my_q1 = __shfl_down_sync(0xffffffffu, my_q0, 1);
-    if (lane == nvalid - 1) my_q1 = a.in_ptr[node - a.lo + 1];
-    const uint64_t Q0 = __shfl_sync(0xffffffffu, my_q0, 0);
-    const uint64_t Q1 = __shfl_sync(0xffffffffu, my_q1, nvalid - 1);
-    // this owner's in-edge positions relative to the sweep cursor (advanced by 32 per round)
-    int rel_lo = valid ? (int)(my_q0 - Q0) : 0x3fffffff, rel_hi = valid ? (int)(my_q1 - Q0) : 0x3fffffff;
+    const uint64_t Q0 = a.in_ptr[(uint32_t)n0 - a.lo];
+    const uint64_t Q1 = a.in_ptr[(uint32_t)n0 - a.lo + nvalid];
     const uint32_t n_in = (uint32_t)(Q1 - Q0);                 // in-edges of the tile
     if (n_in == 0) {                                           // nothing to apply: y_next already holds the result
         if (valid)
             for (uint32_t pr = 0; pr < a.n_peers; pr++) store_row<DP>(a.peer_next[pr], node, y);
         return;
     }
+    t_alpha[lane] = 1.0f;
+#pragma unroll
+    for (int c = 0; c < DP; c++) t_beta[c * 32 + lane] = 0.0f;
     const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
     const uint8_t *ownp = a.in_own + (Q0 - a.in_base) + lane;
-    // log2(longest in-edge segment of the tile, capped at a round) scan steps compose any owner's maps of a round
-    const int max_len = __reduce_max_sync(0xffffffffu, valid ? (int)min((uint64_t)32, my_q1 - my_q0) : 0);
-    float alpha_tot = 1.0f, beta_tot[DP];                      // composite of all rounds, applied once at the end
-#pragma unroll
-    for (int c = 0; c < DP; c++) beta_tot[c] = 0.0f;
 
-    uint4 rec2 = make_uint4(0, 0, 0, 0);                       // records of the round after next
-    uint32_t own2 = 0;
-    int nc = 0;                                                // prepared round
-    uint32_t nown = 0;
-    float nPl = 0.0f, nPh = 0.0f, nis2 = 0.0f, nys[DP];
-#pragma unroll
-    for (int cc = 0; cc < DP; cc++) nys[cc] = 0.0f;
-    auto prepare = [&](const uint4 &rec, uint32_t own, bool have) {
-        nc = 0;
-        if (have) {
-            const float us = node_uniform(rec.x, a.epoch, a.k2);
-            nc = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
-        }
-        nown = own; nPl = as_float(rec.y); nPh = as_float(rec.z); nis2 = as_float(rec.w);
-        if (nc > 0) load_row<DP>(a.y_snap, rec.x, nys);
-    };
-    {
-        uint4 rec1 = make_uint4(0, 0, 0, 0);
-        uint32_t own1 = 0;
-        if (lane < n_in) { rec1 = __ldcs(recp); own1 = __ldcs(ownp); }
-        if (32 + lane < n_in) { rec2 = __ldcs(recp + 32); own2 = __ldcs(ownp + 32); }
-        prepare(rec1, own1, lane < n_in);
-    }
-    const uint4 *recp2 = recp + 32;                            // slot of this lane in the round after next
-    const uint8_t *ownp2 = ownp + 32;
-    int left = (int)n_in - 32 - lane;                          // > 0 iff that slot holds an in-edge
-    for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
-        const int c = nc;
-        const uint32_t own = nown;
-        const float Pl = nPl, Ph = nPh, is2 = nis2;
-        float ys[DP];
-#pragma unroll
-        for (int cc = 0; cc < DP; cc++) ys[cc] = nys[cc];
-        {   // prepare the next round (its records were loaded one iteration ago), fetch the records after it
-            const uint4 rec1 = rec2;
-            const uint32_t own1 = own2;
-            recp2 += 32; ownp2 += 32; left -= 32;               // `left` = in-edges from this lane's slot two rounds ahead
-            if (left > 0) { rec2 = __ldcs(recp2); own2 = __ldcs(ownp2); }
-            prepare(rec1, own1, left + 32 > 0);
-        }
-        // the affine map of this lane's in-edge: y -> alpha y + beta  (identity when it did not fire)
+    // ---- dense stage: `cnt` queued in-edges starting at ring position `head`, lane = queue entry.  Each becomes the
+    // affine map y -> alpha y + beta of its owner (coefficient at the owner's position after k_epoch_out); the maps of
+    // one owner are adjacent (the sweep is in in-edge order) and are composed by a segmented scan; the last lane of a
+    // segment folds the composite into the owner's running composite.
+    auto dense = [&](uint32_t head, int cnt) {
+        const bool act = lane < cnt;
+        const uint32_t e = (head + (uint32_t)lane) & (QCAP - 1);
+        uint32_t own = 32u + (uint32_t)lane;                   // inactive lanes: a segment of their own
         float alpha = 1.0f, beta[DP];
 #pragma unroll
         for (int cc = 0; cc < DP; cc++) beta[cc] = 0.0f;
-        // reference position and segment start of this in-edge's owner
+        int c = 0;
+        float pe = 0.0f, is2 = 0.0f, ys[DP];
+#pragma unroll
+        for (int cc = 0; cc < DP; cc++) ys[cc] = 0.0f;
+        if (act) {
+            const uint32_t oc = q_oc[e];
+            own = oc & 0xffu; c = (int)(oc >> 8);
+            pe = q_pe[e]; is2 = q_is2[e];
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) ys[cc] = q_ys[cc * QCAP + e];
+        }
         float yr[DP];
 #pragma unroll
-        for (int cc = 0; cc < DP; cc++) yr[cc] = __shfl_sync(0xffffffffu, y[cc], (int)own);
-        const int seg_lo = max(0, __shfl_sync(0xffffffffu, rel_lo, (int)own));
-        if (c > 0) {
-            const float A = in_edge_factor(attract_coeff<true>(sqdist<DP>(yr, ys), F_SUB(Ph, Pl), is2, a.K), c);
+        for (int cc = 0; cc < DP; cc++) yr[cc] = __shfl_sync(0xffffffffu, y[cc], (int)(own & 31u));
+        if (act) {
+            const float A = in_edge_factor(attract_coeff<true>(sqdist<DP>(yr, ys), pe, is2, a.K), c);
             alpha = F_ADD(1.0f, A);
 #pragma unroll
             for (int cc = 0; cc < DP; cc++) beta[cc] = F_MUL(-A, ys[cc]);
         }
-        // segmented inclusive scan (composition in index order) over the lanes of each owner
+        const uint32_t prev_own = __shfl_up_sync(0xffffffffu, own, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || own != prev_own);
+        const int seg_lo = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+        const int max_len = __reduce_max_sync(0xffffffffu, act ? lane - seg_lo + 1 : 0);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             if (d >= max_len) break;
@@ -776,26 +788,83 @@ k_epoch_in(EpochArgs a)
                 alpha = F_MUL(alpha, ap);
             }
         }
-        // owner: composite of its in-edges of this round sits in the last lane of its range
-        {
-            const int lo_c = max(0, min(32, rel_lo)), hi_c = max(0, min(32, rel_hi));
-            const bool mine = hi_c > lo_c;
-            const int src = mine ? hi_c - 1 : lane;
-            const float ar = __shfl_sync(0xffffffffu, alpha, src);
-            float br[DP];
+        const bool tail = act && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+        if (tail) {                                            // one tail per owner and stage: no conflicts
+            const float at = t_alpha[own];
 #pragma unroll
-            for (int cc = 0; cc < DP; cc++) br[cc] = __shfl_sync(0xffffffffu, beta[cc], src);
-            if (mine) {
+            for (int cc = 0; cc < DP; cc++) t_beta[cc * 32 + own] = F_FMA(alpha, t_beta[cc * 32 + own], beta[cc]);
+            t_alpha[own] = F_MUL(alpha, at);
+        }
+        __syncwarp();
+    };
+
+    // ---- sparse stage: lane = in-edge record.  Replays the source's firing decision; fired in-edges (about
+    // kappa * p_e of them) are compacted into the ring, the source-row gather of round r+1 and the records of round
+    // r+2 are in flight during round r.
+    uint4 rec2 = make_uint4(0, 0, 0, 0);                       // records of the round after next
+    uint32_t own2 = 0;
+    int nc = 0;                                                // prepared round
+    uint32_t nown = 0;
+    float npe = 0.0f, nis2 = 0.0f, nys[DP];
 #pragma unroll
-                for (int cc = 0; cc < DP; cc++) beta_tot[cc] = F_FMA(ar, beta_tot[cc], br[cc]);
-                alpha_tot = F_MUL(ar, alpha_tot);
-            }
-            rel_lo -= 32; rel_hi -= 32;
+    for (int cc = 0; cc < DP; cc++) nys[cc] = 0.0f;
+    auto prepare = [&](const uint4 &rec, uint32_t own, bool have) {
+        nc = 0;
+        if (have) {
+            const float us = node_uniform(rec.x, a.ukey);
+            nc = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
+        }
+        nown = own; npe = F_SUB(as_float(rec.z), as_float(rec.y)); nis2 = as_float(rec.w);
+        if (nc > 0) load_row<DP>(a.y_snap, rec.x, nys);
+    };
+    {
+        uint4 rec1 = make_uint4(0, 0, 0, 0);
+        uint32_t own1 = 0;
+        if (lane < n_in) { rec1 = __ldcs(recp); own1 = __ldcs(ownp); }
+        if (32 + lane < n_in) { rec2 = __ldcs(recp + 32); own2 = __ldcs(ownp + 32); }
+        prepare(rec1, own1, lane < n_in);
+    }
+    const uint4 *recp2 = recp + 32;                            // slot of this lane in the round after next
+    const uint8_t *ownp2 = ownp + 32;
+    int left = (int)n_in - 32 - lane;                          // > 0 iff that slot holds an in-edge
+    uint32_t q_head = 0;                                       // ring start (warp-uniform)
+    int q_n = 0;                                               // queued entries (warp-uniform)
+    __syncwarp();
+    for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
+        const int c = nc;
+        const uint32_t own = nown;
+        const float pe = npe, is2 = nis2;
+        float ys[DP];
+#pragma unroll
+        for (int cc = 0; cc < DP; cc++) ys[cc] = nys[cc];
+        {   // prepare the next round (its records were loaded one iteration ago), fetch the records after it
+            const uint4 rec1 = rec2;
+            const uint32_t own1 = own2;
+            recp2 += 32; ownp2 += 32; left -= 32;               // `left` = in-edges from this lane's slot two rounds ahead
+            if (left > 0) { rec2 = __ldcs(recp2); own2 = __ldcs(ownp2); }
+            prepare(rec1, own1, left + 32 > 0);
+        }
+        const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
+        if (c > 0) {
+            const uint32_t e = (q_head + (uint32_t)q_n + (uint32_t)__popc(fired & ((1u << lane) - 1u))) & (QCAP - 1);
+            q_oc[e] = own | ((uint32_t)min(c, 0xffffff) << 8);
+            q_pe[e] = pe; q_is2[e] = is2;
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) q_ys[cc * QCAP + e] = ys[cc];
+        }
+        q_n += __popc(fired);
+        __syncwarp();
+        if (q_n >= 32) {
+            dense(q_head, 32);
+            q_head = (q_head + 32u) & (QCAP - 1);
+            q_n -= 32;
         }
     }
+    if (q_n > 0) dense(q_head, q_n);
     if (valid) {
+        const float at = t_alpha[lane];
 #pragma unroll
-        for (int c = 0; c < DP; c++) y[c] = F_FMA(alpha_tot, y[c], beta_tot[c]);
+        for (int c = 0; c < DP; c++) y[c] = F_FMA(at, y[c], t_beta[c * 32 + lane]);
         store_row<DP>(a.y_next, node, y);
         // fused exchange: the owner writes its row straight into every peer's replica (NVLink P2P stores, coalesced
         // 32 rows per warp) while other tiles are still computing; a tiny all-reduce closes the mini-epoch
@@ -843,7 +912,7 @@ __global__ void k_debug_draws(EpochArgs a, uint32_t *__restrict__ counts, uint32
     const uint64_t node = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= a.n) return;
     const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
-    const float u = node_uniform((uint32_t)node, a.epoch, a.k2);
+    const float u = node_uniform((uint32_t)node, a.ukey);
     int c_lo = 0;
     for (uint64_t m = r0; m < r1; m++) {
         const int c_hi = cum_ceil(a.kappa, a.cum[m], u);
@@ -1527,6 +1596,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);
     a.n = (uint32_t)ctx->n; a.lo = ctx->lo; a.hi = ctx->hi;
     a.epoch = epoch;
+    a.ukey = epoch_ukey(epoch, a.k2);
     a.k0 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu); a.k1 = (uint32_t)(ctx->prm.seed >> 32);
     // expected firings of edge e per mini-epoch: nb_sampling_by_edge * E * (p_e / n) / M   (embedder.rs:858,987)
     a.kappa = (float)((double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)ctx->n) / (double)M);
@@ -1561,7 +1631,11 @@ static cudaError_t launch_tiled(annembed_cuda_ctx *ctx, const EpochArgs &a)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const unsigned int nb2 = (unsigned int)((tiles + ANNEMBED_WARPS_IN - 1) / ANNEMBED_WARPS_IN);
-    k_epoch_in<DP><<<nb2, ANNEMBED_WARPS_IN * 32, 0, ctx->launch_stream>>>(a);
+    if (InTile<DP>::SMEM > 48 * 1024) {
+        e = cudaFuncSetAttribute(k_epoch_in<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, InTile<DP>::SMEM);
+        if (e != cudaSuccess) return e;
+    }
+    k_epoch_in<DP><<<nb2, ANNEMBED_WARPS_IN * 32, InTile<DP>::SMEM, ctx->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -1570,7 +1644,8 @@ static cudaError_t launch_epoch_dp(annembed_cuda_ctx *ctx, const EpochArgs &a)
 {
     if (a.hi <= a.lo) return cudaSuccess;
     const bool force_generic = (ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL) != 0;
-    const bool tiled_ok = !force_generic && ctx->prm.b == 1.0;     // the tiled kernels are specialised for b == 1
+    // the tiled kernels are specialised for b == 1 and keep the per-edge firing counts of a node in bytes
+    const bool tiled_ok = !force_generic && ctx->prm.b == 1.0 && a.kappa + 2.0f < (float)EpochTile<DP, 8>::MAX_FIRINGS;
     ctx->last_epoch_kernels = (tiled_ok && ctx->kmax <= 16) ? 2 : 1;
     if (tiled_ok && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
     if (tiled_ok && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);

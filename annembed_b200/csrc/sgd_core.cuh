@@ -34,6 +34,17 @@ __host__ __device__ __forceinline__ float fast_div(float a, float b)
     return a / b;
 #endif
 }
+// reciprocal: one MUFU.RCP on the device (rcp.approx.ftz, <= 1 ulp), exact division on the host build
+__host__ __device__ __forceinline__ float fast_rcp(float x)
+{
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 // Explicitly rounded fp32 operations: nvcc may not contract or reorder them, so every kernel that inlines the
 // functions below (tiled, generic, fixed-step) produces bit-identical results for the same inputs.
 #ifdef __CUDA_ARCH__
@@ -122,9 +133,17 @@ template <bool B1>
 __host__ __device__ __forceinline__ float attract_coeff_raw(float D, float p, float inv_s2, const SgdConst &K)
 {
     const float u = F_MUL(D, inv_s2);
-    const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 1.0e4f));                 // alfa = 1/PROBA_MIN :1225-1226
+    if (B1 || K.b_is_one) {
+        // b == 1: gamma * 2/(s^2 (1+u)) * ((1-p)/m - p), m = max(u^2, 1/PROBA_MIN), over one common denominator:
+        // a single reciprocal per interaction
+        const float m = fmaxf(F_MUL(u, u), 1.0e4f);                               // alfa = 1/PROBA_MIN :1225-1226
+        const float num = F_FMA(-p, m, F_SUB(1.0f, p));
+        const float c0 = F_MUL(F_MUL(K.gamma, K.two_b), inv_s2);
+        return fmaxf(F_MUL(F_MUL(c0, num), fast_rcp(F_MUL(F_ADD(1.0f, u), m))), -0.49f);   // :1228-1229
+    }
+    const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 1.0e4f));
     const float w = F_FMA(F_SUB(1.0f, p), rep, -p);                               // -p + (1-p) * rep
-    return fmaxf(F_MUL(F_MUL(K.gamma, cauchy_coeff<B1>(u, inv_s2, K)), w), -0.49f);   // :1228-1229
+    return fmaxf(F_MUL(F_MUL(K.gamma, cauchy_coeff<B1>(u, inv_s2, K)), w), -0.49f);
 }
 template <bool B1>
 __host__ __device__ __forceinline__ float attract_coeff(float D, float p, float inv_s2, const SgdConst &K)
@@ -159,8 +178,15 @@ __host__ __device__ __forceinline__ void repulse(float (&yi)[DP], const float (&
 {
     const float dk = sqdist<DP>(yi, yk);
     const float u = F_MUL(dk, inv_s2);
-    const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 0.0625f));                // alfa = 1/16 :1286-1288
-    const float a = fminf(F_MUL(F_MUL(K.gamma, cauchy_coeff<B1>(u, inv_s2, K)), rep), 2.0f);
+    float a;
+    if (B1 || K.b_is_one) {                                                       // one reciprocal, see attract_coeff_raw
+        const float m = fmaxf(F_MUL(u, u), 0.0625f);                              // alfa = 1/16 :1286-1288
+        const float c0 = F_MUL(F_MUL(K.gamma, K.two_b), inv_s2);
+        a = fminf(F_MUL(c0, fast_rcp(F_MUL(F_ADD(1.0f, u), m))), 2.0f);
+    } else {
+        const float rep = fast_div(1.0f, fmaxf(F_MUL(u, u), 0.0625f));
+        a = fminf(F_MUL(F_MUL(K.gamma, cauchy_coeff<B1>(u, inv_s2, K)), rep), 2.0f);
+    }
     const bool ok = dk > 0.0f;
 #pragma unroll
     for (int c = 0; c < DP; c++) {
@@ -224,7 +250,8 @@ struct EpochArgs {
     const uint8_t *__restrict__ in_own;  // (dst - lo) & 31 of every owned in-edge: its owner lane in the warp tile
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
     const float *__restrict__ cum;       // inclusive cumulative probability along each row (last entry exactly 1)
-    uint32_t k2;                         // Philox2x32 key of the per-node uniform
+    uint32_t k2;                         // Philox2x32 key of the per-mini-epoch key below
+    uint32_t ukey;                       // epoch_ukey(epoch, k2): key of the per-node uniforms of this mini-epoch
     uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
     uint32_t n_peers;                    // fused exchange: replicas of y_next on the other ranks (peer memory over NVLink)
     float *peer_next[7];
@@ -247,16 +274,27 @@ __host__ __device__ __forceinline__ uint32_t map_negative(const EpochArgs &a, ui
 
 // =====================================================================================================
 // the sampler: systematic (low-variance) sampling per node.
-// Node i owns one uniform u_i(epoch) (Philox2x32-10 of (node, epoch)).  Its sample points are s + u_i,
+// Node i owns one uniform u_i(epoch) (node_uniform below).  Its sample points are s + u_i,
 // s = 0,1,..; edge m of the row covers [kappa*P_{m-1}, kappa*P_m) where P is the cumulative edge probability
 // of the row (row sums are 1), so  count_m = ceil(kappa*P_m - u) - ceil(kappa*P_{m-1} - u),
 // E[count_m] = kappa * p_m  (the reference's expectation, embedder.rs:858,987,1182) and every node fires
 // ceil(kappa - u) times per mini-epoch: the reference samples every node at the same rate (P(e) = p_e / N).
 // The destination's owner replays the decision from (src, epoch, P_lo, P_hi): no communication, no atomics.
 // =====================================================================================================
-__host__ __device__ __forceinline__ float node_uniform(uint32_t node, uint32_t epoch, uint32_t k2)
+// ukey = Philox2x32-10(epoch; seed) is drawn once per mini-epoch on the host; per node the uniform is a 2-round
+// multiply-xorshift finaliser of (node * golden + ukey) -- 9 integer instructions instead of a 10-round Philox per
+// node AND per in-edge (the in-edge sweep replays its source's uniform).  Top 24 bits -> [0,1).
+__host__ __device__ __forceinline__ uint32_t epoch_ukey(uint32_t epoch, uint32_t k2)
 {
-    return u01_24(philox2x32_10(node, epoch, k2).x);
+    return philox2x32_10(epoch, 0x75A1C0DEu, k2).x;
+}
+__host__ __device__ __forceinline__ float node_uniform(uint32_t node, uint32_t ukey)
+{
+    uint32_t x = node * 0x9E3779B1u + ukey;
+    x ^= x >> 16; x *= 0x21F0AAADu;
+    x ^= x >> 15; x *= 0x735A2D97u;
+    x ^= x >> 15;
+    return u01_24(x);
 }
 __host__ __device__ __forceinline__ int cum_ceil(float kappa, float P, float u)
 {
@@ -383,7 +421,7 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
     load_row<DP>(a.y_snap, node, y);
     const float inv_s2 = a.inv_s2[node];
     const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
-    const float u = node_uniform(node, a.epoch, a.k2);
+    const float u = node_uniform(node, a.ukey);
     unsigned int s = 0;
     // phase A: out-edges in row order; firing index s runs over the node's sample points
     float P_lo = 0.0f;
@@ -415,7 +453,7 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
     const uint64_t q0 = a.in_ptr[node - a.lo], q1 = a.in_ptr[node - a.lo + 1];
     for (uint64_t q = q0; q < q1; q++) {
         const uint4 rec = a.in_rec[q - a.in_base];
-        const float us = node_uniform(rec.x, a.epoch, a.k2);
+        const float us = node_uniform(rec.x, a.ukey);
         const float Pl = as_float(rec.y), Ph = as_float(rec.z);
         const int c = cum_ceil(a.kappa, Ph, us) - cum_ceil(a.kappa, Pl, us);
         if (c <= 0) continue;

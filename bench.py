@@ -278,7 +278,9 @@ def run_ours(a):
                 e2e_t += time.perf_counter() - t1
                 e2e_samples += emb.stats["positive_samples"]
                 h2d, d2h = emb.stats["h2d_bytes"], emb.stats["d2h_bytes"]
-        e2e = (e2e_t, e2e_samples, h2d, d2h)
+                e2e_dev = {k: emb.stats[k] for k in ("edge_weights_ms", "build_ms", "optimize_ms", "cross_entropy_ms")}
+                e2e_dev["wall_ms"] = 1e3 * (time.perf_counter() - t1)
+        e2e = (e2e_t, e2e_samples, h2d, d2h, e2e_dev)
 
     # ---- reduce over ranks: time = max, work = sum
     def allreduce(v, op):
@@ -330,7 +332,8 @@ def run_ours(a):
         if e2e is not None:
             line["e2e"] = {"value": 6.0 * e2e_s / e2e_tmax, "unit": UNIT, "h2d_bytes_per_step": int(e2e[2]),
                            "d2h_bytes_per_step": int(e2e[3]), "ms_per_step": 1e3 * e2e_tmax / a.steps,
-                           "api": "annembed_b200.Embedder(kgraph, params, initial_embedding).embed() + get_embedded()"}
+                           "api": "annembed_b200.Embedder(kgraph, params, initial_embedding).embed() + get_embedded()",
+                           "last_step_device_ms": e2e[4]}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_arm(a, row_ptr, col, distances, y0, a.cpu_seconds, "rank 0")
         print(json.dumps(line))

@@ -32,6 +32,14 @@ extern "C" void hostsim_philox2(const uint32_t ctr[2], uint32_t key, uint32_t ou
     out[0] = r.x; out[1] = r.y;
 }
 
+// the per-node uniforms of one mini-epoch (systematic-sampling offsets), as the kernels compute them
+extern "C" void hostsim_node_uniforms(uint32_t node0, uint32_t count, uint32_t epoch, uint64_t seed, float *out)
+{
+    const uint32_t k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+    const uint32_t ukey = epoch_ukey(epoch, k2);
+    for (uint32_t i = 0; i < count; i++) out[i] = node_uniform(node0 + i, ukey);
+}
+
 static void build(HostCtx &h, uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *p, const float *emb_scale)
 {
     const uint64_t E = row_ptr[n];
@@ -103,7 +111,7 @@ extern "C" int64_t hostsim_optimize(uint64_t n, uint32_t d, const uint64_t *row_
             a.neg_alias = (const uint2 *)neg_alias;
             a.regular_k = 0; a.cum = h.cum.data(); a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
             a.n = (uint32_t)n; a.lo = 0; a.hi = (uint32_t)n;
-            a.epoch = (iter - 1) * M + m; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+            a.epoch = (iter - 1) * M + m; a.ukey = epoch_ukey(a.epoch, a.k2); a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
             a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
             a.K.gamma = (float)gs; a.K.b = (float)b; a.K.two_b = (float)(2.0 * b); a.K.b_is_one = b == 1.0;
             total += (int64_t)(neg_alias ? run_epoch_dp<true>(DP, a) : run_epoch_dp<false>(DP, a));
@@ -131,10 +139,11 @@ extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_
     a.row_ptr = row_ptr; a.col = col; a.p = p; a.neg_alias = (const uint2 *)neg_alias; a.cum = cum.data();
     a.n = (uint32_t)n; a.epoch = epoch; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
     a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+    a.ukey = epoch_ukey(epoch, a.k2);
     a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
     for (uint64_t node = 0; node < n; node++) {
         const uint64_t r0 = row_ptr[node], r1 = row_ptr[node + 1];
-        const float u = node_uniform((uint32_t)node, epoch, a.k2);
+        const float u = node_uniform((uint32_t)node, a.ukey);
         int c_lo = 0;
         for (uint64_t m = r0; m < r1; m++) {
             const int c_hi = cum_ceil(a.kappa, cum[m], u);

@@ -28,6 +28,12 @@ def philox2(ctr, key):
     return out
 
 
+def node_uniforms(node0, count, epoch, seed):
+    out = np.zeros(count, np.float32)
+    lib().hostsim_node_uniforms(C.c_uint32(node0), C.c_uint32(count), C.c_uint32(epoch), C.c_uint64(seed), _p(out, C.c_float))
+    return out
+
+
 def philox(ctr, key):
     ctr = np.asarray(ctr, np.uint32); key = np.asarray(key, np.uint32); out = np.zeros(4, np.uint32)
     lib().hostsim_philox(_p(ctr, C.c_uint32), _p(key, C.c_uint32), _p(out, C.c_uint32))

@@ -69,6 +69,35 @@ def test_philox4x32_10_known_answers():
         np.testing.assert_array_equal(hs.philox(ctr, key), np.array(exp, np.uint32))
 
 
+def test_node_uniforms_are_uniform_and_uncorrelated():
+    """The systematic-sampling offsets u_i(epoch) (sgd_core.cuh node_uniform: Philox2x32 epoch key + 2-round
+    multiply-xorshift over the node id): uniform over nodes and over epochs, no serial correlation either way,
+    24-bit grid, deterministic, seed-sensitive."""
+    from scipy import stats
+    n = 200000
+    u = hs.node_uniforms(0, n, epoch=7, seed=3)
+    assert u.min() >= 0.0 and u.max() < 1.0
+    assert np.all(u * 16777216.0 == np.floor(u * 16777216.0))
+    assert stats.kstest(u, "uniform").pvalue > 1e-3
+    for lag in (1, 2, 3, 4, 32, 1024):                                        # neighbouring nodes / lanes / tiles
+        assert abs(np.corrcoef(u[:-lag], u[lag:])[0, 1]) < 4.0 / np.sqrt(n)
+    chi = stats.chisquare(np.bincount((u * 256).astype(np.int64), minlength=256)).pvalue
+    assert chi > 1e-3
+    # one node (and a group of 4 lanes) over consecutive mini-epochs
+    E = 4000
+    ue = np.stack([hs.node_uniforms(12344, 4, epoch=e, seed=3) for e in range(E)])   # (E, 4)
+    for c in range(4):
+        assert stats.kstest(ue[:, c], "uniform").pvalue > 1e-3
+        assert abs(np.corrcoef(ue[:-1, c], ue[1:, c])[0, 1]) < 4.0 / np.sqrt(E)
+    assert abs(np.corrcoef(ue[:, 0], ue[:, 1])[0, 1]) < 4.0 / np.sqrt(E)         # two nodes across epochs
+    # pairs (u_i, u_{i+1}) fill the unit square evenly
+    h2 = np.histogram2d(u[0::2], u[1::2], bins=16, range=[[0, 1], [0, 1]])[0].ravel()
+    assert stats.chisquare(h2).pvalue > 1e-3
+    np.testing.assert_array_equal(u, hs.node_uniforms(0, n, epoch=7, seed=3))
+    assert np.mean(u == hs.node_uniforms(0, n, epoch=7, seed=4)) < 1e-3
+    assert np.mean(u == hs.node_uniforms(0, n, epoch=8, seed=3)) < 1e-3
+
+
 def test_sampler_expectation_and_rejection():
     """T6 on the host build: E[count_e] = nbs*E/n/M * p_e ; negatives avoid {i, j} U N(i) (embedder.rs:1246-1252)."""
     row_ptr, col, dist = random_graph(400, 4, 10, seed=5)
