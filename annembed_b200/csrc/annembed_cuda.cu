@@ -108,7 +108,6 @@ struct annembed_cuda_ctx {
     DevBuf<float> emb_scale, inv_s2;
     DevBuf<uint64_t> in_ptr_all;   // n+1, transposed index of the whole graph
     DevBuf<uint4> in_rec;          // in-edge records of the owned slice
-    DevBuf<uint8_t> in_own;        // owner lane of each record in its warp tile
     DevBuf<uint32_t> in_src, in_eid; // structure of the transposed index (graph only)
     uint64_t in_cnt = 0;
     bool have_struct = false;
@@ -337,7 +336,7 @@ __global__ void k_in_ptr(uint64_t E, uint64_t n, const uint32_t *__restrict__ so
 // owned in-edge, in (destination, edge id) order
 __global__ void k_in_struct(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint32_t *__restrict__ sorted_eid,
                             const uint32_t *__restrict__ sorted_dst, uint32_t lo, const uint64_t *__restrict__ row_ptr,
-                            uint32_t *__restrict__ in_src, uint32_t *__restrict__ in_eid, uint8_t *__restrict__ own)
+                            uint32_t *__restrict__ in_src, uint32_t *__restrict__ in_eid)
 {
     const uint64_t q = q_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= q_hi) return;
@@ -346,7 +345,6 @@ __global__ void k_in_struct(uint64_t q_lo, uint64_t q_hi, uint64_t n, const uint
     while (b - a > 1) { const uint64_t mid = (a + b) >> 1; if (row_ptr[mid] <= e) a = mid; else b = mid; }
     in_src[q - q_lo] = (uint32_t)a;
     in_eid[q - q_lo] = e;
-    own[q - q_lo] = (uint8_t)((sorted_dst[q] - lo) & 31u);
 }
 // payload (depends on the weights): {src, P_lo, P_hi, 1/s_src^2}
 __global__ void k_in_rec(uint64_t cnt, const uint32_t *__restrict__ in_src, const uint32_t *__restrict__ in_eid,
@@ -464,7 +462,7 @@ struct EpochTile {
 #define ANNEMBED_WARPS_OUT 4
 #endif
 #ifndef ANNEMBED_MINB_OUT
-#define ANNEMBED_MINB_OUT 5
+#define ANNEMBED_MINB_OUT 6
 #endif
     static constexpr int WARPS = DP <= 4 ? ANNEMBED_WARPS_OUT : (DP <= 16 ? 4 : 2);
     static constexpr int MINB = DP <= 2 ? ANNEMBED_MINB_OUT : (DP <= 4 ? 4 : (DP <= 8 ? 2 : 1));  // blocks/SM the register budget aims at
@@ -695,7 +693,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
 template <int DP>
 struct InTile {
     static constexpr int QCAP = 64;                              // >= 31 left over + 32 new entries
-    static constexpr int WORDS = QCAP * (3 + DP) + 32 * (1 + DP);
+    static constexpr int WORDS = QCAP * (4 + DP) + 32 * (1 + DP);
     static constexpr int PER_WARP = WORDS * 4;
     static constexpr int SMEM = ANNEMBED_WARPS_IN * PER_WARP;
 };
@@ -711,8 +709,9 @@ k_epoch_in(EpochArgs a)
     const uint64_t tile = (uint64_t)blockIdx.x * ANNEMBED_WARPS_IN + wib;
     const uint64_t n0 = (uint64_t)a.lo + tile * 32;
     if (n0 >= a.hi) return;
-    uint32_t *q_oc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)wib * TL::PER_WARP);   // own | count << 8
-    float *q_pe = reinterpret_cast<float *>(q_oc + QCAP);
+    uint32_t *q_q = reinterpret_cast<uint32_t *>(smem_raw + (size_t)wib * TL::PER_WARP);   // in-edge index in the tile
+    uint32_t *q_c = q_q + QCAP;                                  // firings
+    float *q_pe = reinterpret_cast<float *>(q_c + QCAP);
     float *q_is2 = q_pe + QCAP;
     float *q_ys = q_is2 + QCAP;                                  // [DP][QCAP]
     float *t_alpha = q_ys + DP * QCAP;                           // [32]      running composite of each owner:
@@ -726,8 +725,12 @@ k_epoch_in(EpochArgs a)
 #pragma unroll
     for (int c = 0; c < DP; c++) y[c] = 0.0f;
     if (valid) load_row<DP>(a.y_next, node, y);
-    const uint64_t Q0 = a.in_ptr[(uint32_t)n0 - a.lo];
+    const uint64_t my_q0 = a.in_ptr[(valid ? node : (uint32_t)n0) - a.lo];
     const uint64_t Q1 = a.in_ptr[(uint32_t)n0 - a.lo + nvalid];
+    const uint64_t Q0 = __shfl_sync(0xffffffffu, my_q0, 0);
+    // first in-edge of this lane's node relative to the tile's first one (non-decreasing over the lanes): the owner
+    // of in-edge q is the last lane whose value is <= q
+    const uint32_t rel_lo = valid ? (uint32_t)(my_q0 - Q0) : 0xffffffffu;
     const uint32_t n_in = (uint32_t)(Q1 - Q0);                 // in-edges of the tile
     if (n_in == 0) {                                           // nothing to apply: y_next already holds the result
         if (valid)
@@ -738,7 +741,6 @@ k_epoch_in(EpochArgs a)
 #pragma unroll
     for (int c = 0; c < DP; c++) t_beta[c * 32 + lane] = 0.0f;
     const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
-    const uint8_t *ownp = a.in_own + (Q0 - a.in_base) + lane;
 
     // ---- dense stage: `cnt` queued in-edges starting at ring position `head`, lane = queue entry.  Each becomes the
     // affine map y -> alpha y + beta of its owner (coefficient at the owner's position after k_epoch_out); the maps of
@@ -755,12 +757,21 @@ k_epoch_in(EpochArgs a)
         float pe = 0.0f, is2 = 0.0f, ys[DP];
 #pragma unroll
         for (int cc = 0; cc < DP; cc++) ys[cc] = 0.0f;
+        uint32_t q = 0;
         if (act) {
-            const uint32_t oc = q_oc[e];
-            own = oc & 0xffu; c = (int)(oc >> 8);
+            q = q_q[e]; c = (int)q_c[e];
             pe = q_pe[e]; is2 = q_is2[e];
 #pragma unroll
             for (int cc = 0; cc < DP; cc++) ys[cc] = q_ys[cc * QCAP + e];
+        }
+        {   // owner lane: binary search over the lanes' first in-edge (5 shuffles)
+            int o = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, rel_lo, o + step);
+                o += (v <= q) ? step : 0;
+            }
+            if (act) own = (uint32_t)o;
         }
         float yr[DP];
 #pragma unroll
@@ -802,52 +813,46 @@ k_epoch_in(EpochArgs a)
     // kappa * p_e of them) are compacted into the ring, the source-row gather of round r+1 and the records of round
     // r+2 are in flight during round r.
     uint4 rec2 = make_uint4(0, 0, 0, 0);                       // records of the round after next
-    uint32_t own2 = 0;
     int nc = 0;                                                // prepared round
-    uint32_t nown = 0;
     float npe = 0.0f, nis2 = 0.0f, nys[DP];
 #pragma unroll
     for (int cc = 0; cc < DP; cc++) nys[cc] = 0.0f;
-    auto prepare = [&](const uint4 &rec, uint32_t own, bool have) {
+    auto prepare = [&](const uint4 &rec, bool have) {
         nc = 0;
         if (have) {
             const float us = node_uniform(rec.x, a.ukey);
             nc = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
         }
-        nown = own; npe = F_SUB(as_float(rec.z), as_float(rec.y)); nis2 = as_float(rec.w);
+        npe = F_SUB(as_float(rec.z), as_float(rec.y)); nis2 = as_float(rec.w);
         if (nc > 0) load_row<DP>(a.y_snap, rec.x, nys);
     };
     {
         uint4 rec1 = make_uint4(0, 0, 0, 0);
-        uint32_t own1 = 0;
-        if (lane < n_in) { rec1 = __ldcs(recp); own1 = __ldcs(ownp); }
-        if (32 + lane < n_in) { rec2 = __ldcs(recp + 32); own2 = __ldcs(ownp + 32); }
-        prepare(rec1, own1, lane < n_in);
+        if (lane < n_in) rec1 = __ldcs(recp);
+        if (32 + lane < n_in) rec2 = __ldcs(recp + 32);
+        prepare(rec1, lane < n_in);
     }
     const uint4 *recp2 = recp + 32;                            // slot of this lane in the round after next
-    const uint8_t *ownp2 = ownp + 32;
     int left = (int)n_in - 32 - lane;                          // > 0 iff that slot holds an in-edge
     uint32_t q_head = 0;                                       // ring start (warp-uniform)
     int q_n = 0;                                               // queued entries (warp-uniform)
     __syncwarp();
     for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
         const int c = nc;
-        const uint32_t own = nown;
         const float pe = npe, is2 = nis2;
         float ys[DP];
 #pragma unroll
         for (int cc = 0; cc < DP; cc++) ys[cc] = nys[cc];
         {   // prepare the next round (its records were loaded one iteration ago), fetch the records after it
             const uint4 rec1 = rec2;
-            const uint32_t own1 = own2;
-            recp2 += 32; ownp2 += 32; left -= 32;               // `left` = in-edges from this lane's slot two rounds ahead
-            if (left > 0) { rec2 = __ldcs(recp2); own2 = __ldcs(ownp2); }
-            prepare(rec1, own1, left + 32 > 0);
+            recp2 += 32; left -= 32;                            // `left` = in-edges from this lane's slot two rounds ahead
+            if (left > 0) rec2 = __ldcs(recp2);
+            prepare(rec1, left + 32 > 0);
         }
         const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
         if (c > 0) {
             const uint32_t e = (q_head + (uint32_t)q_n + (uint32_t)__popc(fired & ((1u << lane) - 1u))) & (QCAP - 1);
-            q_oc[e] = own | ((uint32_t)min(c, 0xffffff) << 8);
+            q_q[e] = base_q + (uint32_t)lane; q_c[e] = (uint32_t)c;
             q_pe[e] = pe; q_is2[e] = is2;
 #pragma unroll
             for (int cc = 0; cc < DP; cc++) q_ys[cc * QCAP + e] = ys[cc];
@@ -1120,7 +1125,11 @@ static int alloc_layout(annembed_cuda_ctx *ctx)
     const size_t want = (size_t)rows * ctx->DP;
     if (ctx->y[0].n == want) return ANNEMBED_OK;
     close_peers(ctx);
-    CU(ctx->y[0].alloc(want, true)); CU(ctx->y[1].alloc(want, true)); CU(ctx->y0.alloc(want));
+    // multi-rank: plain cudaMalloc (the fused exchange exports these buffers through CUDA IPC, which pool memory
+    // does not support); single rank: pool memory, so that creating and destroying a context per embed() costs no
+    // cudaMalloc/cudaFree (a cudaFree of these buffers was measured at 80-900 ms)
+    const bool ipc = ctx->nranks > 1;
+    CU(ctx->y[0].alloc(want, ipc)); CU(ctx->y[1].alloc(want, ipc)); CU(ctx->y0.alloc(want));
     CU(cudaMemsetAsync(ctx->y[0].p, 0, want * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(ctx->y[1].p, 0, want * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(ctx->y0.p, 0, want * sizeof(float), ctx->stream));
@@ -1359,12 +1368,11 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
     const uint64_t cnt = qr[1] - qr[0];
     ctx->in_cnt = cnt;
     CU(ctx->in_rec.alloc(std::max<uint64_t>(cnt, 1)));
-    CU(ctx->in_own.alloc(std::max<uint64_t>(cnt, 1)));
     CU(ctx->in_src.alloc(std::max<uint64_t>(cnt, 1)));
     CU(ctx->in_eid.alloc(std::max<uint64_t>(cnt, 1)));
     if (cnt) {
         k_in_struct<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, dst_sorted.p, ctx->lo, ctx->row_ptr.p,
-                                                                ctx->in_src.p, ctx->in_eid.p, ctx->in_own.p);
+                                                                ctx->in_src.p, ctx->in_eid.p);
         ctx->st.kernel_launches++;
     }
     if ((rc = sync_stream(ctx))) return rc;
@@ -1587,7 +1595,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.y_snap = ctx->y[ctx->cur].p;
     a.y_next = ctx->y[ctx->cur ^ 1].p;
     a.row_ptr = ctx->row_ptr.p; a.col = ctx->col.p; a.p = ctx->proba.p; a.inv_s2 = ctx->inv_s2.p;
-    a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base; a.in_own = ctx->in_own.p;
+    a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
     a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;

@@ -247,7 +247,6 @@ struct EpochArgs {
     const uint64_t *__restrict__ in_ptr; // transposed index of the owned nodes: in_ptr[node-lo] .. in_ptr[node-lo+1]
     const uint4 *__restrict__ in_rec;   // {src node, edge id, bits(p_e), bits(inv_s2[src])}, entry q at in_rec[q - in_base]
     uint64_t in_base;
-    const uint8_t *__restrict__ in_own;  // (dst - lo) & 31 of every owned in-edge: its owner lane in the warp tile
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
     const float *__restrict__ cum;       // inclusive cumulative probability along each row (last entry exactly 1)
     uint32_t k2;                         // Philox2x32 key of the per-mini-epoch key below

@@ -332,31 +332,46 @@ class Embedder:
             self.initial_embedding = self._get_random_init(1.0)       # embedder.rs:348
         ctx = self.context
         own_ctx = ctx is None
+        import time as _time
+        lap = [_time.perf_counter()]
+        self.host_timings_ms = tm = {}
+
+        def mark(name):                                  # host wall time per phase (the calls are synchronous)
+            lap.append(_time.perf_counter())
+            tm[name] = tm.get(name, 0.0) + 1e3 * (lap[-1] - lap[-2])
         try:
             if own_ctx:
                 ctx = CudaContext(p, self.device)
                 if self.comm is not None:
                     ctx.comm_init(*self.comm)
+            mark("create")
             row_ptr, col, dist = self.kgraph.get_neighbours()
             ctx.set_graph_csr(row_ptr, col, dist)
+            mark("set_graph_csr")
             if own_ctx and self.comm is not None and self.comm[1] > 1 and self.fused_exchange:
                 from .dist import exchange_layout_handles
                 exchange_layout_handles(ctx, self.comm[0], self.comm[1])
+                mark("exchange_layout_handles")
             ctx.edge_weights(want_outputs=False)                       # to_proba_edges, embedder.rs:351
             if p.hubness_weighting:                                    # embedder.rs:810-837
                 counts = ctx.get_hubness_counts()
                 self.hubness_counts = counts
                 n = float(len(counts))
                 ctx.set_neg_weights(np.clip(counts.astype(np.float32), 1.0, n))
+            mark("edge_weights")
             ctx.set_embedding(self.initial_embedding)
+            mark("set_embedding")
             self.cross_entropy = ctx.optimize(want_ce=True)            # entropy_optimize, embedder.rs:356
+            mark("optimize")
             self.embedding = ctx.get_embedding()
+            mark("get_embedding")
             self.stats = ctx.get_stats()
         except AnnembedCudaError as e:
             raise EmbedError(str(e)) from e
         finally:
             if own_ctx and ctx is not None:
                 ctx.close()
+                mark("close")
         return 1
 
     def get_quality_estimate_from_edge_length(self, nbng: int) -> dict:

@@ -280,6 +280,7 @@ def run_ours(a):
                 h2d, d2h = emb.stats["h2d_bytes"], emb.stats["d2h_bytes"]
                 e2e_dev = {k: emb.stats[k] for k in ("edge_weights_ms", "build_ms", "optimize_ms", "cross_entropy_ms")}
                 e2e_dev["wall_ms"] = 1e3 * (time.perf_counter() - t1)
+                e2e_dev["host_phases_ms"] = {k: round(v, 2) for k, v in emb.host_timings_ms.items()}
         e2e = (e2e_t, e2e_samples, h2d, d2h, e2e_dev)
 
     # ---- reduce over ranks: time = max, work = sum
