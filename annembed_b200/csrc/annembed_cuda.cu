@@ -476,12 +476,12 @@ struct EpochTile {
 // ceil(kappa P_m - u) of the row are kept as bytes (<= 126; 0x7f pads the row) in registers: byte-wise
 // (0x80 | s) - ch never borrows and leaves bit 7 set exactly when ch <= s.
 template <int KREG>
-__device__ __forceinline__ int edge_of_firing(const uint32_t (&chb)[KREG / 4], int s)
+__device__ __forceinline__ int edge_of_firing(const uint32_t (&chb)[(KREG + 3) / 4], int s)
 {
     const uint32_t S = (uint32_t)s * 0x01010101u | 0x80808080u;
     int m = 0;
 #pragma unroll
-    for (int w = 0; w < KREG / 4; w++) m += __popc((S - chb[w]) & 0x80808080u);
+    for (int w = 0; w < (KREG + 3) / 4; w++) m += __popc((S - chb[w]) & 0x80808080u);
     return m;
 }
 
@@ -505,7 +505,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
     const bool valid = lane < nvalid;
     float y[DP], g[DP];
     uint32_t rc[KREG];
-    uint32_t chb[KREG / 4];
+    uint32_t chb[(KREG + 3) / 4];
     float inv_s2 = 1.0f;
     int T = 0;
     // ---------------- stage the tile's rows: coalesced global reads, [lane][m] layout with odd stride in smem
@@ -513,7 +513,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         int k;
         if (a.regular_k) {
             // every row has exactly regular_k entries: no row_ptr round trip, edge e of the tile belongs to lane e / k
-            const uint32_t kk = a.regular_k, inv_k = (65536u + kk - 1u) / kk;
+            const uint32_t kk = a.regular_k, inv_k = a.regular_k_inv;
             const uint64_t R0 = n0 * kk;
             const uint32_t tile_edges = (uint32_t)nvalid * kk;
             k = valid ? (int)kk : 0;
@@ -536,7 +536,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
 #pragma unroll
         for (int m = 0; m < KREG; m++) rc[m] = ANNEMBED_NO_NODE;
 #pragma unroll
-        for (int w = 0; w < KREG / 4; w++) chb[w] = 0x7f7f7f7fu;
+        for (int w = 0; w < (KREG + 3) / 4; w++) chb[w] = 0x7f7f7f7fu;
         if (valid) {
             load_row<DP>(a.y_snap, node, y);
             inv_s2 = __ldcs(a.inv_s2 + node);
@@ -699,7 +699,7 @@ struct InTile {
 };
 
 template <int DP>
-__global__ void __launch_bounds__(ANNEMBED_WARPS_IN * 32, (DP <= 4 ? ANNEMBED_MINB_IN : (DP <= 8 ? 6 : (DP <= 16 ? 4 : 2))))
+__global__ void __launch_bounds__(ANNEMBED_WARPS_IN * 32, (DP <= 2 ? ANNEMBED_MINB_IN : (DP <= 4 ? 8 : (DP <= 8 ? 6 : (DP <= 16 ? 4 : 2)))))
 k_epoch_in(EpochArgs a)
 {
     using TL = InTile<DP>;
@@ -812,50 +812,30 @@ k_epoch_in(EpochArgs a)
     // ---- sparse stage: lane = in-edge record.  Replays the source's firing decision; fired in-edges (about
     // kappa * p_e of them) are compacted into the ring, the source-row gather of round r+1 and the records of round
     // r+2 are in flight during round r.
-    uint4 rec2 = make_uint4(0, 0, 0, 0);                       // records of the round after next
-    int nc = 0;                                                // prepared round
-    float npe = 0.0f, nis2 = 0.0f, nys[DP];
-#pragma unroll
-    for (int cc = 0; cc < DP; cc++) nys[cc] = 0.0f;
-    auto prepare = [&](const uint4 &rec, bool have) {
-        nc = 0;
+    // Two alternating register sets (rounds are processed in pairs): no copies between the pipeline stages.
+    struct Prep {
+        int c;                                                 // firings of this lane's in-edge (0: not fired / no in-edge)
+        float pe, is2, ys[DP];
+    };
+    auto prepare = [&](const uint4 &rec, bool have, Prep &P) {
+        P.c = 0;
         if (have) {
             const float us = node_uniform(rec.x, a.ukey);
-            nc = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
+            P.c = cum_ceil(a.kappa, as_float(rec.z), us) - cum_ceil(a.kappa, as_float(rec.y), us);
         }
-        npe = F_SUB(as_float(rec.z), as_float(rec.y)); nis2 = as_float(rec.w);
-        if (nc > 0) load_row<DP>(a.y_snap, rec.x, nys);
+        P.pe = F_SUB(as_float(rec.z), as_float(rec.y)); P.is2 = as_float(rec.w);
+        if (P.c > 0) load_row<DP>(a.y_snap, rec.x, P.ys);
     };
-    {
-        uint4 rec1 = make_uint4(0, 0, 0, 0);
-        if (lane < n_in) rec1 = __ldcs(recp);
-        if (32 + lane < n_in) rec2 = __ldcs(recp + 32);
-        prepare(rec1, lane < n_in);
-    }
-    const uint4 *recp2 = recp + 32;                            // slot of this lane in the round after next
-    int left = (int)n_in - 32 - lane;                          // > 0 iff that slot holds an in-edge
     uint32_t q_head = 0;                                       // ring start (warp-uniform)
     int q_n = 0;                                               // queued entries (warp-uniform)
-    __syncwarp();
-    for (uint32_t base_q = 0; base_q < n_in; base_q += 32) {
-        const int c = nc;
-        const float pe = npe, is2 = nis2;
-        float ys[DP];
-#pragma unroll
-        for (int cc = 0; cc < DP; cc++) ys[cc] = nys[cc];
-        {   // prepare the next round (its records were loaded one iteration ago), fetch the records after it
-            const uint4 rec1 = rec2;
-            recp2 += 32; left -= 32;                            // `left` = in-edges from this lane's slot two rounds ahead
-            if (left > 0) rec2 = __ldcs(recp2);
-            prepare(rec1, left + 32 > 0);
-        }
-        const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
-        if (c > 0) {
+    auto consume = [&](const Prep &P, uint32_t base_q) {
+        const unsigned fired = __ballot_sync(0xffffffffu, P.c > 0);
+        if (P.c > 0) {
             const uint32_t e = (q_head + (uint32_t)q_n + (uint32_t)__popc(fired & ((1u << lane) - 1u))) & (QCAP - 1);
-            q_q[e] = base_q + (uint32_t)lane; q_c[e] = (uint32_t)c;
-            q_pe[e] = pe; q_is2[e] = is2;
+            q_q[e] = base_q + (uint32_t)lane; q_c[e] = (uint32_t)P.c;
+            q_pe[e] = P.pe; q_is2[e] = P.is2;
 #pragma unroll
-            for (int cc = 0; cc < DP; cc++) q_ys[cc * QCAP + e] = ys[cc];
+            for (int cc = 0; cc < DP; cc++) q_ys[cc * QCAP + e] = P.ys[cc];
         }
         q_n += __popc(fired);
         __syncwarp();
@@ -864,6 +844,30 @@ k_epoch_in(EpochArgs a)
             q_head = (q_head + 32u) & (QCAP - 1);
             q_n -= 32;
         }
+    };
+    Prep PA, PB;
+    PA.c = PB.c = 0; PA.pe = PB.pe = PA.is2 = PB.is2 = 0.0f;
+#pragma unroll
+    for (int cc = 0; cc < DP; cc++) PA.ys[cc] = PB.ys[cc] = 0.0f;
+    uint4 recA = make_uint4(0, 0, 0, 0), recB = make_uint4(0, 0, 0, 0);
+    if (lane < n_in) recA = __ldcs(recp);                      // round 0
+    if (32 + lane < n_in) recB = __ldcs(recp + 32);            // round 1
+    prepare(recA, lane < n_in, PA);
+    const uint4 *recp2 = recp + 32;                            // slot of this lane in the round after next
+    int left = (int)n_in - 32 - lane;                          // > 0 iff that slot holds an in-edge
+    __syncwarp();
+    for (uint32_t base_q = 0; base_q < n_in; base_q += 64) {
+        // even round: PA is prepared, recB holds the records of the next round
+        recp2 += 32; left -= 32;                               // `left` = in-edges from this lane's slot two rounds ahead
+        if (left > 0) recA = __ldcs(recp2);
+        prepare(recB, left + 32 > 0, PB);
+        consume(PA, base_q);
+        if (base_q + 32 >= n_in) break;
+        // odd round: PB is prepared, recA holds the records of the next round
+        recp2 += 32; left -= 32;
+        if (left > 0) recB = __ldcs(recp2);
+        prepare(recA, left + 32 > 0, PA);
+        consume(PB, base_q + 32);
     }
     if (q_n > 0) dense(q_head, q_n);
     if (valid) {
@@ -1599,6 +1603,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
     a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;
+    a.regular_k_inv = a.regular_k ? (65536u + a.regular_k - 1u) / a.regular_k : 0u;
     a.n_peers = 0;
     for (int r = 0; r < 7; r++) a.peer_next[r] = nullptr;
     a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);
@@ -1655,6 +1660,7 @@ static cudaError_t launch_epoch_dp(annembed_cuda_ctx *ctx, const EpochArgs &a)
     // the tiled kernels are specialised for b == 1 and keep the per-edge firing counts of a node in bytes
     const bool tiled_ok = !force_generic && ctx->prm.b == 1.0 && a.kappa + 2.0f < (float)EpochTile<DP, 8>::MAX_FIRINGS;
     ctx->last_epoch_kernels = (tiled_ok && ctx->kmax <= 16) ? 2 : 1;
+    if (tiled_ok && ctx->kmax <= 6) return launch_tiled<DP, HUB, 6>(ctx, a);     // row length of the reference's examples
     if (tiled_ok && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
     if (tiled_ok && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);
     k_epoch_generic<DP, HUB><<<nblocks(a.hi - a.lo, 256), 256, 0, ctx->launch_stream>>>(a, ctx->counter.p);

@@ -252,6 +252,7 @@ struct EpochArgs {
     uint32_t k2;                         // Philox2x32 key of the per-mini-epoch key below
     uint32_t ukey;                       // epoch_ukey(epoch, k2): key of the per-node uniforms of this mini-epoch
     uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
+    uint32_t regular_k_inv;              // ceil(65536 / regular_k): e / k == (e * inv) >> 16 for e < 32 * 16
     uint32_t n_peers;                    // fused exchange: replicas of y_next on the other ranks (peer memory over NVLink)
     float *peer_next[7];
     uint32_t n, lo, hi;
@@ -297,7 +298,11 @@ __host__ __device__ __forceinline__ float node_uniform(uint32_t node, uint32_t u
 }
 __host__ __device__ __forceinline__ int cum_ceil(float kappa, float P, float u)
 {
+#ifdef __CUDA_ARCH__
+    return __float2int_ru(fmaf(kappa, P, -u));                // one F2I.CEIL
+#else
     return (int)ceilf(fmaf(kappa, P, -u));
+#endif
 }
 
 // the 5 accepted negatives of firing s of `node` (v2 streams: counter (node, sub, epoch, tag))

@@ -5,9 +5,11 @@ import numpy as np
 import annembed_b200 as A
 from tests.conftest import random_graph
 
-for (n, kmin, kmax, d, hub, flags) in [(1003, 2, 7, 2, False, 0), (777, 3, 14, 3, True, 0), (500, 17, 20, 2, False, 0), (900, 6, 6, 15, False, 0)]:
+for (n, kmin, kmax, d, hub, flags, mini) in [(1003, 2, 7, 2, False, 0, 0), (777, 3, 14, 3, True, 0, 0), (500, 17, 20, 2, False, 0, 0), (900, 6, 6, 15, False, 0, 0),
+                                           (1290, 6, 6, 2, False, 0, 3), (650, 8, 8, 4, True, 0, 2)]:   # constant row length, many firings per node
     row_ptr, col, dist = random_graph(n, kmin, kmax, seed=n)
-    ctx = A.CudaContext(A.EmbedderParams(asked_dim=d, nb_grad_batch=2, grad_step=1.0, hubness_weighting=hub, flags=flags))
+    ctx = A.CudaContext(A.EmbedderParams(asked_dim=d, nb_grad_batch=2, grad_step=1.0, hubness_weighting=hub, flags=flags,
+                                           mini_epochs_per_batch=mini))
     ctx.set_graph_csr(row_ptr, col, dist)
     ctx.edge_weights()
     if hub:
