@@ -66,6 +66,10 @@ SYMBOLS = [
     ("annembed_cuda_get_hubness_counts", C.c_int, [_ctx, u32p]),
     ("annembed_cuda_set_embedding", C.c_int, [_ctx, f32p]),
     ("annembed_cuda_reset_embedding", C.c_int, [_ctx]),
+    ("annembed_cuda_dmap_init", C.c_int, [_ctx, C.c_uint32, C.c_float, f32p]),
+    ("annembed_cuda_dmap_kernel", C.c_int, [_ctx, C.c_uint32, f32p, f32p, f32p, f32p]),
+    ("annembed_cuda_dmap_set_test_matrix", C.c_int, [_ctx, f32p, C.c_uint64]),
+    ("annembed_cuda_dmap_singular_values", C.c_int, [_ctx, f64p, C.c_uint32]),
     ("annembed_cuda_set_embedding_from_projection", C.c_int, [_ctx, C.c_uint64, f32p, u32p, f32p, C.c_float]),
     ("annembed_cuda_get_embedded_scales", C.c_int, [_ctx, f32p]),
     ("annembed_cuda_step_fixed", C.c_int, [_ctx, C.c_uint64, u64p, u32p, C.c_double]),

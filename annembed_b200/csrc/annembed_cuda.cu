@@ -17,6 +17,7 @@
 
 #include "sgd_core.cuh"
 #include "quality.cuh"
+#include "dmap.cuh"
 
 using namespace annembed;
 
@@ -94,6 +95,9 @@ struct annembed_cuda_ctx {
     int n_sm = 148;
     int last_epoch_kernels = 1;                  // kernels per mini-epoch of the path in use (tiled: 2, generic: 1)
     int l2_persist_max = 0, l2_window_max = 0;   // bytes (device attributes)
+    int sm_count = 148;
+    std::vector<double> dmap_sigma;              // singular values of the last dmap_init (diagnostics)
+    std::vector<float> dmap_omega;               // caller-provided test matrix of the range finder (tests), else Philox
 
     // graph (replicated on every rank)
     uint64_t n = 0, E = 0;
@@ -1045,6 +1049,7 @@ extern "C" int annembed_cuda_create(annembed_cuda_ctx **out, const annembed_cuda
         }
     }
     cudaDeviceGetAttribute(&ctx->l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, device);
     if (ctx->l2_persist_max > 0 && !(ctx->prm.flags & ANNEMBED_FLAG_NO_L2_PERSIST))
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ctx->l2_persist_max);
@@ -1482,6 +1487,323 @@ extern "C" int annembed_cuda_set_embedding_from_projection(annembed_cuda_ctx *ct
     if ((rc = sync_stream(ctx))) return rc;
     ctx->have_embedding = true;
     return annembed_cuda_reset_embedding(ctx);
+}
+
+// =====================================================================================================
+// N2: diffusion-map initial layout (embedder.rs:308-345) -- kernels in dmap.cuh
+// =====================================================================================================
+namespace {
+// small dense fp64 helpers for the DMAP_RANK x DMAP_RANK projected problems (host side)
+bool cholesky_upper(const double *G, int r, double *R)          // G = R^T R, R upper triangular (row-major)
+{
+    for (int i = 0; i < r * r; i++) R[i] = 0.0;
+    for (int j = 0; j < r; j++) {
+        double s = G[j * r + j];
+        for (int k = 0; k < j; k++) s -= R[k * r + j] * R[k * r + j];
+        if (!(s > 0.0)) return false;
+        const double d = std::sqrt(s);
+        R[j * r + j] = d;
+        for (int i = j + 1; i < r; i++) {
+            double t = G[j * r + i];
+            for (int k = 0; k < j; k++) t -= R[k * r + j] * R[k * r + i];
+            R[j * r + i] = t / d;
+        }
+    }
+    return true;
+}
+void upper_inverse(const double *R, int r, double *Ri)           // Ri = R^-1 (upper triangular)
+{
+    for (int i = 0; i < r * r; i++) Ri[i] = 0.0;
+    for (int j = 0; j < r; j++) {
+        Ri[j * r + j] = 1.0 / R[j * r + j];
+        for (int i = j - 1; i >= 0; i--) {
+            double s = 0.0;
+            for (int k = i + 1; k <= j; k++) s += R[i * r + k] * Ri[k * r + j];
+            Ri[i * r + j] = -s / R[i * r + i];
+        }
+    }
+}
+// cyclic Jacobi for a symmetric matrix: A = V diag(w) V^T, eigenvalues sorted in decreasing order, V column j <-> w[j]
+void jacobi_eigh(const double *A_in, int r, double *w, double *V)
+{
+    std::vector<double> A(A_in, A_in + r * r);
+    for (int i = 0; i < r; i++) for (int j = 0; j < r; j++) V[i * r + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 100; sweep++) {
+        double off = 0.0, dia = 0.0;
+        for (int i = 0; i < r; i++) for (int j = 0; j < r; j++) (i == j ? dia : off) += A[i * r + j] * A[i * r + j];
+        if (off <= 1e-30 * dia) break;
+        for (int p = 0; p < r - 1; p++)
+            for (int q = p + 1; q < r; q++) {
+                const double apq = A[p * r + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * r + q] - A[p * r + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < r; k++) {
+                    const double akp = A[k * r + p], akq = A[k * r + q];
+                    A[k * r + p] = c * akp - s * akq; A[k * r + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < r; k++) {
+                    const double apk = A[p * r + k], aqk = A[q * r + k];
+                    A[p * r + k] = c * apk - s * aqk; A[q * r + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < r; k++) {
+                    const double vkp = V[k * r + p], vkq = V[k * r + q];
+                    V[k * r + p] = c * vkp - s * vkq; V[k * r + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    std::vector<int> order(r);
+    for (int i = 0; i < r; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return A[a * r + a] > A[b * r + b]; });
+    std::vector<double> Vs(r * r);
+    for (int j = 0; j < r; j++) {
+        w[j] = A[order[j] * r + order[j]];
+        for (int k = 0; k < r; k++) Vs[k * r + j] = V[k * r + order[j]];
+    }
+    std::copy(Vs.begin(), Vs.end(), V);
+}
+} // namespace
+
+static int host_sum(annembed_cuda_ctx *ctx, const float *x, uint64_t n, double *out)
+{
+    int rc;
+    if ((rc = sum_f64(ctx, x, n, ctx->partials.p + 4095))) return rc;
+    CU(cudaMemcpyAsync(out, ctx->partials.p + 4095, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_stream(ctx);
+}
+
+// the symmetric normalised kernel of the loaded graph:  diag + A + A^T, A = one value per directed edge
+struct DmapKernel {
+    DevBuf<uint64_t> tp_ptr;                 // transposed index of the whole graph
+    DevBuf<uint32_t> tp_src, tp_eid;
+    DevBuf<float> normed, val, diag, sw;     // normed first-pass scales, A values, diagonal, sqrt(degrees)
+    double sw_sum = 0.0;
+};
+
+static int dmap_build_kernel(annembed_cuda_ctx *ctx, uint32_t gnbn, DmapKernel &K)
+{
+    const uint64_t n = ctx->n, E = ctx->E;
+    const float alfa = 0.5f, beta = -0.1f, epsil = 2.0f;            // embedder.rs:319-320, diffmaps.rs:100
+    int rc;
+    cudaStream_t st = ctx->stream;
+    const unsigned int gn = nblocks(n, 256);
+    DevBuf<uint64_t> &tp_ptr = K.tp_ptr;
+    DevBuf<uint32_t> &tp_src = K.tp_src, &tp_eid = K.tp_eid;
+    DevBuf<float> &normed = K.normed, &val = K.val, &diag = K.diag, &sw = K.sw;
+    // ---- transposed index of the whole graph (every rank computes the whole layout: it is replicated anyway)
+    {
+        DevBuf<uint32_t> eid, dst_sorted, eid_sorted;
+        DevBuf<unsigned char> tmp;
+        CU(tp_ptr.alloc(n + 2)); CU(tp_src.alloc(E)); CU(tp_eid.alloc(E));
+        CU(eid.alloc(E)); CU(dst_sorted.alloc(E)); CU(eid_sorted.alloc(E));
+        k_iota<<<nblocks(E, 256), 256, 0, st>>>(E, eid.p);
+        int bits = 1; while (bits < 32 && (1ull << bits) < n) bits++;
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, st));
+        CU(tmp.alloc(tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, st));
+        k_in_ptr<<<nblocks(E + 1, 256), 256, 0, st>>>(E, n, dst_sorted.p, tp_ptr.p);
+        k_in_struct<<<nblocks(E, 256), 256, 0, st>>>(0, E, n, eid_sorted.p, dst_sorted.p, 0u, ctx->row_ptr.p, tp_src.p, tp_eid.p);
+        ctx->st.kernel_launches += 4;
+        if ((rc = sync_stream(ctx))) return rc;
+    }
+
+    // ---- node kernels: two passes of scales (diffmaps.rs:752-849)
+    DevBuf<float> scale, w_self, q;
+    CU(scale.alloc(n)); CU(normed.alloc(n)); CU(w_self.alloc(n)); CU(val.alloc(E)); CU(q.alloc(n)); CU(diag.alloc(n));
+    const uint32_t nbgh = std::min<uint32_t>(gnbn, ctx->kmax);
+    k_dmap_local_scale<<<gn, 256, 0, st>>>(n, ctx->row_ptr.p, ctx->dist.p, nbgh, scale.p);
+    double ssum = 0.0;
+    if ((rc = host_sum(ctx, scale.p, n, &ssum))) return rc;
+    const float mean_scale = (float)(ssum / (double)n);
+    REQUIRE(mean_scale > 0.0f && std::isfinite(mean_scale), ANNEMBED_ERR_INVALID_ARG, "dmap_init: all neighbour distances are zero");
+    k_dmap_fix_scale<<<gn, 256, 0, st>>>(n, mean_scale, scale.p, normed.p);
+    const float sqrt_epsil = std::sqrt(epsil);
+    auto kernel_pass = [&](const float *scales) -> int {             // w_self, val = symmetrised weights, q = row sums
+        DevBuf<float> w;
+        CU(w.alloc(E));
+        k_dmap_kernel_weights<<<gn, 256, 0, st>>>(n, ctx->row_ptr.p, ctx->col.p, ctx->dist.p, scales, sqrt_epsil, w_self.p, w.p);
+        k_dmap_symmetrise<<<gn, 256, 0, st>>>(n, ctx->row_ptr.p, ctx->col.p, w.p, val.p);
+        k_dmap_rowsum<<<gn, 256, 0, st>>>(n, ctx->row_ptr.p, tp_ptr.p, tp_eid.p, val.p, w_self.p, 2.0f, q.p);
+        ctx->st.kernel_launches += 3;
+        return sync_stream(ctx);
+    };
+    if ((rc = kernel_pass(scale.p))) return rc;
+    double qsum = 0.0;
+    if ((rc = host_sum(ctx, q.p, n, &qsum))) return rc;
+    {   // kernel0_to_density (diffmaps.rs:852-942): scales <- (q / mean q)^beta * mean_scale
+        DevBuf<float> scale2;
+        CU(scale2.alloc(n));
+        k_dmap_beta_scales<<<gn, 256, 0, st>>>(n, q.p, qsum / (double)n, beta, mean_scale, scale2.p);
+        if ((rc = kernel_pass(scale2.p))) return rc;
+    }
+    // ---- compute_laplacian, sparse branch (diffmaps.rs:504-587)
+    if ((rc = host_sum(ctx, q.p, n, &qsum))) return rc;
+    k_dmap_alpha<<<gn, 256, 0, st>>>(n, ctx->row_ptr.p, ctx->col.p, q.p, qsum / (double)ctx->kmax, alfa, val.p, w_self.p, diag.p);
+    CU(sw.alloc(n));
+    k_dmap_rowsum<<<gn, 256, 0, st>>>(n, ctx->row_ptr.p, tp_ptr.p, tp_eid.p, val.p, diag.p, 1.0f, sw.p);
+    k_dmap_sqrt<<<gn, 256, 0, st>>>(n, sw.p);
+    k_dmap_normalise<<<gn, 256, 0, st>>>(n, ctx->row_ptr.p, ctx->col.p, sw.p, val.p, diag.p);
+    ctx->st.kernel_launches += 7;
+    return host_sum(ctx, sw.p, n, &K.sw_sum);
+}
+
+
+extern "C" int annembed_cuda_dmap_init(annembed_cuda_ctx *ctx, uint32_t gnbn, float diffusion_time, float *y_out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "dmap_init: graph not set");
+    constexpr int R = DMAP_RANK;
+    const uint64_t n = ctx->n;
+    const int d = (int)ctx->prm.asked_dim, DP = ctx->DP;
+    REQUIRE(d <= R - 1, ANNEMBED_ERR_UNSUPPORTED, "dmap_init: asked_dim must be <= 19 (rank-20 range finder, graphlaplace.rs:113)");
+    REQUIRE(n >= 4 * R, ANNEMBED_ERR_UNSUPPORTED, "dmap_init: graph too small for the rank-20 range finder");
+    if (gnbn == 0) gnbn = 12;                                       // embedder.rs:317
+    if (!(diffusion_time > 0.0f)) diffusion_time = 5.0f;            // embedder.rs:316
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = alloc_layout(ctx))) return rc;
+    cudaStream_t st = ctx->stream;
+    const unsigned int gn = nblocks(n, 256);
+    DmapKernel K;
+    if ((rc = dmap_build_kernel(ctx, gnbn, K))) return rc;
+    DevBuf<uint64_t> &tp_ptr = K.tp_ptr;
+    DevBuf<uint32_t> &tp_src = K.tp_src, &tp_eid = K.tp_eid;
+    DevBuf<float> &normed = K.normed, &val = K.val, &diag = K.diag, &sw = K.sw;
+    const double sw_sum = K.sw_sum;
+
+    // ---- range finder: rank-20 subspace iteration, 5 iterations (svdapprox.rs:343-410), QR by two Cholesky passes
+    DevBuf<float> Ya, Yb;
+    DevBuf<double> gpart, dM;
+    CU(Ya.alloc(n * R)); CU(Yb.alloc(n * R)); CU(dM.alloc(R * R + R * R));
+    const unsigned int gram_blocks = std::min<unsigned int>(nblocks(n, DMAP_GRAM_ROWS), (unsigned int)ctx->sm_count * 4u);
+    CU(gpart.alloc((size_t)gram_blocks * R * R));
+    std::vector<double> G(R * R), Rm(R * R), Ri(R * R);
+    auto gram = [&](const float *Y) -> int {
+        k_dmap_gram<<<gram_blocks, R * R, 0, st>>>(n, Y, gpart.p);
+        k_dmap_gram_final<<<1, R * R, 0, st>>>(gram_blocks, gpart.p, dM.p + R * R);
+        ctx->st.kernel_launches += 2;
+        CU(cudaMemcpyAsync(G.data(), dM.p + R * R, sizeof(double) * R * R, cudaMemcpyDeviceToHost, st));
+        return sync_stream(ctx);
+    };
+    auto right_multiply = [&](const double *M, int ncols, const float *Yin, float *out, int stride) -> int {
+        CU(cudaMemcpyAsync(dM.p, M, sizeof(double) * R * ncols, cudaMemcpyHostToDevice, st));
+        k_dmap_right_multiply<<<nblocks(n, 128), 128, 0, st>>>(n, ncols, dM.p, Yin, out, stride);
+        ctx->st.kernel_launches++;
+        return sync_stream(ctx);
+    };
+    auto orthonormalise = [&](float *Y) -> int {                     // Y <- Q of its QR factorisation (in place)
+        for (int pass = 0; pass < 2; pass++) {
+            if ((rc = gram(Y))) return rc;
+            REQUIRE(cholesky_upper(G.data(), R, Rm.data()), ANNEMBED_ERR_UNSUPPORTED, "dmap_init: range finder lost rank (graph kernel has fewer than 20 significant directions)");
+            upper_inverse(Rm.data(), R, Ri.data());
+            if ((rc = right_multiply(Ri.data(), R, Y, Y, R))) return rc;
+        }
+        return ANNEMBED_OK;
+    };
+    auto spmm = [&](const float *X, float *Y) {
+        k_dmap_spmm<<<nblocks(n, 128), 128, 0, st>>>(n, ctx->row_ptr.p, ctx->col.p, tp_ptr.p, tp_src.p, tp_eid.p, val.p, diag.p, X, Y);
+        ctx->st.kernel_launches++;
+    };
+    if (ctx->dmap_omega.size() == (size_t)n * R) {
+        if ((rc = h2d(ctx, Yb.p, ctx->dmap_omega.data(), (size_t)n * R * sizeof(float)))) return rc;
+    } else {
+        k_dmap_gaussian<<<gn, 256, 0, st>>>(n, (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu), (uint32_t)(ctx->prm.seed >> 32), Yb.p);
+    }
+    spmm(Yb.p, Ya.p);
+    if ((rc = orthonormalise(Ya.p))) return rc;
+    for (int it = 1; it < DMAP_ITERS; it++) {
+        spmm(Ya.p, Yb.p);                                           // K^T Q (the kernel is symmetric)
+        if ((rc = orthonormalise(Yb.p))) return rc;
+        spmm(Yb.p, Ya.p);
+        if ((rc = orthonormalise(Ya.p))) return rc;
+    }
+    // ---- direct SVD (svdapprox.rs:721-801): B = Q^T K; B B^T = (K Q)^T (K Q); U = Q U_B, sigma = sqrt(eig)
+    spmm(Ya.p, Yb.p);
+    if ((rc = gram(Yb.p))) return rc;
+    std::vector<double> ev(R), V(R * R);
+    jacobi_eigh(G.data(), R, ev.data(), V.data());
+    REQUIRE(ev[0] > 0.0, ANNEMBED_ERR_CUDA, "dmap_init: projected kernel has no positive eigenvalue");
+    std::vector<double> Vd((size_t)R * d);
+    std::vector<float> lam_t(32, 0.0f);
+    for (int c = 0; c < d; c++) {
+        for (int k = 0; k < R; k++) Vd[(size_t)k * d + c] = V[k * R + (c + 1)];      // skip the first (stationary) vector
+        const double ratio = std::sqrt(std::max(ev[c + 1], 0.0) / ev[0]);           // lambda_{c+1} / lambda_0 (diffmaps.rs:1208)
+        lam_t[c] = (float)std::pow(ratio, (double)diffusion_time);
+    }
+    ctx->dmap_sigma.assign(R, 0.0);
+    for (int k = 0; k < R; k++) ctx->dmap_sigma[k] = std::sqrt(std::max(ev[k], 0.0));
+    DevBuf<float> U, dlam;
+    CU(U.alloc(n * d)); CU(dlam.alloc(32));
+    if ((rc = right_multiply(Vd.data(), d, Ya.p, U.p, d))) return rc;
+    CU(cudaMemcpyAsync(dlam.p, lam_t.data(), 32 * sizeof(float), cudaMemcpyHostToDevice, st));
+    // ---- coordinates (diffmaps.rs:1219-1236) into the padded layout, then set_data_box(., 10) (embedder.rs:345)
+    CU(cudaMemsetAsync(ctx->y0.p, 0, ctx->y0.n * sizeof(float), st));
+    k_dmap_coordinates<<<gn, 256, 0, st>>>(n, d, DP, U.p, dlam.p, normed.p, sw.p, (float)(sw_sum / (double)n), ctx->y0.p);
+    const unsigned int rb = std::min<unsigned int>(gn, 1024u);
+    DevBuf<double> cpart;
+    DevBuf<float> bmax, dmeans;
+    CU(cpart.alloc((size_t)rb * 32)); CU(bmax.alloc(rb)); CU(dmeans.alloc(32));
+    k_dmap_colsum<<<rb, 256, 0, st>>>(n, d, DP, ctx->y0.p, cpart.p);
+    std::vector<double> hpart((size_t)rb * 32);
+    CU(cudaMemcpyAsync(hpart.data(), cpart.p, hpart.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if ((rc = sync_stream(ctx))) return rc;
+    std::vector<float> means(32, 0.0f);
+    for (int c = 0; c < d; c++) {
+        double s = 0.0;
+        for (unsigned int b = 0; b < rb; b++) s += hpart[(size_t)b * 32 + c];
+        means[c] = (float)(s / (double)n);
+    }
+    CU(cudaMemcpyAsync(dmeans.p, means.data(), 32 * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_dmap_center_max<<<rb, 256, 0, st>>>(n, d, DP, dmeans.p, ctx->y0.p, bmax.p);
+    std::vector<float> hmax(rb);
+    CU(cudaMemcpyAsync(hmax.data(), bmax.p, rb * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if ((rc = sync_stream(ctx))) return rc;
+    float mx = 0.0f;
+    for (float v : hmax) mx = std::max(mx, v);
+    REQUIRE(mx > 0.0f && std::isfinite(mx), ANNEMBED_ERR_CUDA, "dmap_init: degenerate layout");
+    k_dmap_scale<<<nblocks(n * DP, 256), 256, 0, st>>>(n * DP, 1.0f / (mx / 5.0f), ctx->y0.p);       // box_size 10 / 2
+    ctx->st.kernel_launches += 6;
+    if ((rc = sync_stream(ctx))) return rc;
+    ctx->have_embedding = true;
+    if ((rc = annembed_cuda_reset_embedding(ctx))) return rc;
+    if (y_out) return annembed_cuda_get_embedding(ctx, y_out);
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_dmap_singular_values(const annembed_cuda_ctx *ctx, double *sigma_out, uint32_t count)
+{
+    if (!ctx || !sigma_out) return ANNEMBED_ERR_INVALID_ARG;
+    if (ctx->dmap_sigma.empty()) return ANNEMBED_ERR_STATE;
+    for (uint32_t k = 0; k < count; k++) sigma_out[k] = k < ctx->dmap_sigma.size() ? ctx->dmap_sigma[k] : 0.0;
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_dmap_set_test_matrix(annembed_cuda_ctx *ctx, const float *omega, uint64_t rows)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    if (!omega) { ctx->dmap_omega.clear(); return ANNEMBED_OK; }
+    REQUIRE(ctx->have_graph && rows == ctx->n, ANNEMBED_ERR_INVALID_ARG, "dmap_set_test_matrix: needs the graph and n rows of 20 columns");
+    ctx->dmap_omega.assign(omega, omega + (size_t)rows * DMAP_RANK);
+    return ANNEMBED_OK;
+}
+
+extern "C" int annembed_cuda_dmap_kernel(annembed_cuda_ctx *ctx, uint32_t gnbn, float *diag_out, float *val_out,
+                                        float *sw_out, float *normed_scale_out)
+{
+    if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
+    REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "dmap_kernel: graph not set");
+    if (gnbn == 0) gnbn = 12;
+    CU(cudaSetDevice(ctx->device));
+    DmapKernel K;
+    int rc;
+    if ((rc = dmap_build_kernel(ctx, gnbn, K))) return rc;
+    if (diag_out && (rc = d2h(ctx, diag_out, K.diag.p, ctx->n * sizeof(float)))) return rc;
+    if (val_out && (rc = d2h(ctx, val_out, K.val.p, ctx->E * sizeof(float)))) return rc;
+    if (sw_out && (rc = d2h(ctx, sw_out, K.sw.p, ctx->n * sizeof(float)))) return rc;
+    if (normed_scale_out && (rc = d2h(ctx, normed_scale_out, K.normed.p, ctx->n * sizeof(float)))) return rc;
+    return ANNEMBED_OK;
 }
 
 extern "C" int annembed_cuda_reset_embedding(annembed_cuda_ctx *ctx)

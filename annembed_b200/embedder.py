@@ -145,6 +145,34 @@ class CudaContext:
                                                                       ptr(proj_node, C.c_uint32), ptr(proj_dist, C.c_float),
                                                                       median_dist))
 
+    def dmap_init(self, gnbn: int = 12, diffusion_time: float = 5.0, want_output: bool = True):
+        """≙ the dmap_init branch of one_step_embed (embedder.rs:308-345) on the device: computes the diffusion-map
+        layout of the loaded graph, installs it as the initial embedding and returns it (n x asked_dim)."""
+        out = np.empty((self.n, self.params.asked_dim), np.float32) if want_output else None
+        self._ck(self.lib.annembed_cuda_dmap_init(self.h, int(gnbn), float(diffusion_time), ptr(out, C.c_float)))
+        return out
+
+    def dmap_kernel(self, gnbn: int = 12):
+        """(diag[n], val[E], sw[n], normed_scale[n]) of the symmetric normalised kernel (see annembed_cuda_dmap_kernel)."""
+        diag = np.empty(self.n, np.float32); val = np.empty(self.E, np.float32)
+        sw = np.empty(self.n, np.float32); normed = np.empty(self.n, np.float32)
+        self._ck(self.lib.annembed_cuda_dmap_kernel(self.h, int(gnbn), ptr(diag, C.c_float), ptr(val, C.c_float),
+                                                    ptr(sw, C.c_float), ptr(normed, C.c_float)))
+        return diag, val, sw, normed
+
+    def dmap_set_test_matrix(self, omega):
+        if omega is None:
+            self._ck(self.lib.annembed_cuda_dmap_set_test_matrix(self.h, None, 0))
+            return
+        omega = np.ascontiguousarray(omega, np.float32)
+        assert omega.shape == (self.n, 20)
+        self._ck(self.lib.annembed_cuda_dmap_set_test_matrix(self.h, ptr(omega, C.c_float), self.n))
+
+    def dmap_singular_values(self, count: int = 20) -> np.ndarray:
+        out = np.zeros(count, np.float64)
+        self._ck(self.lib.annembed_cuda_dmap_singular_values(self.h, ptr(out, C.c_double), count))
+        return out
+
     def reset_embedding(self):
         self._ck(self.lib.annembed_cuda_reset_embedding(self.h))
 
@@ -325,10 +353,8 @@ class Embedder:
         p = self.parameters
         if getattr(self, "hkgraph", None) is not None:
             return self.h_embed()                                                   # embedder.rs:186-190
-        if self.initial_embedding is None:
-            if p.dmap_init:
-                raise EmbedError("dmap_init=true needs an explicit initial_embedding: the diffusion-map layout "
-                                 "(embedder.rs:308-345) is outside this library's hot path")
+        device_dmap = self.initial_embedding is None and p.dmap_init    # embedder.rs:308-345 on the device
+        if self.initial_embedding is None and not p.dmap_init:
             self.initial_embedding = self._get_random_init(1.0)       # embedder.rs:348
         ctx = self.context
         own_ctx = ctx is None
@@ -359,8 +385,12 @@ class Embedder:
                 n = float(len(counts))
                 ctx.set_neg_weights(np.clip(counts.astype(np.float32), 1.0, n))
             mark("edge_weights")
-            ctx.set_embedding(self.initial_embedding)
-            mark("set_embedding")
+            if device_dmap:
+                self.initial_embedding = ctx.dmap_init()
+                mark("dmap_init")
+            else:
+                ctx.set_embedding(self.initial_embedding)
+                mark("set_embedding")
             self.cross_entropy = ctx.optimize(want_ce=True)            # entropy_optimize, embedder.rs:356
             mark("optimize")
             self.embedding = ctx.get_embedding()

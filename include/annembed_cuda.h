@@ -139,6 +139,28 @@ int annembed_cuda_get_hubness_counts(annembed_cuda_ctx *ctx, uint32_t *counts /*
  * embedder.rs:794-798).  A device-resident copy is kept for annembed_cuda_reset_embedding. */
 int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *y);
 int annembed_cuda_reset_embedding(annembed_cuda_ctx *ctx);
+/* Diffusion-map initial layout computed on the device from the loaded graph and installed like set_embedding
+ * ≙ the dmap_init branch of one_step_embed (embedder.rs:308-345): DiffusionMaps::embed_from_kgraph with
+ * DiffusionParams::new(., Some(5.), Some(12)), alfa 0.5, beta -0.1 (diffmaps.rs:397-587,752-942: density-adapted
+ * symmetrised kernel, sparse formulation), rank-20 / 5-iteration subspace SVD (graphlaplace.rs:97-134,
+ * tools/svdapprox.rs:343-425,721-801), coordinates (lambda_j/lambda_0)^t U_ij / weight_i clipped to +-10
+ * (diffmaps.rs:1145-1243), then set_data_box(., 10) (embedder.rs:345,1376-1408).  The layout has asked_dim columns
+ * (<= 19).  gnbn = 0 -> 12, diffusion_time <= 0 -> 5.  The Gaussian test matrix is drawn from the context seed, so
+ * the layout is deterministic.  y_out (n x asked_dim) may be NULL. */
+int annembed_cuda_dmap_init(annembed_cuda_ctx *ctx, uint32_t gnbn, float diffusion_time, float *y_out);
+/* The symmetric normalised kernel annembed_cuda_dmap_init decomposes ≙ GraphLaplacian{sym_kernel, normalizer}
+ * (diffmaps.rs:504-587), as  diag + A + A^T  with A = val on the directed edges of the graph (CSR order);
+ * sw = sqrt(degrees) (`normalizer`), normed_scale = first-pass scales / their mean (diffmaps.rs:806).  Any output
+ * may be NULL.  For tests and diagnostics. */
+int annembed_cuda_dmap_kernel(annembed_cuda_ctx *ctx, uint32_t gnbn, float *diag_out /*[n]*/, float *val_out /*[E]*/,
+                              float *sw_out /*[n]*/, float *normed_scale_out /*[n]*/);
+/* Replace the Gaussian test matrix of the range finder (svdapprox.rs:363) by the caller's (rows = n, 20 columns,
+ * row-major) for the following annembed_cuda_dmap_init calls; NULL restores the seeded generator.  Lets a test feed
+ * the CPU restatement and the device the same random matrix. */
+int annembed_cuda_dmap_set_test_matrix(annembed_cuda_ctx *ctx, const float *omega /*[rows*20], nullable*/, uint64_t rows);
+/* Singular values (decreasing) of the rank-20 approximation computed by the last annembed_cuda_dmap_init
+ * ≙ the spectrum logged at diffmaps.rs:1182-1197. */
+int annembed_cuda_dmap_singular_values(const annembed_cuda_ctx *ctx, double *sigma_out, uint32_t count);
 /* Hierarchical embedding, second-step initial layout ≙ h_embed (embedder.rs:245-269): nodes < n_small keep `first`
  * (the first-step layout of the small graph, n_small x asked_dim); every other node i starts at
  * first[proj_node[i]] + clip(sqrt((proj_dist[i] / median_dist) / asked_dim) * N(0,1), 2) per coordinate, where

@@ -10,8 +10,9 @@
 //   get_embedded_by_dataid / _by_nodeid           embedder.rs:409,421
 //   get_initial_embedding[_reindexed]             embedder.rs:426,430
 //   get_nb_nodes, get_asked_dimension, ...        embedder.rs:135-153,785
-// Out of this library's scope: the diffusion-map initial layout (an explicit initial layout is
-// required when dmap_init is true), from_hkgraph, get_quality_estimate_from_edge_length.
+// dmap_init = true without an explicit initial layout computes the diffusion-map layout on the device
+// (annembed_cuda_dmap_init ≙ embedder.rs:308-345).  Not mirrored here (the Python mirror has them): from_hkgraph,
+// get_quality_estimate_from_edge_length.
 #pragma once
 #include <cstdint>
 #include <random>
@@ -106,16 +107,15 @@ public:
     int embed()
     {
         const size_t n = get_nb_nodes(), d = parameters_.asked_dim;
-        if (initial_embedding_.empty()) {
-            if (parameters_.dmap_init)
-                throw EmbedError(ANNEMBED_ERR_STATE, "dmap_init=true needs an explicit initial embedding (embedder.rs:308-345 is outside the device path)");
+        const bool device_dmap = initial_embedding_.empty() && parameters_.dmap_init;   // embedder.rs:308-345 on the device
+        if (initial_embedding_.empty() && !parameters_.dmap_init) {
             // ≙ get_random_init(1.) (embedder.rs:348,456-470): uniform in [-0.5, 0.5]^d
             std::mt19937_64 rng(parameters_.seed);
             std::uniform_real_distribution<float> u(-0.5f, 0.5f);
             initial_embedding_.resize(n * d);
             for (auto &v : initial_embedding_) v = u(rng);
         }
-        if (initial_embedding_.size() != n * d) throw EmbedError(ANNEMBED_ERR_INVALID_ARG, "initial embedding must be n x asked_dim");
+        if (!device_dmap && initial_embedding_.size() != n * d) throw EmbedError(ANNEMBED_ERR_INVALID_ARG, "initial embedding must be n x asked_dim");
         annembed_cuda_ctx *ctx = nullptr;
         const annembed_cuda_params cp = parameters_.to_c();
         int st = annembed_cuda_create(&ctx, &cp, device_);
@@ -136,7 +136,12 @@ public:
             for (size_t i = 0; i < n; i++) w[i] = std::min(std::max((float)hubness_counts_[i], 1.0f), (float)n);
             check(annembed_cuda_set_neg_weights(ctx, w.data()));
         }
-        check(annembed_cuda_set_embedding(ctx, initial_embedding_.data()));
+        if (device_dmap) {
+            initial_embedding_.resize(n * d);
+            check(annembed_cuda_dmap_init(ctx, 12, 5.0f, initial_embedding_.data()));   // gnbn, diffusion time: embedder.rs:316-317
+        } else {
+            check(annembed_cuda_set_embedding(ctx, initial_embedding_.data()));
+        }
         check(annembed_cuda_optimize(ctx, &ce_initial_, &ce_final_));              // embedder.rs:356
         embedding_.resize(n * d);
         check(annembed_cuda_get_embedding(ctx, embedding_.data()));

@@ -40,6 +40,8 @@ extern "C" {
     pub fn annembed_cuda_edge_weights(ctx: *mut annembed_cuda_ctx, scale_out: *mut f32, proba_out: *mut f32) -> c_int;
     pub fn annembed_cuda_set_neg_weights(ctx: *mut annembed_cuda_ctx, w: *const f32) -> c_int;
     pub fn annembed_cuda_set_embedding(ctx: *mut annembed_cuda_ctx, y: *const f32) -> c_int;
+    /// the dmap_init branch of one_step_embed (src/embedder.rs:308-345) on the device; y_out may be null
+    pub fn annembed_cuda_dmap_init(ctx: *mut annembed_cuda_ctx, gnbn: u32, diffusion_time: f32, y_out: *mut f32) -> c_int;
     pub fn annembed_cuda_optimize(ctx: *mut annembed_cuda_ctx, ce_initial: *mut f64, ce_final: *mut f64) -> c_int;
     pub fn annembed_cuda_get_embedding(ctx: *mut annembed_cuda_ctx, y_out: *mut f32) -> c_int;
 }

@@ -48,7 +48,7 @@ int main(int argc, char **argv)
     EmbedderParams params;                       // EmbedderParams::default()
     CHECK(params.asked_dim == 2 && params.nb_grad_batch == 20 && params.nb_sampling_by_edge == 10 && params.grad_step == 2.0);
     params.asked_dim = 5;                        // embedder.rs:1463
-    params.dmap_init = false;                    // the dmap layout is outside the device path
+    params.dmap_init = false;                    // random initial layout (embedder.rs:348)
     Embedder embedder(g, params);
     int res = 0;
     try { res = embedder.embed(); } catch (const EmbedError &e) { std::fprintf(stderr, "embed failed: %s\n", e.what()); return 1; }
@@ -69,10 +69,15 @@ int main(int argc, char **argv)
     uint64_t tot = 0; for (uint32_t c : hub.get_hubness()) tot += c;
     CHECK(tot == g.col.size());
 
-    // error behaviour: dmap_init without a layout, an empty neighbourhood (kdumap.rs:75-85), wrong layout size
+    // dmap_init = true (the default): the diffusion-map layout is computed on the device (embedder.rs:308-345),
+    // boxed to [-5, 5] by set_data_box(., 10)
     EmbedderParams p2;
     Embedder e2(g, p2);
-    try { e2.embed(); return 1; } catch (const EmbedError &e) { CHECK(e.status == ANNEMBED_ERR_STATE); }
+    CHECK(e2.embed() == 1);
+    float mx = 0.f;
+    for (float v : e2.get_initial_embedding()) mx = std::max(mx, std::fabs(v));
+    CHECK(e2.get_initial_embedding().size() == n * 2 && std::fabs(mx - 5.f) < 1e-3f);
+    // error behaviour: an empty neighbourhood (kdumap.rs:75-85), wrong layout size
     KGraph bad = g;
     bad.row_ptr[4] = bad.row_ptr[3];             // node 3 loses its neighbours (and row 3/4 become inconsistent -> status)
     p2.dmap_init = false;

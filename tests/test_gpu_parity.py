@@ -365,8 +365,11 @@ def test_embedder_mirror_end_to_end():
     np.testing.assert_array_equal(r[ids.astype(np.int64)], y)
     assert emb.cross_entropy[1] < emb.cross_entropy[0]
     assert emb.get_hubness().sum() == len(col)
-    with pytest.raises(A.EmbedError):
-        A.Embedder(g, A.EmbedderParams(dmap_init=True)).embed()
+    # the default dmap_init=True computes the diffusion-map layout on the device (embedder.rs:308-345, tests/test_gpu_dmap.py)
+    e2 = A.Embedder(g, A.EmbedderParams(dmap_init=True, nb_grad_batch=3))
+    assert e2.embed() == 1 and abs(np.abs(e2.get_initial_embedding()).max() - 5) < 1e-3
+    with pytest.raises(A.EmbedError):                       # asked_dim beyond the rank-20 range finder
+        A.Embedder(g, A.EmbedderParams(dmap_init=True, asked_dim=25)).embed()
 
 
 def test_cpp_driver_of_the_host_mirror():
