@@ -128,3 +128,26 @@ def test_dmap_errors():
         ctx.dmap_init()                                    # too small for a rank-20 range finder
     assert e.value.status == 6
     ctx.close()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_dmap_against_golden_fixture(d):
+    """The committed vectors (tests/golden/dmap_small.npz, graph of hotpath_small.npz: ragged rows, zero distances,
+    duplicated rows): kernel entries and, with the fixture's Gaussian matrix, singular values and layout."""
+    import os
+    here = os.path.dirname(__file__)
+    G = np.load(os.path.join(here, "golden", "hotpath_small.npz"))
+    D = np.load(os.path.join(here, "golden", "dmap_small.npz"))
+    g = A.KGraph(G["row_ptr"], G["col"], G["dist"])
+    ctx = ctx_for(g, asked_dim=d)
+    diag, val, sw, normed = ctx.dmap_kernel(12)
+    assert rel_err(diag, D["diag"]) <= 1e-5 and rel_err(val, D["val"]) <= 2e-5
+    assert rel_err(sw, D["sw"]) <= 1e-5 and rel_err(normed, D["normed"]) <= 1e-5
+    ctx.dmap_set_test_matrix(D["omega"])
+    y = ctx.dmap_init()
+    np.testing.assert_allclose(ctx.dmap_singular_values(), D["sigma"], atol=2e-4)
+    ref = D[f"layout_d{d}"]
+    for c in range(d):
+        s = np.sign(np.dot(y[:, c], ref[:, c]))
+        assert np.abs(s * y[:, c] - ref[:, c]).max() < 0.05, c
+    ctx.close()
