@@ -210,3 +210,71 @@ def test_hubness_sampler_follows_the_weights():
     chi2 = ((hist - expect) ** 2 / expect).sum()
     assert chi2 < n + 6 * np.sqrt(2 * n), chi2
     assert np.corrcoef(hist, w)[0, 1] > 0.98
+
+
+class _RecordingContext:
+    """Stands in for CudaContext (the `context=` argument of Embedder): records the call sequence of embed()."""
+
+    def __init__(self, n, d):
+        self.calls, self.n, self.d = [], n, d
+
+    def set_graph_csr(self, row_ptr, col, dist):
+        self.calls.append("set_graph_csr")
+
+    def edge_weights(self, want_outputs=True):
+        self.calls.append("edge_weights")
+
+    def get_hubness_counts(self):
+        self.calls.append("get_hubness_counts")
+        return np.arange(self.n, dtype=np.uint32)
+
+    def set_neg_weights(self, w):
+        self.calls.append("set_neg_weights")
+        self.neg_w = np.array(w)
+
+    def set_embedding(self, y):
+        self.calls.append("set_embedding")
+
+    def dmap_init(self):
+        self.calls.append("dmap_init")
+        return np.full((self.n, self.d), 0.5, np.float32)
+
+    def optimize(self, want_ce=True):
+        self.calls.append("optimize")
+        return (2.0, 1.0)
+
+    def get_embedding(self):
+        self.calls.append("get_embedding")
+        return np.zeros((self.n, self.d), np.float32)
+
+    def get_stats(self):
+        return {"positive_samples": 0}
+
+
+def test_embed_call_sequence_follows_one_step_embed():
+    """one_step_embed (embedder.rs:298-371): dmap_init without a layout -> device diffusion-map layout (:308-345);
+    explicit layout -> set_embedding; dmap_init=false -> get_random_init(1.) (:348); hubness weights = clamp(count, 1, n)
+    (:826-833).  Host logic only: the device context is a recording stand-in."""
+    row_ptr, col, dist = random_graph(60, 3, 5, seed=2)
+    g = A.KGraph(row_ptr, col, dist)
+    ctx = _RecordingContext(60, 2)
+    e = A.Embedder(g, A.EmbedderParams(dmap_init=True), context=ctx)
+    assert e.embed() == 1
+    assert ctx.calls == ["set_graph_csr", "edge_weights", "dmap_init", "optimize", "get_embedding"]
+    assert e.get_initial_embedding().shape == (60, 2) and e.cross_entropy == (2.0, 1.0)
+    assert "dmap_init" in e.host_timings_ms and "set_embedding" not in e.host_timings_ms
+
+    ctx = _RecordingContext(60, 2)
+    y0 = np.zeros((60, 2), np.float32)
+    e = A.Embedder(g, A.EmbedderParams(dmap_init=True, hubness_weighting=True), initial_embedding=y0, context=ctx)
+    e.embed()
+    assert ctx.calls == ["set_graph_csr", "edge_weights", "get_hubness_counts", "set_neg_weights", "set_embedding",
+                         "optimize", "get_embedding"]
+    assert ctx.neg_w.min() == 1.0 and ctx.neg_w.max() == 59.0          # clamp(count, 1, n)
+
+    ctx = _RecordingContext(60, 3)
+    e = A.Embedder(g, A.EmbedderParams(dmap_init=False, asked_dim=3, seed=7), context=ctx)
+    e.embed()
+    assert "dmap_init" not in ctx.calls and "set_embedding" in ctx.calls
+    y_init = e.get_initial_embedding()
+    assert y_init.shape == (60, 3) and np.abs(y_init).max() <= 0.5      # uniform in [-0.5, 0.5]^d
