@@ -449,18 +449,22 @@ __global__ void __launch_bounds__(256) k_epoch_generic(EpochArgs a, unsigned lon
 
 // K4 (tiled) = two kernels per mini-epoch; one warp owns a tile of 32 consecutive nodes in both, warps are independent
 // (no block barrier), nothing is atomic on the layout.
-//  k_epoch_out  lane = node.  The row (<= KREG neighbours) is kept in registers for the rejection test and mirrored in
-//               shared memory ([lane][m], odd stride) for the edge pick; every node fires ceil(kappa - u) times
-//               (systematic sampling) so lanes stay converged; the 6 gathers of firing s+1 are in flight during the
-//               arithmetic of firing s.  Writes the node's position after its own firings to y_next.
-//  k_epoch_in   lane = in-edge.  The warp sweeps the tile's in-edge records (coalesced 16-byte streaming loads, two
-//               rounds of records and one round of source-row gathers in flight), replays the source's firing decision
-//               (Philox2x32 of (src, epoch)), turns every fired in-edge into the affine map y -> (1+A) y - A y_src with
-//               A evaluated at the owner's position after k_epoch_out, composes the maps of each owner with a
-//               segmented warp scan and lets the owner lane apply the composite: y_next <- alpha * y_next + beta.
-//  Splitting keeps both register footprints small (k_epoch_in: ~48 registers) so that enough warps are resident to
-//  hide the random-gather latency.
-template <int DP, int KREG>
+//  k_epoch_out  lane = node.  The node's row (KP padded {neighbour, cumulative probability} pairs, 16-byte vector loads,
+//               no shared memory) lives in registers: rejection test, edge pick (select chain) and probabilities are
+//               register-only.  Every node fires ceil(kappa - u) times (systematic sampling) so lanes stay converged;
+//               the 6 gathers of firings s+1 and s+2 are in flight during the arithmetic of firing s.  Writes the
+//               node's position after its own firings to y_next and (single rank) pushes the firing count of every
+//               fired edge into the byte map `fired` at the edge's position in the transposed index.
+//  k_epoch_in_flags (single rank)  lane = in-edge slot.  Reads the tile's slice of the byte map (coalesced), clears
+//               it, and only for the fired slots (15-30 % at the fine levels) loads the in-edge record and gathers the
+//               source row; compacted into a ring and applied by the dense stage below.
+//  k_epoch_in   (multi rank: sources live on other ranks)  lane = in-edge.  The warp sweeps the tile's in-edge records
+//               (coalesced 16-byte streaming loads) and REPLAYS the source's firing decision from (src, epoch, P_lo,
+//               P_hi) -- no communication -- then proceeds like the flags kernel.
+//  Dense stage: every fired in-edge is the affine map y -> (1+A) y - A y_src with A evaluated at the owner's position
+//               after k_epoch_out; the maps of each owner are composed with a segmented warp scan and the owner lane
+//               applies the composite: y_next <- alpha * y_next + beta.
+template <int DP, int KP>
 struct EpochTile {
 #ifndef ANNEMBED_WARPS_OUT
 #define ANNEMBED_WARPS_OUT 4
@@ -469,102 +473,104 @@ struct EpochTile {
 #define ANNEMBED_MINB_OUT 6
 #endif
     static constexpr int WARPS = DP <= 4 ? ANNEMBED_WARPS_OUT : (DP <= 16 ? 4 : 2);
-    static constexpr int MINB = DP <= 2 ? ANNEMBED_MINB_OUT : (DP <= 4 ? 4 : (DP <= 8 ? 2 : 1));  // blocks/SM the register budget aims at
-    static constexpr int RS = KREG + 1;                                          // odd row stride: conflict-free
-    static constexpr int PER_WARP = ((32 * RS * (4 + 4) + 15) / 16) * 16;        // col, cum
-    static constexpr int SMEM = WARPS * PER_WARP;
+    static constexpr int MINB = DP <= 2 ? (KP <= 8 ? ANNEMBED_MINB_OUT : 4) : (DP <= 4 ? 4 : (DP <= 8 ? 2 : 1));  // blocks/SM the register budget aims at
     static constexpr int MAX_FIRINGS = 126;                                      // per node and mini-epoch (byte counters)
 };
 
 // Number of edges of the row whose cumulative firing count is <= s, i.e. the edge firing s lands on.  The counts
-// ceil(kappa P_m - u) of the row are kept as bytes (<= 126; 0x7f pads the row) in registers: byte-wise
+// ceil(kappa P_m - u) of the row are kept as bytes (<= 126; 0x7f pads the last word) in registers: byte-wise
 // (0x80 | s) - ch never borrows and leaves bit 7 set exactly when ch <= s.
-template <int KREG>
-__device__ __forceinline__ int edge_of_firing(const uint32_t (&chb)[(KREG + 3) / 4], int s)
+template <int KP>
+__device__ __forceinline__ int edge_of_firing(const uint32_t (&chb)[(KP + 3) / 4], int s)
 {
     const uint32_t S = (uint32_t)s * 0x01010101u | 0x80808080u;
     int m = 0;
 #pragma unroll
-    for (int w = 0; w < (KREG + 3) / 4; w++) m += __popc((S - chb[w]) & 0x80808080u);
+    for (int w = 0; w < (KP + 3) / 4; w++) m += __popc((S - chb[w]) & 0x80808080u);
     return m;
 }
 
-template <int DP, bool HUB, int KREG>
-__global__ void __launch_bounds__(EpochTile<DP, KREG>::WARPS * 32, EpochTile<DP, KREG>::MINB)
+template <int DP, bool HUB, int KP>
+__global__ void __launch_bounds__(EpochTile<DP, KP>::WARPS * 32, EpochTile<DP, KP>::MINB)
 k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
 {
-    using TL = EpochTile<DP, KREG>;
-    constexpr int RS = TL::RS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using TL = EpochTile<DP, KP>;
+    static_assert(KP % 2 == 0, "rows are padded to an even number of entries (16-byte loads)");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t tile = (uint64_t)blockIdx.x * TL::WARPS + wib;
     const uint64_t n0 = (uint64_t)a.lo + tile * 32;
     if (n0 >= a.hi) return;                                    // whole warp leaves together
-    unsigned char *base = smem_raw + (size_t)wib * TL::PER_WARP;
-    uint32_t *s_col = reinterpret_cast<uint32_t *>(base);                       // [32][RS]
-    float *s_cum = reinterpret_cast<float *>(s_col + 32 * RS);                  // [32][RS]
 
     const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
     const uint32_t node = (uint32_t)n0 + lane;
     const bool valid = lane < nvalid;
     float y[DP], g[DP];
-    uint32_t rc[KREG];
-    uint32_t chb[(KREG + 3) / 4];
+    uint32_t rc[KP];
+    float cm[KP];
+    uint32_t chb[(KP + 3) / 4];
     float inv_s2 = 1.0f;
     int T = 0;
-    // ---------------- stage the tile's rows: coalesced global reads, [lane][m] layout with odd stride in smem
+    // ---------------- the node's row: KP/2 vector loads straight into registers
     {
-        int k;
-        if (a.regular_k) {
-            // every row has exactly regular_k entries: no row_ptr round trip, edge e of the tile belongs to lane e / k
-            const uint32_t kk = a.regular_k, inv_k = a.regular_k_inv;
-            const uint64_t R0 = n0 * kk;
-            const uint32_t tile_edges = (uint32_t)nvalid * kk;
-            k = valid ? (int)kk : 0;
-            for (uint32_t e = lane; e < tile_edges; e += 32) {
-                const uint32_t nl = (e * inv_k) >> 16, m = e - nl * kk;
-                s_col[nl * RS + m] = __ldcs(a.col + R0 + e);
-                s_cum[nl * RS + m] = __ldcs(a.cum + R0 + e);
-            }
-        } else {
-            const uint64_t rp = a.row_ptr[valid ? node : (uint32_t)n0];
-            uint64_t rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
-            if (lane == nvalid - 1) rp_next = a.row_ptr[node + 1];
-            k = valid ? (int)(rp_next - rp) : 0;
-            for (int m = 0; m < k; m++) {
-                s_col[lane * RS + m] = a.col[rp + m];
-                s_cum[lane * RS + m] = a.cum[rp + m];
-            }
+        const uint4 *rp = reinterpret_cast<const uint4 *>(a.rowpack + (size_t)(valid ? node : (uint32_t)n0) * KP);
+#pragma unroll
+        for (int h = 0; h < KP / 2; h++) {
+            const uint4 t = __ldg(rp + h);
+            rc[2 * h] = t.x; cm[2 * h] = __uint_as_float(t.y);
+            rc[2 * h + 1] = t.z; cm[2 * h + 1] = __uint_as_float(t.w);
         }
-        __syncwarp();
 #pragma unroll
-        for (int m = 0; m < KREG; m++) rc[m] = ANNEMBED_NO_NODE;
-#pragma unroll
-        for (int w = 0; w < (KREG + 3) / 4; w++) chb[w] = 0x7f7f7f7fu;
+        for (int w = 0; w < (KP + 3) / 4; w++) chb[w] = 0x7f7f7f7fu;
         if (valid) {
             load_row<DP>(a.y_snap, node, y);
             inv_s2 = __ldcs(a.inv_s2 + node);
             const float u = node_uniform(node, a.ukey);
+            int prev = 0;
 #pragma unroll
-            for (int m = 0; m < KREG; m++) {
-                if (m < k) {
-                    rc[m] = s_col[lane * RS + m];
-                    const int ch = cum_ceil(a.kappa, s_cum[lane * RS + m], u);
-                    chb[m >> 2] = (chb[m >> 2] & ~(0xffu << (8 * (m & 3)))) | ((uint32_t)ch << (8 * (m & 3)));
-                    T = ch;
-                }
+            for (int m = 0; m < KP; m++) {
+                const int ch = cum_ceil(a.kappa, cm[m], u);    // pads have cum == 1: ch == T, they never fire
+                chb[m >> 2] = (chb[m >> 2] & ~(0xffu << (8 * (m & 3)))) | ((uint32_t)ch << (8 * (m & 3)));
+                if (a.fired != nullptr && ch > prev)           // push the firing count to the destination's in-edge slot
+                    a.fired[__ldg(a.erank + (size_t)node * KP + m)] = (unsigned char)(ch - prev);
+                prev = ch;
             }
+            T = prev;
+        } else {
+#pragma unroll
+            for (int m = 0; m < KP; m++) rc[m] = ANNEMBED_NO_NODE;
         }
     }
     // ---------------- the node's own firings
     const uint32_t nkey = neg_stream_key<HUB>(a, node);
+    // range of the ids the rejection test can match (node, its neighbours): with the locality relabelling it is narrow,
+    // so that almost every negative is accepted by two comparisons
+    uint32_t id_lo = node, id_hi = node;
+#pragma unroll
+    for (int m = 0; m < KP; m++) {
+        const uint32_t v = rc[m] == ANNEMBED_NO_NODE ? node : rc[m];
+        id_lo = min(id_lo, v); id_hi = max(id_hi, v);
+    }
+    const uint32_t id_span = id_hi - id_lo;
     auto rejector = [&](uint32_t j) {
         return [&, j](uint32_t kk) -> bool {
-            bool r = (kk == node) | (kk == j);
+            (void)j;                                           // j is one of rc[]
+            bool r = false;
+            if (kk - id_lo <= id_span) {
+                r = (kk == node);
 #pragma unroll
-            for (int mm = 0; mm < KREG; mm++) r |= (kk == rc[mm]);
+                for (int mm = 0; mm < KP; mm++) r |= (kk == rc[mm]);
+            }
             return r;
         };
+    };
+    // edge m of the row: neighbour and probability interval by select chains (the row is in registers)
+    auto edge = [&](int m, uint32_t &j, float &P_lo, float &P_hi) {
+        j = rc[0]; P_hi = cm[0]; P_lo = 0.0f;
+#pragma unroll
+        for (int mm = 1; mm < KP; mm++) {
+            const bool t = m >= mm;
+            j = t ? rc[mm] : j; P_hi = t ? cm[mm] : P_hi; P_lo = t ? cm[mm - 1] : P_lo;
+        }
     };
     if constexpr (DP <= 4) {
         // Software pipelined over two register sets: the 6 row gathers (y_j + 5 negatives) of firings s+1 and s+2 are
@@ -611,11 +617,10 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
             w4n = __shfl_sync(0xffffffffu, bw, src);
         };
         auto prepare = [&](int s, Pre &P) {
-            const int m = edge_of_firing<KREG>(chb, s);        // < k because ch[k-1] == T > s
+            const int m = edge_of_firing<KP>(chb, s);          // < row length because ch[last] == T > s
             P.m = m;
-            const uint32_t j = s_col[lane * RS + m];
-            const float P_hi = s_cum[lane * RS + m];
-            const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
+            uint32_t j; float P_lo, P_hi;
+            edge(m, j, P_lo, P_hi);
             P.pe = F_SUB(P_hi, P_lo);
             load_row<DP>(a.y_snap, j, P.yj);
             uint32_t negs[ANNEMBED_NB_NEG];
@@ -664,11 +669,10 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         float yj[DP];
         Philox4 B;
         for (int s = 0; s < T; s++) {
-            const int m = edge_of_firing<KREG>(chb, s);
+            const int m = edge_of_firing<KP>(chb, s);
             if (m != m_prev) {
-                j = s_col[lane * RS + m];
-                const float P_hi = s_cum[lane * RS + m];
-                const float P_lo = m ? s_cum[lane * RS + m - 1] : 0.0f;
+                float P_lo, P_hi;
+                edge(m, j, P_lo, P_hi);
                 pe = F_SUB(P_hi, P_lo);
                 load_row<DP>(a.y_snap, j, yj);
                 m_prev = m;
@@ -693,64 +697,48 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
 #ifndef ANNEMBED_MINB_IN
 #define ANNEMBED_MINB_IN 10
 #endif
-// shared memory of one k_epoch_in warp: a ring of fired in-edges (SoA, 64 slots) and the running composite per owner
+// shared memory of one in-edge warp: a ring of fired in-edges (SoA, 64 slots) and the running composite per owner
 template <int DP>
 struct InTile {
     static constexpr int QCAP = 64;                              // >= 31 left over + 32 new entries
     static constexpr int WORDS = QCAP * (4 + DP) + 32 * (1 + DP);
     static constexpr int PER_WARP = WORDS * 4;
     static constexpr int SMEM = ANNEMBED_WARPS_IN * PER_WARP;
+    static constexpr int MINB = DP <= 2 ? ANNEMBED_MINB_IN : (DP <= 4 ? 8 : (DP <= 8 ? 6 : (DP <= 16 ? 4 : 2)));
 };
 
-template <int DP>
-__global__ void __launch_bounds__(ANNEMBED_WARPS_IN * 32, (DP <= 2 ? ANNEMBED_MINB_IN : (DP <= 4 ? 8 : (DP <= 8 ? 6 : (DP <= 16 ? 4 : 2)))))
-k_epoch_in(EpochArgs a)
-{
-    using TL = InTile<DP>;
-    constexpr int QCAP = TL::QCAP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t tile = (uint64_t)blockIdx.x * ANNEMBED_WARPS_IN + wib;
-    const uint64_t n0 = (uint64_t)a.lo + tile * 32;
-    if (n0 >= a.hi) return;
-    uint32_t *q_q = reinterpret_cast<uint32_t *>(smem_raw + (size_t)wib * TL::PER_WARP);   // in-edge index in the tile
-    uint32_t *q_c = q_q + QCAP;                                  // firings
-    float *q_pe = reinterpret_cast<float *>(q_c + QCAP);
-    float *q_is2 = q_pe + QCAP;
-    float *q_ys = q_is2 + QCAP;                                  // [DP][QCAP]
-    float *t_alpha = q_ys + DP * QCAP;                           // [32]      running composite of each owner:
-    float *t_beta = t_alpha + 32;                                // [DP][32]  y -> t_alpha * y + t_beta
-    const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
-    const uint32_t node = (uint32_t)n0 + lane;
-    const bool valid = lane < nvalid;
-    // the owner's position after its own firings (written by k_epoch_out): reference point of the coefficients and
-    // the value the composite map is applied to
-    float y[DP];
-#pragma unroll
-    for (int c = 0; c < DP; c++) y[c] = 0.0f;
-    if (valid) load_row<DP>(a.y_next, node, y);
-    const uint64_t my_q0 = a.in_ptr[(valid ? node : (uint32_t)n0) - a.lo];
-    const uint64_t Q1 = a.in_ptr[(uint32_t)n0 - a.lo + nvalid];
-    const uint64_t Q0 = __shfl_sync(0xffffffffu, my_q0, 0);
-    // first in-edge of this lane's node relative to the tile's first one (non-decreasing over the lanes): the owner
-    // of in-edge q is the last lane whose value is <= q
-    const uint32_t rel_lo = valid ? (uint32_t)(my_q0 - Q0) : 0xffffffffu;
-    const uint32_t n_in = (uint32_t)(Q1 - Q0);                 // in-edges of the tile
-    if (n_in == 0) {                                           // nothing to apply: y_next already holds the result
-        if (valid)
-            for (uint32_t pr = 0; pr < a.n_peers; pr++) store_row<DP>(a.peer_next[pr], node, y);
-        return;
+// Per-warp state of the in-edge kernels (both variants): the tile's owners, the ring of fired in-edges and the dense stage.
+template <int DP, bool FLAGS>
+struct InWarp {
+    static constexpr int QCAP = InTile<DP>::QCAP;
+    const EpochArgs &a;
+    int lane;
+    uint32_t *q_q, *q_c;           // in-edge index in the tile, firings
+    float *q_pe, *q_is2, *q_ys;    // edge probability, 1/s_src^2 (replay variant only), source row [DP][QCAP]
+    float *t_alpha, *t_beta;       // running composite of each owner: y -> t_alpha * y + t_beta ([32], [DP][32])
+    float y[DP];                   // the owner's position after its own firings (written by k_epoch_out)
+    uint32_t rel_lo;               // first in-edge of this lane's node relative to the tile's first one
+    const uint4 *rec0;             // record of the tile's first in-edge
+    uint32_t q_head = 0;           // ring start (warp-uniform)
+    int q_n = 0;                   // queued entries (warp-uniform)
+
+    __device__ __forceinline__ InWarp(const EpochArgs &a_, unsigned char *smem, int lane_) : a(a_), lane(lane_)
+    {
+        q_q = reinterpret_cast<uint32_t *>(smem);
+        q_c = q_q + QCAP;
+        q_pe = reinterpret_cast<float *>(q_c + QCAP);
+        q_is2 = q_pe + QCAP;
+        q_ys = q_is2 + QCAP;
+        t_alpha = q_ys + DP * QCAP;
+        t_beta = t_alpha + 32;
     }
-    t_alpha[lane] = 1.0f;
-#pragma unroll
-    for (int c = 0; c < DP; c++) t_beta[c * 32 + lane] = 0.0f;
-    const uint4 *recp = a.in_rec + (Q0 - a.in_base) + lane;
 
     // ---- dense stage: `cnt` queued in-edges starting at ring position `head`, lane = queue entry.  Each becomes the
     // affine map y -> alpha y + beta of its owner (coefficient at the owner's position after k_epoch_out); the maps of
     // one owner are adjacent (the sweep is in in-edge order) and are composed by a segmented scan; the last lane of a
     // segment folds the composite into the owner's running composite.
-    auto dense = [&](uint32_t head, int cnt) {
+    __device__ __forceinline__ void dense(uint32_t head, int cnt)
+    {
         const bool act = lane < cnt;
         const uint32_t e = (head + (uint32_t)lane) & (QCAP - 1);
         uint32_t own = 32u + (uint32_t)lane;                   // inactive lanes: a segment of their own
@@ -764,7 +752,12 @@ k_epoch_in(EpochArgs a)
         uint32_t q = 0;
         if (act) {
             q = q_q[e]; c = (int)q_c[e];
-            pe = q_pe[e]; is2 = q_is2[e];
+            if constexpr (FLAGS) {                             // probability interval and source scale from the record
+                const uint4 r = __ldg(rec0 + q);
+                pe = F_SUB(__uint_as_float(r.z), __uint_as_float(r.y)); is2 = __uint_as_float(r.w);
+            } else {
+                pe = q_pe[e]; is2 = q_is2[e];
+            }
 #pragma unroll
             for (int cc = 0; cc < DP; cc++) ys[cc] = q_ys[cc * QCAP + e];
         }
@@ -811,7 +804,145 @@ k_epoch_in(EpochArgs a)
             t_alpha[own] = F_MUL(alpha, at);
         }
         __syncwarp();
-    };
+    }
+
+    // the lanes with c > 0 append their in-edge (index q in the tile) to the ring, in lane order; a full warp of queued
+    // entries is applied at once
+    __device__ __forceinline__ void push(int c, uint32_t q, float pe, float is2, const float (&ys)[DP])
+    {
+        const unsigned fired = __ballot_sync(0xffffffffu, c > 0);
+        if (fired == 0u) return;                               // warp-uniform
+        if (c > 0) {
+            const uint32_t e = (q_head + (uint32_t)q_n + (uint32_t)__popc(fired & ((1u << lane) - 1u))) & (QCAP - 1);
+            q_q[e] = q; q_c[e] = (uint32_t)c;
+            if constexpr (!FLAGS) { q_pe[e] = pe; q_is2[e] = is2; }
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) q_ys[cc * QCAP + e] = ys[cc];
+        }
+        q_n += __popc(fired);
+        __syncwarp();
+        if (q_n >= 32) {
+            dense(q_head, 32);
+            q_head = (q_head + 32u) & (QCAP - 1);
+            q_n -= 32;
+        }
+    }
+
+    // apply the owners' composites and publish the rows (own replica, then the other ranks' replicas)
+    __device__ __forceinline__ void finish(uint32_t node, bool valid)
+    {
+        if (q_n > 0) dense(q_head, q_n);
+        if (valid) {
+            const float at = t_alpha[lane];
+#pragma unroll
+            for (int c = 0; c < DP; c++) y[c] = F_FMA(at, y[c], t_beta[c * 32 + lane]);
+            store_row<DP>(a.y_next, node, y);
+            // fused exchange: the owner writes its row straight into every peer's replica (NVLink P2P stores, coalesced
+            // 32 rows per warp; ONE store when peer_next[0] is a multicast mapping) while other tiles are still computing
+            for (uint32_t pr = 0; pr < a.n_peers; pr++) store_row<DP>(a.peer_next[pr], node, y);
+        }
+    }
+};
+
+// common prologue of the in-edge kernels.  Returns false when the tile has no in-edge (rows already final).
+template <int DP, bool FLAGS>
+__device__ __forceinline__ bool in_tile_begin(const EpochArgs &a, InWarp<DP, FLAGS> &W, uint64_t n0, int nvalid, bool valid,
+                                              uint32_t node, uint64_t &Q0, uint32_t &n_in)
+{
+#pragma unroll
+    for (int c = 0; c < DP; c++) W.y[c] = 0.0f;
+    if (valid) load_row<DP>(a.y_next, node, W.y);
+    const uint64_t my_q0 = a.in_ptr[(valid ? node : (uint32_t)n0) - a.lo];
+    const uint64_t Q1 = a.in_ptr[(uint32_t)n0 - a.lo + nvalid];
+    Q0 = __shfl_sync(0xffffffffu, my_q0, 0);
+    // first in-edge of this lane's node relative to the tile's first one (non-decreasing over the lanes): the owner
+    // of in-edge q is the last lane whose value is <= q
+    W.rel_lo = valid ? (uint32_t)(my_q0 - Q0) : 0xffffffffu;
+    n_in = (uint32_t)(Q1 - Q0);                                // in-edges of the tile
+    W.rec0 = a.in_rec + (Q0 - a.in_base);
+    if (n_in == 0) {                                           // nothing to apply: y_next already holds the result
+        if (valid)
+            for (uint32_t pr = 0; pr < a.n_peers; pr++) store_row<DP>(a.peer_next[pr], node, W.y);
+        return false;
+    }
+    W.t_alpha[W.lane] = 1.0f;
+#pragma unroll
+    for (int c = 0; c < DP; c++) W.t_beta[c * 32 + W.lane] = 0.0f;
+    return true;
+}
+
+// ---- single rank: the firing counts were pushed by k_epoch_out into the byte map ----------------------------------
+template <int DP>
+__global__ void __launch_bounds__(ANNEMBED_WARPS_IN * 32, InTile<DP>::MINB)
+k_epoch_in_flags(EpochArgs a)
+{
+    using TL = InTile<DP>;
+    constexpr int RC = DP <= 2 ? 8 : (DP <= 4 ? 4 : (DP <= 8 ? 2 : 1));     // rounds of 32 slots in flight per chunk
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t)blockIdx.x * ANNEMBED_WARPS_IN + wib;
+    const uint64_t n0 = (uint64_t)a.lo + tile * 32;
+    if (n0 >= a.hi) return;
+    const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
+    const uint32_t node = (uint32_t)n0 + lane;
+    const bool valid = lane < nvalid;
+    InWarp<DP, true> W(a, smem_raw + (size_t)wib * TL::PER_WARP, lane);
+    uint64_t Q0; uint32_t n_in;
+    if (!in_tile_begin<DP, true>(a, W, n0, nvalid, valid, node, Q0, n_in)) return;
+    unsigned char *fb = a.fired + (Q0 - a.in_base);
+    __syncwarp();
+    for (uint32_t base = 0; base < n_in; base += 32u * RC) {
+        const uint32_t cnt = min(32u * RC, n_in - base);
+        uint32_t fl[RC], src[RC];
+        float ys[RC][DP];
+        // firing counts of RC x 32 slots (coalesced byte loads), cleared for the next mini-epoch
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+            const uint32_t i = 32u * r + lane;
+            fl[r] = i < cnt ? (uint32_t)fb[base + i] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < RC; r++)
+            if (fl[r]) fb[base + 32u * r + lane] = 0;
+        // source of the fired slots, then its row: all RC rounds in flight together
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+            src[r] = 0u;
+            if (fl[r]) src[r] = __ldg(reinterpret_cast<const uint32_t *>(W.rec0 + base + 32u * r + lane));
+        }
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+#pragma unroll
+            for (int cc = 0; cc < DP; cc++) ys[r][cc] = 0.0f;
+            if (fl[r]) load_row<DP>(a.y_snap, src[r], ys[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+            if (32u * r >= cnt) break;                         // warp-uniform
+            W.push((int)fl[r], base + 32u * r + lane, 0.0f, 0.0f, ys[r]);
+        }
+    }
+    W.finish(node, valid);
+}
+
+// ---- multi rank: the sources' decisions are replayed from the in-edge records ----------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(ANNEMBED_WARPS_IN * 32, InTile<DP>::MINB)
+k_epoch_in(EpochArgs a)
+{
+    using TL = InTile<DP>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t)blockIdx.x * ANNEMBED_WARPS_IN + wib;
+    const uint64_t n0 = (uint64_t)a.lo + tile * 32;
+    if (n0 >= a.hi) return;
+    const int nvalid = (int)min((uint64_t)32, (uint64_t)a.hi - n0);
+    const uint32_t node = (uint32_t)n0 + lane;
+    const bool valid = lane < nvalid;
+    InWarp<DP, false> W(a, smem_raw + (size_t)wib * TL::PER_WARP, lane);
+    uint64_t Q0; uint32_t n_in;
+    if (!in_tile_begin<DP, false>(a, W, n0, nvalid, valid, node, Q0, n_in)) return;
+    const uint4 *recp = W.rec0 + lane;
 
     // ---- sparse stage: lane = in-edge record.  Replays the source's firing decision; fired in-edges (about
     // kappa * p_e of them) are compacted into the ring, the source-row gather of round r+1 and the records of round
@@ -830,25 +961,6 @@ k_epoch_in(EpochArgs a)
         P.pe = F_SUB(as_float(rec.z), as_float(rec.y)); P.is2 = as_float(rec.w);
         if (P.c > 0) load_row<DP>(a.y_snap, rec.x, P.ys);
     };
-    uint32_t q_head = 0;                                       // ring start (warp-uniform)
-    int q_n = 0;                                               // queued entries (warp-uniform)
-    auto consume = [&](const Prep &P, uint32_t base_q) {
-        const unsigned fired = __ballot_sync(0xffffffffu, P.c > 0);
-        if (P.c > 0) {
-            const uint32_t e = (q_head + (uint32_t)q_n + (uint32_t)__popc(fired & ((1u << lane) - 1u))) & (QCAP - 1);
-            q_q[e] = base_q + (uint32_t)lane; q_c[e] = (uint32_t)P.c;
-            q_pe[e] = P.pe; q_is2[e] = P.is2;
-#pragma unroll
-            for (int cc = 0; cc < DP; cc++) q_ys[cc * QCAP + e] = P.ys[cc];
-        }
-        q_n += __popc(fired);
-        __syncwarp();
-        if (q_n >= 32) {
-            dense(q_head, 32);
-            q_head = (q_head + 32u) & (QCAP - 1);
-            q_n -= 32;
-        }
-    };
     Prep PA, PB;
     PA.c = PB.c = 0; PA.pe = PB.pe = PA.is2 = PB.is2 = 0.0f;
 #pragma unroll
@@ -865,24 +977,15 @@ k_epoch_in(EpochArgs a)
         recp2 += 32; left -= 32;                               // `left` = in-edges from this lane's slot two rounds ahead
         if (left > 0) recA = __ldcs(recp2);
         prepare(recB, left + 32 > 0, PB);
-        consume(PA, base_q);
+        W.push(PA.c, base_q + (uint32_t)lane, PA.pe, PA.is2, PA.ys);
         if (base_q + 32 >= n_in) break;
         // odd round: PB is prepared, recA holds the records of the next round
         recp2 += 32; left -= 32;
         if (left > 0) recB = __ldcs(recp2);
         prepare(recA, left + 32 > 0, PA);
-        consume(PB, base_q + 32);
+        W.push(PB.c, base_q + 32 + (uint32_t)lane, PB.pe, PB.is2, PB.ys);
     }
-    if (q_n > 0) dense(q_head, q_n);
-    if (valid) {
-        const float at = t_alpha[lane];
-#pragma unroll
-        for (int c = 0; c < DP; c++) y[c] = F_FMA(at, y[c], t_beta[c * 32 + lane]);
-        store_row<DP>(a.y_next, node, y);
-        // fused exchange: the owner writes its row straight into every peer's replica (NVLink P2P stores, coalesced
-        // 32 rows per warp) while other tiles are still computing; a tiny all-reduce closes the mini-epoch
-        for (uint32_t pr = 0; pr < a.n_peers; pr++) store_row<DP>(a.peer_next[pr], node, y);
-    }
+    W.finish(node, valid);
 }
 
 // K5: embedder.rs:1127-1163 + cauchy_edge_weight :1322-1345, fp64 like the reference
@@ -1827,23 +1930,19 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
 }
 
 // Mini-epochs per reference batch.  What governs the fidelity of the bulk-synchronous loop is how much of a batch is
-// applied against one snapshot, i.e. samples per edge per mini-epoch (nb_sampling_by_edge / M), not the node degree:
-// at ~0.3 samples per edge per mini-epoch (M = 34 for the default 10 samples per edge) the layout statistics are
-// within 1 % of the serial reference's for kNN 6 and 10, with and without the hubness sampler
-// (tests/studies/gpu_quality_study.py); they converge monotonically to the reference's as M grows.
+// applied against one snapshot, i.e. samples per edge per mini-epoch (nb_sampling_by_edge / M), not the node degree.
+// At 0.15 samples per edge per mini-epoch (M = 67 for the default 10 samples per edge) the layout statistics of the
+// BASELINE.json configs (70k MNIST / Fashion shapes, k = 10; 1M Higgs shape from a random start, k = 6, with and
+// without hubness; d = 15) are within 1 % of the serial reference's (tests/test_gpu_fidelity.py against
+// tests/golden/fidelity_*.json); at the 0.3 used in round 1 the Higgs-shape case was 4-8 % off
+// (tests/studies/fidelity_configs.py).  The statistics converge monotonically to the reference's as M grows.
 #ifndef ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH
-#define ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH 0.3
+#define ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH 0.15
 #endif
-static double study_env(const char *name, double dflt)      // knobs of the design studies; not part of the ABI
-{
-    const char *v = getenv(name);
-    return (v && *v) ? atof(v) : dflt;
-}
 static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
 {
     if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;
-    const double spe = study_env("ANNEMBED_STUDY_SAMPLES_PER_EDGE", ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH);
-    return (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge / spe));
+    return (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge / ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH));
 }
 // Default (mini_epochs_per_batch == 0) schedule: graded.  The final statistics are set by the last, small-step batches
 // (tests/studies/adaptive_kappa_study.py: coarse-early / fine-late schedules land as close to the serial oracle as the
@@ -1854,9 +1953,8 @@ static uint32_t mini_epochs_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter
     const uint32_t base = eff_mini_epochs(ctx);
     if (ctx->prm.mini_epochs_per_batch) return base;
     const uint32_t nb = ctx->prm.nb_grad_batch;
-    const uint32_t d1 = (uint32_t)study_env("ANNEMBED_STUDY_DIV1", 4.0), d2 = (uint32_t)study_env("ANNEMBED_STUDY_DIV2", 2.0);
-    const uint32_t div = (3 * iter <= nb) ? d1 : ((3 * iter <= 2 * nb) ? d2 : 1u);
-    return std::max(1u, (base + div - 1) / std::max(div, 1u));
+    const uint32_t div = (3 * iter <= nb) ? 4u : ((3 * iter <= 2 * nb) ? 2u : 1u);
+    return std::max(1u, (base + div - 1) / div);
 }
 // global index of the first mini-epoch of batch `iter` (counter word of the Philox streams)
 static uint32_t first_epoch_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter)

@@ -237,6 +237,9 @@ __host__ __device__ __forceinline__ void fixed_sample(float *Y, uint32_t i, uint
 }
 
 // ---- arguments of one mini-epoch ------------------------------------------------------------------------------
+// Every index below lives in the INTERNAL node numbering of the optimizer context (locality relabelling of the graph,
+// DESIGN.md 4): the layout buffers, rows, transposed index and alias table are all permuted consistently, the
+// permutation is undone at the C ABI.
 struct EpochArgs {
     const float *__restrict__ y_snap;   // layout at the start of the mini-epoch (replicated, n x DP)
     float *__restrict__ y_next;         // layout after it; only rows [lo,hi) are written here
@@ -245,16 +248,19 @@ struct EpochArgs {
     const float *__restrict__ p;
     const float *__restrict__ inv_s2;   // 1 / embedded_scale^2 per node
     const uint64_t *__restrict__ in_ptr; // transposed index of the owned nodes: in_ptr[node-lo] .. in_ptr[node-lo+1]
-    const uint4 *__restrict__ in_rec;   // {src node, edge id, bits(p_e), bits(inv_s2[src])}, entry q at in_rec[q - in_base]
+    const uint4 *__restrict__ in_rec;   // {src node, bits(P_lo), bits(P_hi), bits(inv_s2[src])}, entry q at in_rec[q - in_base]
     uint64_t in_base;
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
     const float *__restrict__ cum;       // inclusive cumulative probability along each row (last entry exactly 1)
+    // tiled kernels: rows padded to KP entries {col, bits(cum)} (pads: {NO_NODE, 1.0f}), 16-byte aligned per node
+    const uint2 *__restrict__ rowpack;
+    const uint32_t *__restrict__ erank;  // [n][KP]: position q of the out-edge in the transposed index
+    unsigned char *__restrict__ fired;   // [E]: firing counts pushed by k_epoch_out, consumed (and cleared) by k_epoch_in_flags;
+                                         // null: the in-edge kernel replays the sources' decisions instead (multi-rank)
     uint32_t k2;                         // Philox2x32 key of the per-mini-epoch key below
     uint32_t ukey;                       // epoch_ukey(epoch, k2): key of the per-node uniforms of this mini-epoch
-    uint32_t regular_k;                  // >0: every row has exactly this many entries (coalesced row staging)
-    uint32_t regular_k_inv;              // ceil(65536 / regular_k): e / k == (e * inv) >> 16 for e < 32 * 16
-    uint32_t n_peers;                    // fused exchange: replicas of y_next on the other ranks (peer memory over NVLink)
-    float *peer_next[7];
+    uint32_t n_peers;                    // fused exchange: replicas of y_next on the other ranks (peer memory over NVLink),
+    float *peer_next[7];                 // or ONE multicast mapping of all replicas (NVSwitch replicates the store)
     uint32_t n, lo, hi;
     uint32_t epoch, k0, k1;
     float kappa;                        // expected firings of edge e in this mini-epoch = kappa * p_e

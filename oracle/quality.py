@@ -12,8 +12,24 @@ import numpy as np
 from . import oracle
 
 
-def quality_stats(row_ptr, col, y, nbng):
-    from scipy.spatial import cKDTree
+def kth_neighbour_bruteforce(y, nbng, device=None, chunk=2048):
+    """index of the nbng-th nearest embedded neighbour (self excluded) by exact blocked search (any dimension)."""
+    import torch
+
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    yt = torch.as_tensor(np.ascontiguousarray(y, np.float32), device=dev).double()
+    sq = (yt * yt).sum(1)
+    out = torch.empty(yt.shape[0], dtype=torch.int64, device=dev)
+    for s in range(0, yt.shape[0], chunk):
+        e = min(yt.shape[0], s + chunk)
+        d2 = sq[s:e, None] + sq[None, :] - 2.0 * (yt[s:e] @ yt.T)
+        d2[torch.arange(e - s, device=dev), torch.arange(s, e, device=dev)] = -1.0      # self first
+        out[s:e] = torch.topk(d2, nbng + 1, dim=1, largest=False, sorted=True)[1][:, nbng]
+    return out.cpu().numpy()
+
+
+def quality_stats(row_ptr, col, y, nbng, kth_index=None):
+    """kth_index: optional precomputed index of every node's nbng-th nearest embedded neighbour (else cKDTree)."""
 
     row_ptr = np.asarray(row_ptr, np.uint64)
     y = np.ascontiguousarray(y, np.float32)
@@ -21,11 +37,14 @@ def quality_stats(row_ptr, col, y, nbng):
     # embedder.rs:478-522
     t = oracle.transformed_kgraph(row_ptr, col, y).astype(np.float64)
     # embedder.rs:527-554 + kgraph.rs:167-183: per node, length of the longest of its nbng embedded kNN edges
-    tree = cKDTree(y.astype(np.float64))
-    _, ii = tree.query(y.astype(np.float64), k=nbng + 1, workers=-1)
+    if kth_index is None:
+        from scipy.spatial import cKDTree
+        tree = cKDTree(y.astype(np.float64))
+        _, ii = tree.query(y.astype(np.float64), k=nbng + 1, workers=-1)
+        kth_index = ii[:, nbng]
     # the radius in the same fp32 arithmetic as the transformed edges (the reference compares f32 distances with `<=`,
     # embedder.rs:659: an original neighbour that IS the nbng-th embedded neighbour counts as a match)
-    diff = y - y[ii[:, nbng]]
+    diff = y - y[kth_index]
     acc = np.zeros(n, np.float32)
     for c in range(y.shape[1]):
         acc = (acc + diff[:, c] * diff[:, c]).astype(np.float32)

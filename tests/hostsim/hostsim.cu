@@ -105,11 +105,12 @@ extern "C" int64_t hostsim_optimize(uint64_t n, uint32_t d, const uint64_t *row_
         const double gs = grad_step0 * (1.0 - (double)iter / (double)nb_batch);
         for (uint32_t m = 0; m < M; m++) {
             EpochArgs a;
+            memset(&a, 0, sizeof a);
             a.y_snap = Y[cur].data(); a.y_next = Y[cur ^ 1].data();
             a.row_ptr = row_ptr; a.col = col; a.p = p; a.inv_s2 = h.inv_s2.data();
             a.in_ptr = h.in_ptr.data(); a.in_rec = h.in_rec.data(); a.in_base = 0;
             a.neg_alias = (const uint2 *)neg_alias;
-            a.regular_k = 0; a.regular_k_inv = 0; a.cum = h.cum.data(); a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+            a.cum = h.cum.data(); a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
             a.n = (uint32_t)n; a.lo = 0; a.hi = (uint32_t)n;
             a.epoch = (iter - 1) * M + m; a.ukey = epoch_ukey(a.epoch, a.k2); a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
             a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);

@@ -68,13 +68,16 @@ def csr_from_knn(idx: np.ndarray, dist: np.ndarray) -> tuple[np.ndarray, np.ndar
 
 
 def blocked_knn_graph(n: int, dim: int, k: int, seed: int = 0, block: int = 4096, dup_frac: float = 0.005,
-                      device: str | None = None, shuffle: bool = True) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+                      device: str | None = None, shuffle: bool = True, host_rng: bool = False) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """C3/C4 'Higgs shape': n x dim standardised mixture, kNN restricted to blocks of `block` points of the same
     sub-cluster (cluster-blocked exact kNN), plus dup_frac exact duplicate rows (zero distances,
     kdumap.rs:163-170).  Node ids are shuffled (HNSW insertion order carries no locality) unless shuffle=False.
+    host_rng=True draws every random number with the CPU generator (the same points and permutation on any device:
+    the fidelity cases, tests/fidelity_cases.py); the default draws on `device` (bench: 11M points in a second).
     Returns CSR (row_ptr u64, col u32, dist f32)."""
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
-    g = torch.Generator(device=dev)
+    gdev = torch.device("cpu") if host_rng else dev
+    g = torch.Generator(device=gdev)
     g.manual_seed(seed)
     nblk = (n + block - 1) // block
     idx_all = torch.empty((n, k), dtype=torch.int64, device=dev)
@@ -86,8 +89,8 @@ def blocked_knn_graph(n: int, dim: int, k: int, seed: int = 0, block: int = 4096
         m = e - s
         nb = b1 - b0
         pad = nb * block - m
-        centre = torch.randn((nb, 1, dim), device=dev, generator=g) * 1.5
-        x = torch.randn((nb, block, dim), device=dev, generator=g) + centre
+        centre = torch.randn((nb, 1, dim), device=gdev, generator=g).to(dev) * 1.5
+        x = torch.randn((nb, block, dim), device=gdev, generator=g).to(dev) + centre
         ndup = int(block * dup_frac)
         if ndup > 0:
             x[:, block - ndup:, :] = x[:, :ndup, :]      # exact duplicates inside each block
@@ -107,7 +110,7 @@ def blocked_knn_graph(n: int, dim: int, k: int, seed: int = 0, block: int = 4096
         d_all, order = torch.sort(d_all, dim=1, stable=True)
         idx_all = torch.gather(idx_all, 1, order)
     if shuffle:
-        perm = torch.randperm(n, device=dev, generator=g)            # new id of old node i is perm[i]
+        perm = torch.randperm(n, device=gdev, generator=g).to(dev)   # new id of old node i is perm[i]
         inv = torch.empty_like(perm)
         inv[perm] = torch.arange(n, device=dev)
         idx_all = perm[idx_all][inv]
@@ -127,10 +130,12 @@ def set_data_box(y: np.ndarray, box_size: float = 10.0) -> np.ndarray:
 def pca_init(x: np.ndarray, d: int, box_size: float = 10.0) -> np.ndarray:
     """A spectral stand-in for the diffusion-map initial layout (embedder.rs:308-345): top-d principal
     components, boxed like the reference boxes its dmap layout (`set_data_box(.., 10.)`, embedder.rs:345)."""
-    xt = torch.as_tensor(x, dtype=torch.float32)
-    xt = xt - xt.mean(0, keepdim=True)
-    _, _, v = torch.pca_lowrank(xt, q=max(d + 2, 6), center=False, niter=4)
-    return set_data_box((xt @ v[:, :d]).numpy(), box_size)
+    xc = np.asarray(x, np.float64)
+    xc = xc - xc.mean(0, keepdims=True)
+    w, v = np.linalg.eigh(xc.T @ xc)                       # deterministic (no randomized range finder)
+    v = v[:, ::-1][:, :d]
+    v = v * np.sign(v[np.abs(v).argmax(0), np.arange(d)])  # fixed sign: largest component positive
+    return set_data_box((xc @ v).astype(np.float32), box_size)
 
 
 def random_init(n: int, d: int, seed: int = 0, size: float = 1.0) -> np.ndarray:
