@@ -105,8 +105,20 @@ struct annembed_cuda_ctx {
     DevBuf<uint64_t> row_ptr;
     DevBuf<uint32_t> col;
     DevBuf<float> dist, rho;
-    DevBuf<float> scale, proba, cum;
+    DevBuf<float> scale, proba;
     bool have_graph = false, have_weights = false, have_build = false, have_embedding = false, have_alias = false;
+
+    // internal node numbering of the optimizer (locality relabelling, built once per graph by ensure_struct)
+    DevBuf<uint32_t> new_of_old, old_of_new;
+    DevBuf<uint64_t> row_ptr2;      // CSR of the relabelled graph
+    DevBuf<uint32_t> col2;
+    DevBuf<float> cum;              // inclusive cumulative row probability, relabelled edge order
+    DevBuf<float> inv_s2n;          // 1 / embedded_scale^2, relabelled node order
+    DevBuf<uint2> rowpack;          // [n][KP] {col, bits(cum)} rows of the tiled kernels
+    DevBuf<uint32_t> erank;         // [n][KP] position of every out-edge in the transposed index (single rank)
+    DevBuf<unsigned char> fired;    // [E] firing counts pushed by k_epoch_out (single rank)
+    int KP = 0;                     // padded row length of the tiled kernels (0: generic kernel only)
+    bool alias_dirty = false;
 
     // optimizer context (≙ EntropyOptim, embedder.rs:936-951)
     DevBuf<float> emb_scale, inv_s2;
@@ -116,8 +128,9 @@ struct annembed_cuda_ctx {
     uint64_t in_cnt = 0;
     bool have_struct = false;
     uint64_t in_base = 0;
-    DevBuf<uint2> neg_alias;
-    DevBuf<float> y[2], y0;
+    DevBuf<uint2> neg_alias_old, neg_alias;   // alias table in the caller's / in the internal numbering
+    DevBuf<float> yapi, y0;        // current and initial layout in the caller's node order
+    DevBuf<float> y[2];            // double-buffered layout of the epoch loop, internal node order (exported to the peers)
     int cur = 0;
     int DP = 2;
 
@@ -360,6 +373,118 @@ __global__ void k_in_rec(uint64_t cnt, const uint32_t *__restrict__ in_src, cons
     const uint32_t src = in_src[q], e = in_eid[q];
     const float P_lo = (row_ptr[src] == e) ? 0.0f : cum[e - 1];
     rec[q] = make_uint4(src, __float_as_uint(P_lo), __float_as_uint(cum[e]), __float_as_uint(inv_s2[src]));
+}
+
+// ---- locality relabelling of the nodes (internal numbering of the optimizer context) -------------------------------
+// Min-label propagation over the symmetrised graph: after r rounds L_r(i) is the smallest random label within r hops of
+// i, so equal labels mark graph-local cells whose size grows with r.  Sorting the nodes by (L_8, L_4, L_2, L_1) nests
+// the cells: neighbours in the graph get nearby ids, which turns the y_j / source-row gathers, the in-edge
+// records and the firing-count pushes of a tile into accesses to a few nearby cache lines.  Deterministic (min is
+// order-independent); depends on the graph only.
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x21F0AAADu; x ^= x >> 15; x *= 0x735A2D97u; x ^= x >> 15;
+    return x;
+}
+__global__ void k_lp_init(uint64_t n, uint32_t *__restrict__ L)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) L[i] = mix32((uint32_t)i * 0x9E3779B1u + 0x7F4A7C15u);
+}
+// Ln (initialised to L) <- min over the closed neighbourhood, both edge directions
+__global__ void k_lp_round(uint64_t n, const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                           const uint32_t *__restrict__ L, uint32_t *__restrict__ Ln)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t mine = L[i];
+    uint32_t m = mine;
+    for (uint64_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+        const uint32_t j = col[e], lj = L[j];
+        m = min(m, lj);
+        if (mine < lj) atomicMin(Ln + j, mine);
+    }
+    if (m < mine) atomicMin(Ln + i, m);
+}
+__global__ void k_gather_u32(uint64_t n, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ src, uint32_t *__restrict__ dst)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_gather_f32(uint64_t n, const uint32_t *__restrict__ idx, const float *__restrict__ src, float *__restrict__ dst)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_invert_perm(uint64_t n, const uint32_t *__restrict__ order, uint32_t *__restrict__ inv)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[order[i]] = (uint32_t)i;
+}
+// degrees of the relabelled rows (entry n = 0 so that an exclusive scan over n+1 entries yields row_ptr2)
+__global__ void k_relabel_degrees(uint64_t n, const uint32_t *__restrict__ old_of_new, const uint64_t *__restrict__ row_ptr,
+                                  uint64_t *__restrict__ deg2)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { deg2[n] = 0; return; }
+    const uint32_t o = old_of_new[i];
+    deg2[i] = row_ptr[o + 1] - row_ptr[o];
+}
+__global__ void k_relabel_rows(uint64_t n, const uint32_t *__restrict__ old_of_new, const uint32_t *__restrict__ new_of_old,
+                               const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                               const uint64_t *__restrict__ row_ptr2, uint32_t *__restrict__ col2)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t o = old_of_new[i];
+    const uint64_t r0 = row_ptr[o], k = row_ptr[o + 1] - r0, w0 = row_ptr2[i];
+    for (uint64_t m = 0; m < k; m++) col2[w0 + m] = new_of_old[col[r0 + m]];
+}
+// rows of the tiled kernels: KP entries {neighbour, bits(cumulative probability)} per node, pads {NO_NODE, 1.0f}
+__global__ void k_rowpack(uint64_t n, int KP, const uint64_t *__restrict__ row_ptr2, const uint32_t *__restrict__ col2,
+                          const float *__restrict__ cum, uint2 *__restrict__ rowpack)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (uint64_t)KP) return;
+    const uint64_t i = t / KP; const uint64_t m = t % KP;
+    const uint64_t r0 = row_ptr2[i], k = row_ptr2[i + 1] - r0;
+    rowpack[t] = m < k ? make_uint2(col2[r0 + m], __float_as_uint(cum[r0 + m])) : make_uint2(ANNEMBED_NO_NODE, __float_as_uint(1.0f));
+}
+// erank[src * KP + m] = position q of out-edge m of src in the transposed index
+__global__ void k_erank(uint64_t cnt, uint64_t q_lo, int KP, const uint32_t *__restrict__ in_src, const uint32_t *__restrict__ in_eid,
+                        const uint64_t *__restrict__ row_ptr2, uint32_t *__restrict__ erank)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= cnt) return;
+    const uint32_t src = in_src[q];
+    erank[(uint64_t)src * KP + (in_eid[q] - row_ptr2[src])] = (uint32_t)(q_lo + q);
+}
+// alias table of the hubness sampler carried into the internal numbering (slots and alias targets)
+__global__ void k_relabel_alias(uint64_t n, const uint32_t *__restrict__ new_of_old, const uint2 *__restrict__ tab_old,
+                                uint2 *__restrict__ tab_new)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 t = tab_old[i];
+    tab_new[new_of_old[i]] = make_uint2(t.x, new_of_old[t.y]);
+}
+// layout rows between the caller's node order and the internal one
+__global__ void k_rows_to_internal(uint64_t n, int DP, const uint32_t *__restrict__ old_of_new, const float *__restrict__ in,
+                                   float *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (uint64_t)DP) return;
+    const uint64_t i = t / DP; const int c = (int)(t % DP);
+    out[t] = in[(uint64_t)old_of_new[i] * DP + c];
+}
+__global__ void k_rows_from_internal(uint64_t n, int DP, const uint32_t *__restrict__ old_of_new, const float *__restrict__ in,
+                                     float *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (uint64_t)DP) return;
+    const uint64_t i = t / DP; const int c = (int)(t % DP);
+    out[(uint64_t)old_of_new[i] * DP + c] = in[t];
 }
 
 __global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint32_t *__restrict__ out)
@@ -1050,15 +1175,18 @@ __global__ void k_debug_draws(EpochArgs a, uint32_t *__restrict__ counts, uint32
     }
 }
 
-// inclusive cumulative edge probability along each row, clamped to 1 and exactly 1 on the last edge
-__global__ void k_row_cumsum(uint64_t n, const uint64_t *__restrict__ row_ptr, const float *__restrict__ p, float *__restrict__ cum)
+// inclusive cumulative edge probability along each row, clamped to 1 and exactly 1 on the last edge; written in the
+// relabelled edge order (row i of the internal numbering = row old_of_new[i] of the caller's graph)
+__global__ void k_row_cumsum(uint64_t n, const uint32_t *__restrict__ old_of_new, const uint64_t *__restrict__ row_ptr,
+                             const float *__restrict__ p, const uint64_t *__restrict__ row_ptr2, float *__restrict__ cum)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    const uint32_t o = old_of_new[i];
+    const uint64_t r0 = row_ptr[o], k = row_ptr[o + 1] - r0, w0 = row_ptr2[i];
     float acc = 0.0f;
-    for (uint64_t m = r0; m < r1; m++) { acc = __fadd_rn(acc, p[m]); cum[m] = fminf(acc, 1.0f); }
-    cum[r1 - 1] = 1.0f;
+    for (uint64_t m = 0; m < k; m++) { acc = __fadd_rn(acc, p[r0 + m]); cum[w0 + m] = fminf(acc, 1.0f); }
+    cum[w0 + k - 1] = 1.0f;
 }
 
 // =====================================================================================================
@@ -1241,10 +1369,11 @@ static int alloc_layout(annembed_cuda_ctx *ctx)
     // does not support); single rank: pool memory, so that creating and destroying a context per embed() costs no
     // cudaMalloc/cudaFree (a cudaFree of these buffers was measured at 80-900 ms)
     const bool ipc = ctx->nranks > 1;
-    CU(ctx->y[0].alloc(want, ipc)); CU(ctx->y[1].alloc(want, ipc)); CU(ctx->y0.alloc(want));
+    CU(ctx->y[0].alloc(want, ipc)); CU(ctx->y[1].alloc(want, ipc)); CU(ctx->y0.alloc(want)); CU(ctx->yapi.alloc(want));
     CU(cudaMemsetAsync(ctx->y[0].p, 0, want * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(ctx->y[1].p, 0, want * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(ctx->y0.p, 0, want * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(ctx->yapi.p, 0, want * sizeof(float), ctx->stream));
     return ANNEMBED_OK;
 }
 
@@ -1418,7 +1547,7 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
     REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_neg_weights: graph not set");
     CU(cudaSetDevice(ctx->device));
-    if (!w) { ctx->have_alias = false; ctx->neg_alias.release(); return ANNEMBED_OK; }
+    if (!w) { ctx->have_alias = false; ctx->neg_alias.release(); ctx->neg_alias_old.release(); return ANNEMBED_OK; }
     const uint64_t n = ctx->n;
     double tot = 0.0;
     for (uint64_t i = 0; i < n; i++) {
@@ -1444,21 +1573,79 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
     }
     for (uint32_t l : large) put(l, 1.0f, l);
     for (uint32_t s : small) put(s, 1.0f, s);
-    CU(ctx->neg_alias.alloc(n));
+    CU(ctx->neg_alias_old.alloc(n));
     int rc;
-    if ((rc = h2d(ctx, ctx->neg_alias.p, tab.data(), n * sizeof(uint2)))) return rc;
-    ctx->have_alias = true;
+    if ((rc = h2d(ctx, ctx->neg_alias_old.p, tab.data(), n * sizeof(uint2)))) return rc;
+    ctx->have_alias = true; ctx->alias_dirty = true;
     return ANNEMBED_OK;
 }
 
-// device context build: K2 + transposed index (≙ EntropyOptim::new, embedder.rs:964-1025)
-// transposed index of the graph (≙ nothing in the reference: its symmetric move writes y_j under a lock,
-// embedder.rs:1239).  Depends on the graph and the shard only; built once per set_graph_csr.
+// Internal numbering of the nodes: identity (ANNEMBED_FLAG_NO_RELABEL, tiny graphs) or the nested min-label cells of
+// k_lp_round.  Graph only; built once per set_graph_csr.
+static int build_relabelling(annembed_cuda_ctx *ctx)
+{
+    const uint64_t n = ctx->n;
+    int rc;
+    CU(ctx->new_of_old.alloc(n)); CU(ctx->old_of_new.alloc(n));
+    k_iota<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p);
+    ctx->st.kernel_launches++;
+    if (!(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL) && n >= 1024) {
+        DevBuf<uint32_t> L[2], key, key_s, ord;
+        DevBuf<unsigned char> tmp;
+        CU(L[0].alloc(n)); CU(L[1].alloc(n)); CU(key.alloc(n)); CU(key_s.alloc(n)); CU(ord.alloc(n));
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key_s.p, ctx->old_of_new.p, ord.p, (int64_t)n, 0, 32, ctx->stream));
+        CU(tmp.alloc(tmp_bytes));
+        k_lp_init<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, L[0].p);
+        int cur = 0;
+        uint32_t *order = ctx->old_of_new.p, *order2 = ord.p;
+        for (int round = 1; round <= 8; round++) {
+            CU(cudaMemcpyAsync(L[cur ^ 1].p, L[cur].p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            k_lp_round<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr.p, ctx->col.p, L[cur].p, L[cur ^ 1].p);
+            cur ^= 1;
+            ctx->st.kernel_launches += 1;
+            if (round == 1 || round == 2 || round == 4 || round == 8) {
+                // stable sort of the current order by this level's label (least significant level first)
+                k_gather_u32<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, order, L[cur].p, key.p);
+                CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key_s.p, order, order2, (int64_t)n, 0, 32, ctx->stream));
+                std::swap(order, order2);
+                ctx->st.kernel_launches += 2;
+            }
+        }
+        if (order != ctx->old_of_new.p)
+            CU(cudaMemcpyAsync(ctx->old_of_new.p, order, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = sync_stream(ctx))) return rc;     // the scratch buffers are released on return
+    }
+    k_invert_perm<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->new_of_old.p);
+    ctx->st.kernel_launches++;
+    CU(cudaGetLastError());
+    return ANNEMBED_OK;
+}
+
+// device context build, graph part (≙ nothing in the reference: its symmetric move writes y_j under a lock,
+// embedder.rs:1239): internal numbering, relabelled CSR, transposed index of the owned nodes, out-edge -> in-edge slot
+// map.  Depends on the graph and the shard only; built once per set_graph_csr.
 static int ensure_struct(annembed_cuda_ctx *ctx)
 {
     if (ctx->have_struct) return ANNEMBED_OK;
     const uint64_t n = ctx->n, E = ctx->E;
     int rc;
+    if ((rc = build_relabelling(ctx))) return rc;
+    // relabelled CSR
+    CU(ctx->row_ptr2.alloc(n + 1)); CU(ctx->col2.alloc(E));
+    {
+        DevBuf<uint64_t> deg2; DevBuf<unsigned char> tmp;
+        CU(deg2.alloc(n + 1));
+        k_relabel_degrees<<<nblocks(n + 1, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->row_ptr.p, deg2.p);
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg2.p, ctx->row_ptr2.p, (int64_t)(n + 1), ctx->stream));
+        CU(tmp.alloc(tmp_bytes));
+        CU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, deg2.p, ctx->row_ptr2.p, (int64_t)(n + 1), ctx->stream));
+        k_relabel_rows<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->new_of_old.p, ctx->row_ptr.p, ctx->col.p,
+                                                                 ctx->row_ptr2.p, ctx->col2.p);
+        ctx->st.kernel_launches += 3;
+        if ((rc = sync_stream(ctx))) return rc;
+    }
     CU(ctx->in_ptr_all.alloc(n + 2));
     DevBuf<uint32_t> eid, dst_sorted, eid_sorted;
     DevBuf<unsigned char> tmp;
@@ -1467,9 +1654,9 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
     int bits = 1; while (bits < 32 && (1ull << bits) < n) bits++;
     size_t tmp_bytes = 0;
     // stable radix sort of (dst, edge id): in-edges of a node stay in edge-id order
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->col2.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
     CU(tmp.alloc(tmp_bytes));
-    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ctx->col.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
+    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ctx->col2.p, dst_sorted.p, eid.p, eid_sorted.p, (int64_t)E, 0, bits, ctx->stream));
     k_in_ptr<<<nblocks(E + 1, 256), 256, 0, ctx->stream>>>(E, n, dst_sorted.p, ctx->in_ptr_all.p);
     ctx->st.kernel_launches += 3;
     uint64_t qr[2];
@@ -1483,42 +1670,76 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
     CU(ctx->in_src.alloc(std::max<uint64_t>(cnt, 1)));
     CU(ctx->in_eid.alloc(std::max<uint64_t>(cnt, 1)));
     if (cnt) {
-        k_in_struct<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, dst_sorted.p, ctx->lo, ctx->row_ptr.p,
+        k_in_struct<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(qr[0], qr[1], n, eid_sorted.p, dst_sorted.p, ctx->lo, ctx->row_ptr2.p,
                                                                 ctx->in_src.p, ctx->in_eid.p);
         ctx->st.kernel_launches++;
     }
+    // rows of the tiled kernels (rows of at most 16 neighbours): padded length, slot map, byte map of firing counts
+    ctx->KP = ctx->kmax <= 6 ? 6 : (ctx->kmax <= 8 ? 8 : (ctx->kmax <= 10 ? 10 : (ctx->kmax <= 16 ? 16 : 0)));
+    ctx->rowpack.release(); ctx->erank.release(); ctx->fired.release();
+    if (ctx->KP) {
+        CU(ctx->rowpack.alloc(n * (uint64_t)ctx->KP));
+        if (ctx->nranks == 1) {
+            CU(ctx->erank.alloc(n * (uint64_t)ctx->KP));
+            CU(ctx->fired.alloc(E + 64));
+            CU(cudaMemsetAsync(ctx->fired.p, 0, E + 64, ctx->stream));
+            CU(cudaMemsetAsync(ctx->erank.p, 0xff, n * (uint64_t)ctx->KP * sizeof(uint32_t), ctx->stream));
+            k_erank<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(cnt, qr[0], ctx->KP, ctx->in_src.p, ctx->in_eid.p, ctx->row_ptr2.p, ctx->erank.p);
+            ctx->st.kernel_launches++;
+        }
+    }
     if ((rc = sync_stream(ctx))) return rc;
     ctx->have_struct = true;
+    ctx->alias_dirty = ctx->have_alias;
     return ANNEMBED_OK;
 }
 
-// device context build: K2 + cumulative row probabilities + in-edge payloads (≙ EntropyOptim::new, embedder.rs:964-1025)
+// device context build, weights part: K2 + cumulative row probabilities + rows + in-edge payloads
+// (≙ EntropyOptim::new, embedder.rs:964-1025)
 static int ensure_build(annembed_cuda_ctx *ctx)
 {
-    if (ctx->have_build) return ANNEMBED_OK;
-    REQUIRE(ctx->have_weights, ANNEMBED_ERR_STATE, "edge weights not computed (embedder.rs:802-808: initial_space not constructed)");
-    const uint64_t n = ctx->n, E = ctx->E;
     int rc;
-    CU(cudaEventRecord(ctx->ev_a, ctx->stream));
-    if ((rc = ensure_struct(ctx))) return rc;
-    if (ctx->emb_scale.n != n) { CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); }
-    if (ctx->cum.n != E) CU(ctx->cum.alloc(E));
-    k_row_cumsum<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr.p, ctx->proba.p, ctx->cum.p);
-    ctx->st.kernel_launches++;
-    // K2
-    if ((rc = sum_f64(ctx, ctx->scale.p, n, ctx->partials.p + 4095))) return rc;
-    k_embedded_scales<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->scale.p, ctx->partials.p + 4095, ctx->emb_scale.p, ctx->inv_s2.p);
-    ctx->st.kernel_launches++;
-    if (ctx->in_cnt) {
-        k_in_rec<<<nblocks(ctx->in_cnt, 256), 256, 0, ctx->stream>>>(ctx->in_cnt, ctx->in_src.p, ctx->in_eid.p, ctx->row_ptr.p, ctx->cum.p,
-                                                                     ctx->inv_s2.p, ctx->in_rec.p);
-        ctx->st.kernel_launches++;
+    if (ctx->have_build) {
+        if (ctx->alias_dirty && ctx->have_alias) goto alias;
+        return ANNEMBED_OK;
     }
-    CU(cudaEventRecord(ctx->ev_b, ctx->stream));
-    if ((rc = sync_stream(ctx))) return rc;
-    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
-    ctx->st.build_ms = ms;
-    ctx->have_build = true;
+    REQUIRE(ctx->have_weights, ANNEMBED_ERR_STATE, "edge weights not computed (embedder.rs:802-808: initial_space not constructed)");
+    {
+        const uint64_t n = ctx->n, E = ctx->E;
+        CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+        if ((rc = ensure_struct(ctx))) return rc;
+        if (ctx->emb_scale.n != n) { CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); CU(ctx->inv_s2n.alloc(n)); }
+        if (ctx->cum.n != E) CU(ctx->cum.alloc(E));
+        k_row_cumsum<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->row_ptr.p, ctx->proba.p, ctx->row_ptr2.p, ctx->cum.p);
+        ctx->st.kernel_launches++;
+        // K2
+        if ((rc = sum_f64(ctx, ctx->scale.p, n, ctx->partials.p + 4095))) return rc;
+        k_embedded_scales<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->scale.p, ctx->partials.p + 4095, ctx->emb_scale.p, ctx->inv_s2.p);
+        k_gather_f32<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->inv_s2.p, ctx->inv_s2n.p);
+        ctx->st.kernel_launches += 2;
+        if (ctx->KP) {
+            k_rowpack<<<nblocks(n * (uint64_t)ctx->KP, 256), 256, 0, ctx->stream>>>(n, ctx->KP, ctx->row_ptr2.p, ctx->col2.p, ctx->cum.p, ctx->rowpack.p);
+            ctx->st.kernel_launches++;
+        }
+        if (ctx->in_cnt) {
+            k_in_rec<<<nblocks(ctx->in_cnt, 256), 256, 0, ctx->stream>>>(ctx->in_cnt, ctx->in_src.p, ctx->in_eid.p, ctx->row_ptr2.p, ctx->cum.p,
+                                                                         ctx->inv_s2n.p, ctx->in_rec.p);
+            ctx->st.kernel_launches++;
+        }
+        CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+        if ((rc = sync_stream(ctx))) return rc;
+        float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+        ctx->st.build_ms = ms;
+        ctx->have_build = true;
+    }
+alias:
+    if (ctx->alias_dirty && ctx->have_alias) {
+        CU(ctx->neg_alias.alloc(ctx->n));
+        k_relabel_alias<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->new_of_old.p, ctx->neg_alias_old.p, ctx->neg_alias.p);
+        ctx->st.kernel_launches++;
+        if ((rc = sync_stream(ctx))) return rc;
+        ctx->alias_dirty = false;
+    }
     return ANNEMBED_OK;
 }
 
@@ -1533,12 +1754,13 @@ extern "C" int annembed_cuda_get_hubness_counts(annembed_cuda_ctx *ctx, uint32_t
         int rc0 = ensure_struct(ctx);
         if (rc0) return rc0;
     }
-    DevBuf<uint32_t> t; CU(t.alloc(ctx->n));
-    k_degree_u32<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->in_ptr_all.p, t.p);
-    ctx->st.kernel_launches++;
+    DevBuf<uint32_t> t, t_old; CU(t.alloc(ctx->n)); CU(t_old.alloc(ctx->n));
+    k_degree_u32<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->in_ptr_all.p, t.p);        // internal numbering
+    k_gather_u32<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->new_of_old.p, t.p, t_old.p);
+    ctx->st.kernel_launches += 2;
     int rc;
     if ((rc = sync_stream(ctx))) return rc;
-    return d2h(ctx, counts, t.p, ctx->n * sizeof(uint32_t));
+    return d2h(ctx, counts, t_old.p, ctx->n * sizeof(uint32_t));
 }
 
 extern "C" int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *y)
@@ -1914,8 +2136,7 @@ extern "C" int annembed_cuda_reset_embedding(annembed_cuda_ctx *ctx)
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
     REQUIRE(ctx->have_embedding, ANNEMBED_ERR_STATE, "reset_embedding: embedding not set");
     CU(cudaSetDevice(ctx->device));
-    ctx->cur = 0;
-    CU(cudaMemcpyAsync(ctx->y[0].p, ctx->y0.p, ctx->y0.n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->yapi.p, ctx->y0.p, ctx->y0.n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     return sync_stream(ctx);
 }
 
@@ -1998,7 +2219,7 @@ extern "C" int annembed_cuda_step_fixed(annembed_cuda_ctx *ctx, uint64_t n_sampl
     if ((rc = h2d(ctx, de.p, edge_idx, n_samples * sizeof(uint64_t)))) return rc;
     if ((rc = h2d(ctx, dn.p, neg_idx, n_samples * 5 * sizeof(uint32_t)))) return rc;
     const SgdConst K = make_const(ctx, grad_step);
-    float *Y = ctx->y[ctx->cur].p;
+    float *Y = ctx->yapi.p;
 #define LAUNCH_FIXED(DPV) k_step_fixed<DPV><<<1, 32, 0, ctx->stream>>>(Y, ctx->n, ctx->row_ptr.p, ctx->col.p, ctx->proba.p, ctx->inv_s2.p, K, n_samples, de.p, dn.p)
     switch (ctx->DP) {
     case 2: LAUNCH_FIXED(2); break;
@@ -2016,14 +2237,16 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
 {
     if (M == 0) M = eff_mini_epochs(ctx);
     EpochArgs a;
+    memset(&a, 0, sizeof a);
     a.y_snap = ctx->y[ctx->cur].p;
     a.y_next = ctx->y[ctx->cur ^ 1].p;
-    a.row_ptr = ctx->row_ptr.p; a.col = ctx->col.p; a.p = ctx->proba.p; a.inv_s2 = ctx->inv_s2.p;
+    // everything below is in the internal numbering
+    a.row_ptr = ctx->row_ptr2.p; a.col = ctx->col2.p; a.p = nullptr; a.inv_s2 = ctx->inv_s2n.p;
     a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
-    a.regular_k = (ctx->kmin == ctx->kmax) ? ctx->kmax : 0u;
-    a.regular_k_inv = a.regular_k ? (65536u + a.regular_k - 1u) / a.regular_k : 0u;
+    a.rowpack = ctx->rowpack.p; a.erank = ctx->erank.p;
+    a.fired = (ctx->nranks == 1 && !(ctx->prm.flags & ANNEMBED_FLAG_REPLAY_IN_EDGES)) ? ctx->fired.p : nullptr;
     a.n_peers = 0;
     for (int r = 0; r < 7; r++) a.peer_next[r] = nullptr;
     a.k2 = (uint32_t)(ctx->prm.seed & 0xFFFFFFFFu) ^ ((uint32_t)(ctx->prm.seed >> 32) * 0x85EBCA6Bu);
@@ -2054,21 +2277,33 @@ static void set_l2_window(annembed_cuda_ctx *ctx, const void *ptr, size_t bytes)
     cudaStreamSetAttribute(ctx->stream2, cudaStreamAttributeAccessPolicyWindow, &v);
 }
 
-template <int DP, bool HUB, int KREG>
+// The tiled kernels are specialised for b == 1, keep the per-edge firing counts of a node in bytes and hold rows of
+// at most 16 neighbours in registers; everything else runs the thread-per-node kernel.  ONE predicate decides both the
+// kernel and (multi-rank) whether the exchange is fused into it.
+static bool use_tiled(const annembed_cuda_ctx *ctx, float kappa)
+{
+    return !(ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL) && ctx->prm.b == 1.0 && ctx->KP != 0 &&
+           kappa + 2.0f < (float)EpochTile<2, 6>::MAX_FIRINGS;
+}
+
+template <int DP, bool HUB, int KP>
 static cudaError_t launch_tiled(annembed_cuda_ctx *ctx, const EpochArgs &a)
 {
-    using TL = EpochTile<DP, KREG>;
+    using TL = EpochTile<DP, KP>;
     const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;
     const unsigned int nb = (unsigned int)((tiles + TL::WARPS - 1) / TL::WARPS);
-    k_epoch_out<DP, HUB, KREG><<<nb, TL::WARPS * 32, TL::SMEM, ctx->launch_stream>>>(a, ctx->counter.p);
+    k_epoch_out<DP, HUB, KP><<<nb, TL::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->counter.p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const unsigned int nb2 = (unsigned int)((tiles + ANNEMBED_WARPS_IN - 1) / ANNEMBED_WARPS_IN);
     if (InTile<DP>::SMEM > 48 * 1024) {
         e = cudaFuncSetAttribute(k_epoch_in<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, InTile<DP>::SMEM);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_epoch_in_flags<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, InTile<DP>::SMEM);
+        if (e != cudaSuccess) return e;
     }
-    k_epoch_in<DP><<<nb2, ANNEMBED_WARPS_IN * 32, InTile<DP>::SMEM, ctx->launch_stream>>>(a);
+    if (a.fired) k_epoch_in_flags<DP><<<nb2, ANNEMBED_WARPS_IN * 32, InTile<DP>::SMEM, ctx->launch_stream>>>(a);
+    else k_epoch_in<DP><<<nb2, ANNEMBED_WARPS_IN * 32, InTile<DP>::SMEM, ctx->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -2076,13 +2311,16 @@ template <int DP, bool HUB>
 static cudaError_t launch_epoch_dp(annembed_cuda_ctx *ctx, const EpochArgs &a)
 {
     if (a.hi <= a.lo) return cudaSuccess;
-    const bool force_generic = (ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL) != 0;
-    // the tiled kernels are specialised for b == 1 and keep the per-edge firing counts of a node in bytes
-    const bool tiled_ok = !force_generic && ctx->prm.b == 1.0 && a.kappa + 2.0f < (float)EpochTile<DP, 8>::MAX_FIRINGS;
-    ctx->last_epoch_kernels = (tiled_ok && ctx->kmax <= 16) ? 2 : 1;
-    if (tiled_ok && ctx->kmax <= 6) return launch_tiled<DP, HUB, 6>(ctx, a);     // row length of the reference's examples
-    if (tiled_ok && ctx->kmax <= 8) return launch_tiled<DP, HUB, 8>(ctx, a);
-    if (tiled_ok && ctx->kmax <= 16) return launch_tiled<DP, HUB, 16>(ctx, a);
+    const bool tiled = use_tiled(ctx, a.kappa);
+    ctx->last_epoch_kernels = tiled ? 2 : 1;
+    if (tiled) {
+        switch (ctx->KP) {
+        case 6: return launch_tiled<DP, HUB, 6>(ctx, a);      // row length of the reference's examples
+        case 8: return launch_tiled<DP, HUB, 8>(ctx, a);
+        case 10: return launch_tiled<DP, HUB, 10>(ctx, a);
+        default: return launch_tiled<DP, HUB, 16>(ctx, a);
+        }
+    }
     k_epoch_generic<DP, HUB><<<nblocks(a.hi - a.lo, 256), 256, 0, ctx->launch_stream>>>(a, ctx->counter.p);
     return cudaGetLastError();
 }
@@ -2106,6 +2344,14 @@ static int use_hubness(annembed_cuda_ctx *ctx, bool *hub)
     return ANNEMBED_OK;
 }
 
+// closes a mini-epoch across the ranks once the peer stores of k_epoch_in are issued (kernel completion makes them visible)
+static int rank_barrier(annembed_cuda_ctx *ctx)
+{
+    ncclResult_t r = g_nccl.AllReduce(ctx->barrier_buf.p, ctx->barrier_buf.p + 1, 1, ncclFloat, ncclSum, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce (barrier): ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+    return ANNEMBED_OK;
+}
+
 extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t first_batch, uint32_t n_batches)
 {
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
@@ -2121,56 +2367,42 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     const uint32_t last = std::min<uint64_t>((uint64_t)first_batch + n_batches, (uint64_t)nb + 1);   // exclusive
     size_t n_launch = 0;
     for (uint32_t iter = first_batch; iter < last; iter++) n_launch += mini_epochs_of_batch(ctx, iter);
-    // fused exchange needs the tiled kernels (k_epoch_in does the peer stores)
-    const bool fused = ctx->nranks > 1 && ctx->have_peers && ctx->prm.b == 1.0 && ctx->kmax <= 16 &&
-                       !(ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL);
     while (ctx->ev.size() < 2 * n_launch + 2 * n_launch * (ctx->nranks > 1)) {
         cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
     }
     CU(cudaMemsetAsync(ctx->counter.p, 0, 256 * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    // the caller's layout, in the internal node order, becomes the first snapshot
+    const uint64_t nrow = ctx->n * (uint64_t)ctx->DP;
+    if (ctx->nranks > 1 && ctx->have_peers && (rc = rank_barrier(ctx))) return rc;    // no peer still reads or writes y[]
+    ctx->cur = 0;
+    k_rows_to_internal<<<nblocks(nrow, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->DP, ctx->old_of_new.p, ctx->yapi.p, ctx->y[0].p);
+    ctx->st.kernel_launches++;
+    if (ctx->nranks > 1 && ctx->have_peers && (rc = rank_barrier(ctx))) return rc;    // every replica holds the snapshot
     size_t li = 0;
     const size_t xoff = 2 * n_launch;
+    size_t n_kernels = 0;
     for (uint32_t iter = first_batch; iter < last; iter++) {
         const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
         const uint32_t M = mini_epochs_of_batch(ctx, iter), e0 = first_epoch_of_batch(ctx, iter);
         for (uint32_t m = 0; m < M; m++, li++) {
             EpochArgs a = make_epoch_args(ctx, e0 + m, grad_step, M);
+            // the fused exchange lives in the tiled in-edge kernel: the same predicate picks the kernel and the exchange
+            const bool fused = ctx->nranks > 1 && ctx->have_peers && use_tiled(ctx, a.kappa);
             if (fused) {
                 for (int r = 0; r < ctx->nranks; r++)
                     if (r != ctx->rank) a.peer_next[a.n_peers++] = ctx->peer_y[r][ctx->cur ^ 1];
             }
             set_l2_window(ctx, a.y_snap, (size_t)ctx->n * ctx->DP * sizeof(float));
             CU(cudaEventRecord(ctx->ev[2 * li], ctx->stream));
-            if (fused) {
-                // Staggered sub-ranges on two streams: the peer stores of one sub-range's in-edge kernel travel over
-                // NVLink while the next sub-range's out-edge kernel computes (the rows only become final in k_epoch_in).
-                const uint32_t tiles = (ctx->hi - ctx->lo + 31) / 32;
-                const uint32_t per = ((tiles + ANNEMBED_FUSED_CHUNKS - 1) / ANNEMBED_FUSED_CHUNKS) * 32;
-                CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-                CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-                for (int c = 0; c < ANNEMBED_FUSED_CHUNKS; c++) {
-                    EpochArgs ac = a;
-                    ac.lo = std::min<uint32_t>(ctx->hi, ctx->lo + (uint32_t)c * per);
-                    ac.hi = std::min<uint32_t>(ctx->hi, ac.lo + per);
-                    if (ac.hi <= ac.lo) continue;
-                    ac.in_ptr = ctx->in_ptr_all.p + ac.lo;
-                    ctx->launch_stream = (c & 1) ? ctx->stream2 : ctx->stream;
-                    CU(hub ? launch_epoch<true>(ctx, ac) : launch_epoch<false>(ctx, ac));
-                }
-                ctx->launch_stream = ctx->stream;
-                CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
-                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-            } else {
-                CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
-            }
+            CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
+            n_kernels += ctx->last_epoch_kernels;
             CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
             if (ctx->nranks > 1) {
                 CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
                 if (fused) {
                     // the in-edge kernel already stored the owned rows into every replica: only a barrier is left
-                    ncclResult_t r = g_nccl.AllReduce(ctx->barrier_buf.p, ctx->barrier_buf.p + 1, 1, ncclFloat, ncclSum, ctx->comm, ctx->stream);
-                    if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce (barrier): ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+                    if ((rc = rank_barrier(ctx))) return rc;
                 } else {
                     // replicate the updated rows: in-place all-gather of the owned slice of y_next
                     float *buf = ctx->y[ctx->cur ^ 1].p;
@@ -2184,6 +2416,8 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
         }
     }
     set_l2_window(ctx, nullptr, 0);
+    k_rows_from_internal<<<nblocks(nrow, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->DP, ctx->old_of_new.p, ctx->y[ctx->cur].p, ctx->yapi.p);
+    ctx->st.kernel_launches++;
     CU(cudaEventRecord(ctx->ev_b, ctx->stream));
     unsigned long long cnts[256];
     CU(cudaMemcpyAsync(cnts, ctx->counter.p, sizeof(cnts), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2197,7 +2431,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
         if (ctx->nranks > 1) { CU(cudaEventElapsedTime(&t, ctx->ev[xoff + 2 * i], ctx->ev[xoff + 2 * i + 1])); xms += t; }
     }
     ctx->st.optimize_ms = ms; ctx->st.epoch_kernel_ms = kms; ctx->st.exchange_ms = xms;
-    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_launch * (ctx->last_epoch_kernels) * (fused ? ANNEMBED_FUSED_CHUNKS : 1);
+    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_kernels;
     ctx->st.positive_samples = cnt; ctx->st.edge_updates = 6 * cnt;
     ctx->st.model_bytes = (double)cnt * (12.0 + 36.0 * (double)ctx->prm.asked_dim);
     return ANNEMBED_OK;
@@ -2213,7 +2447,7 @@ extern "C" int annembed_cuda_cross_entropy(annembed_cuda_ctx *ctx, double *out)
     if ((rc = ensure_build(ctx))) return rc;
     CU(cudaEventRecord(ctx->ev_a, ctx->stream));
     const unsigned int nb = std::min<unsigned int>(2048u, std::max(1u, nblocks(ctx->hi - ctx->lo, 256)));
-    const float *Y = ctx->y[ctx->cur].p;
+    const float *Y = ctx->yapi.p;
 #define LAUNCH_CE(DPV) k_cross_entropy<DPV><<<nb, 256, 0, ctx->stream>>>(ctx->lo, ctx->hi, ctx->row_ptr.p, ctx->col.p, ctx->proba.p, ctx->emb_scale.p, Y, ctx->prm.b, ctx->partials.p)
     switch (ctx->DP) {
     case 2: LAUNCH_CE(2); break;
@@ -2258,9 +2492,9 @@ extern "C" int annembed_cuda_get_embedding(annembed_cuda_ctx *ctx, float *y_out)
     CU(cudaSetDevice(ctx->device));
     const uint64_t n = ctx->n;
     const int d = (int)ctx->prm.asked_dim, DP = ctx->DP;
-    if (d == DP) return d2h(ctx, y_out, ctx->y[ctx->cur].p, n * d * sizeof(float));
+    if (d == DP) return d2h(ctx, y_out, ctx->yapi.p, n * d * sizeof(float));
     DevBuf<float> stage; CU(stage.alloc(n * d));
-    k_unpad_rows<<<nblocks(n * d, 256), 256, 0, ctx->stream>>>(n, d, DP, ctx->y[ctx->cur].p, stage.p);
+    k_unpad_rows<<<nblocks(n * d, 256), 256, 0, ctx->stream>>>(n, d, DP, ctx->yapi.p, stage.p);
     ctx->st.kernel_launches++;
     int rc;
     if ((rc = sync_stream(ctx))) return rc;
@@ -2349,7 +2583,7 @@ static int quality_impl(annembed_cuda_ctx *ctx, uint32_t nbng, annembed_cuda_qua
                         float *first_dist_out, float *node_ratio_out)
 {
     const uint64_t n = ctx->n, E = ctx->E;
-    const float *Y = ctx->y[ctx->cur].p;
+    const float *Y = ctx->yapi.p;
     int rc;
     DevBuf<float> t, radius, ratio, node_ratio, first_dist, sorted;
     DevBuf<uint32_t> nodes_match, cell, idx, cell_s, idx_s, cell_start;
@@ -2441,6 +2675,8 @@ extern "C" int annembed_cuda_debug_draws(annembed_cuda_ctx *ctx, uint32_t epoch,
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
     REQUIRE(counts_out, ANNEMBED_ERR_INVALID_ARG, "null output");
     REQUIRE(ctx->have_graph && ctx->have_weights, ANNEMBED_ERR_STATE, "debug_draws: graph / weights not set");
+    REQUIRE(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL, ANNEMBED_ERR_STATE,
+            "debug_draws reports draws by edge of the caller's graph: create the context with ANNEMBED_FLAG_NO_RELABEL");
     CU(cudaSetDevice(ctx->device));
     int rc;
     bool hub;

@@ -3,6 +3,12 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+# ANNEMBED_FLAG_* of include/annembed_cuda.h
+FLAG_GENERIC_EPOCH_KERNEL = 1
+FLAG_NO_L2_PERSIST = 2
+FLAG_NO_RELABEL = 4
+FLAG_REPLAY_IN_EDGES = 8
+
 
 @dataclass
 class EmbedderParams:
@@ -18,7 +24,7 @@ class EmbedderParams:
     hierarchy_layer: int = 0         # :100,118
     hubness_weighting: bool = False  # :102,119
     # device-side additions (the reference's RNG is unseeded; see include/annembed_cuda.h)
-    mini_epochs_per_batch: int = 0   # 0 -> graded schedule (finest: ceil(nb_sampling_by_edge / 0.3))
+    mini_epochs_per_batch: int = 0   # 0 -> graded schedule (finest: ceil(nb_sampling_by_edge / 0.15))
     seed: int = 0x5EED
     flags: int = 0
 

@@ -67,6 +67,9 @@ typedef struct annembed_cuda_params {
 #define ANNEMBED_FLAG_NONE 0u
 #define ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL 1u   /* force the thread-per-node epoch kernel (cross-check of the tiled one) */
 #define ANNEMBED_FLAG_NO_L2_PERSIST 2u
+#define ANNEMBED_FLAG_NO_RELABEL 4u             /* keep the caller's node order inside the optimizer (no locality relabelling) */
+#define ANNEMBED_FLAG_REPLAY_IN_EDGES 8u        /* single rank: replay the sources' decisions in the in-edge kernel instead of
+                                                   consuming the firing counts pushed by the out-edge kernel (cross-check) */
 
 typedef struct annembed_cuda_stats {
     double   edge_weights_ms;      /* K0+K1 device time, last call */

@@ -174,7 +174,8 @@ def test_cross_entropy_large_vs_oracle():
 # ------------------------------------------------------------------ sampler (T6) and K4
 def test_device_draws_match_host_build_bit_for_bit():
     row_ptr, col, dist = random_graph(3000, 3, 12, seed=61)
-    ctx = ctx_for(row_ptr, col, dist, nb_sampling_by_edge=10, mini_epochs_per_batch=7, seed=1234567890123)
+    # flags=4 (ANNEMBED_FLAG_NO_RELABEL): the draws are keyed by the internal node ids; the host build knows the caller's
+    ctx = ctx_for(row_ptr, col, dist, nb_sampling_by_edge=10, mini_epochs_per_batch=7, seed=1234567890123, flags=4)
     scale, p = ctx.edge_weights()
     for epoch in (0, 1, 77):
         c_dev, n_dev = ctx.debug_draws(epoch)
@@ -184,7 +185,7 @@ def test_device_draws_match_host_build_bit_for_bit():
     # hubness sampler: alias draws follow the weights
     w = oracle.hubness_weights(row_ptr, col)
     np.testing.assert_array_equal(ctx.get_hubness_counts(), np.bincount(col, minlength=3000))
-    ctxh = ctx_for(row_ptr, col, dist, hubness_weighting=True, mini_epochs_per_batch=1)
+    ctxh = ctx_for(row_ptr, col, dist, hubness_weighting=True, mini_epochs_per_batch=1, flags=4)
     ctxh.edge_weights()
     ctxh.set_neg_weights(w)
     hist = np.zeros(3000)
@@ -195,16 +196,18 @@ def test_device_draws_match_host_build_bit_for_bit():
     assert np.corrcoef(freq, w / w.sum())[0, 1] > 0.9
 
 
-@pytest.mark.parametrize("d,hub", [(2, False), (2, True), (5, False), (15, False)])
-def test_epoch_kernel_matches_host_replay(d, hub):
+@pytest.mark.parametrize("d,hub,flags", [(2, False, 4), (2, False, 4 | 8), (2, True, 4), (5, False, 4), (15, False, 4), (15, False, 4 | 8)])
+def test_epoch_kernel_matches_host_replay(d, hub, flags):
     """K4 against the host build of the same mini-epoch body: same draws, same order, fp32 rounding apart.
     ONE mini-epoch is compared: the dynamics are chaotic (repulsion coefficients up to 2 triple a perturbation per
     close negative), so rounding differences between nvcc's fma contraction and the host build grow afterwards."""
     row_ptr, col, dist = random_graph(4000, 3, 10, seed=71)
     n = 4000
     # nb_sampling_by_edge = 1 and one mini-epoch per batch: a batch is exactly one launch of K4
+    # flags: 4 = caller's node order kept inside the optimizer (the host build has no relabelling), 8 = in-edge
+    # decisions replayed (the multi-rank kernel) instead of pushed by the out-edge kernel
     kw = dict(asked_dim=d, nb_grad_batch=4, nb_sampling_by_edge=1, mini_epochs_per_batch=1, grad_step=1.0, seed=99,
-              hubness_weighting=hub)
+              hubness_weighting=hub, flags=flags)
     ctx = ctx_for(row_ptr, col, dist, **kw)
     scale, p = ctx.edge_weights()
     es = ctx.get_embedded_scales()
@@ -260,9 +263,51 @@ def test_tiled_epoch_kernel_equals_generic_kernel(d, kmax, hub, M):
         assert np.quantile(err, 0.999) < 1e-4 and np.median(err) < 1e-6, (np.quantile(err, 0.999), err.max())
 
 
+@pytest.mark.parametrize("d,kmax,hub,M,nbs", [(2, 6, False, 3, 1), (2, 6, False, 4, 10), (2, 10, True, 2, 3), (4, 8, False, 2, 2), (15, 6, False, 2, 2)])
+def test_pushed_firing_counts_equal_replayed_decisions(d, kmax, hub, M, nbs):
+    """Single rank: k_epoch_out pushes every fired edge's count into the byte map that k_epoch_in_flags consumes; the
+    multi-rank kernel k_epoch_in replays the same decisions from the in-edge records.  Same decisions, same order of
+    application: bit-identical layouts over several mini-epochs, and the byte map is left cleared."""
+    row_ptr, col, dist = random_graph(6000, 2, kmax, seed=74)
+    y0 = np.random.default_rng(4).uniform(-1, 1, size=(6000, d)).astype(np.float32)
+    outs = []
+    for flags in (0, 8):                             # 8 = ANNEMBED_FLAG_REPLAY_IN_EDGES
+        ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=3, grad_step=1.0, seed=6, flags=flags,
+                      hubness_weighting=hub, nb_sampling_by_edge=nbs, mini_epochs_per_batch=M)
+        ctx.edge_weights(want_outputs=False)
+        if hub:
+            ctx.set_neg_weights(oracle.hubness_weights(row_ptr, col))
+        ctx.set_embedding(y0)
+        ctx.optimize_batches(1, 2)                   # 2 batches = 2 M mini-epochs
+        outs.append((ctx.get_embedding(), ctx.get_stats()["positive_samples"]))
+    assert outs[0][1] == outs[1][1]
+    assert np.abs(outs[0][0] - y0).max() > 1e-2
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+
+
+def test_relabelling_is_invisible_at_the_boundary():
+    """The optimizer renumbers the nodes internally (locality); every array crossing the C ABI stays in the caller's
+    order: a batch with gradient step 0 returns the initial layout bit for bit, hubness counts are the caller's
+    in-degrees, and the relabelled run is a different random realisation of the same optimisation (close cross entropy)."""
+    row_ptr, col, dist = random_graph(5000, 4, 9, seed=75)
+    y0 = np.random.default_rng(5).uniform(-1, 1, size=(5000, 2)).astype(np.float32)
+    ces = []
+    for flags in (0, 4):
+        ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=6, grad_step=1.0, seed=11, flags=flags)
+        ctx.edge_weights(want_outputs=False)
+        np.testing.assert_array_equal(ctx.get_hubness_counts(), np.bincount(col, minlength=5000))
+        ctx.set_embedding(y0)
+        ctx.optimize_batches(6, 1)                   # last batch: grad_step 0 (embedder.rs:873-876)
+        np.testing.assert_array_equal(ctx.get_embedding(), y0)
+        ce0, ce1 = ctx.optimize()
+        ces.append(ce1)
+        assert ce1 < ce0
+    assert abs(ces[0] - ces[1]) < 0.05 * ces[1]
+
+
 def test_rows_longer_than_16_use_the_generic_kernel():
     row_ptr, col, dist = random_graph(3000, 17, 40, seed=73)
-    ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=3, grad_step=1.0, mini_epochs_per_batch=60)
+    ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=3, grad_step=1.0, mini_epochs_per_batch=60, flags=4)
     scale, p = ctx.edge_weights()
     es = ctx.get_embedded_scales()
     y0 = np.random.default_rng(2).uniform(-1, 1, size=(3000, 2)).astype(np.float32)
