@@ -97,7 +97,9 @@ def load(rebuild_if_stale: bool = True) -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.environ.get("ANNEMBED_CUDA_LIB")           # experiment variants of the same CUDA library
+    # ANNEMBED_CUDA_LIB (documented in README.md, "Build variants"): absolute path of another build of the SAME source
+    # (annembed_b200/build.py build_library(extra_flags=..., out=...)), used by the kernel-tuning studies only
+    path = os.environ.get("ANNEMBED_CUDA_LIB")
     if not path:
         path = _build.LIB
         if not os.path.exists(path) or (rebuild_if_stale and _build.needs_build()):

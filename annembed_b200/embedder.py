@@ -2,8 +2,9 @@
 
 Same method names, argument meaning and error behaviour as the Rust struct (embedder.rs:84-453), with the pair
 `to_proba_edges` + `entropy_optimize` (embedder.rs:351-356) replaced by calls into the C ABI
-(include/annembed_cuda.h).  What is NOT here (out of scope): the diffusion-map initial layout
-(an explicit `initial_embedding` is required when dmap_init is true), hierarchical `from_hkgraph`, quality estimate.
+(include/annembed_cuda.h).  Also here: the device diffusion-map initial layout (dmap_init,
+embedder.rs:308-345), the hierarchical `from_hkgraph` second step (embedder.rs:194-295) and the device quality estimate
+(embedder.rs:620-753).  There is no CPU fallback: every method fails if the CUDA library or a device is missing.
 """
 from __future__ import annotations
 
@@ -84,8 +85,8 @@ class CudaContext:
         col = np.ascontiguousarray(col, np.uint32)
         dist = np.ascontiguousarray(dist, np.float32)
         n = len(row_ptr) - 1
-        if n < 0 or len(col) != len(dist):
-            raise ValueError("inconsistent CSR arrays")
+        if n < 0 or len(col) != len(dist) or (n >= 0 and int(row_ptr[-1]) != len(col)):
+            raise ValueError("inconsistent CSR arrays (len(col) == len(dist) == row_ptr[-1] required)")
         self._ck(self.lib.annembed_cuda_set_graph_csr(self.h, n, ptr(row_ptr, C.c_uint64), ptr(col, C.c_uint32),
                                                       ptr(dist, C.c_float)))
         self.n, self.E = n, len(col)

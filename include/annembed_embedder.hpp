@@ -127,6 +127,8 @@ public:
                 throw EmbedError(s, msg);
             }
         };
+        if (kgraph_.row_ptr.size() != n + 1 || kgraph_.col.size() != kgraph_.dist.size() || kgraph_.row_ptr.back() != kgraph_.col.size())
+            check(ANNEMBED_ERR_INVALID_ARG);                                       // the C side reads row_ptr[n] entries of col / dist
         check(annembed_cuda_set_graph_csr(ctx, n, kgraph_.row_ptr.data(), kgraph_.col.data(), kgraph_.dist.data()));
         check(annembed_cuda_edge_weights(ctx, nullptr, nullptr));                  // embedder.rs:351
         if (parameters_.hubness_weighting) {                                       // embedder.rs:810-837
