@@ -21,7 +21,7 @@ class Params(C.Structure):
         ("beta", C.c_double), ("b", C.c_double), ("scale_rho", C.c_double), ("grad_step", C.c_double),
         ("nb_sampling_by_edge", C.c_uint32), ("nb_grad_batch", C.c_uint32), ("grad_factor", C.c_uint32),
         ("hierarchy_layer", C.c_uint32), ("hubness_weighting", C.c_uint32),
-        ("mini_epochs_per_batch", C.c_uint32), ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("mini_epochs_per_batch", C.c_uint32), ("seed", C.c_uint64), ("flags", C.c_uint32), ("cell_substeps", C.c_uint32),
     ]
 
 
@@ -32,6 +32,7 @@ class Stats(C.Structure):
         ("epoch_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("positive_samples", C.c_uint64),
         ("edge_updates", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("model_bytes", C.c_double),
         ("mini_epochs_per_batch", C.c_uint64), ("l2_persist_max_bytes", C.c_uint64), ("l2_window_max_bytes", C.c_uint64),
+        ("n_cells", C.c_uint64), ("cell_nodes", C.c_uint64), ("cell_substeps", C.c_uint64), ("cross_cell_edges", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is dlopen'ed in comm_init, never linked
 
@@ -69,6 +70,9 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     bool load(std::string &err)
     {
@@ -77,7 +81,8 @@ struct NcclApi {
         if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!handle) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
 #define LOADSYM(name) name = (decltype(name))dlsym(handle, "nccl" #name); if (!name) { err = "missing symbol nccl" #name; return false; }
-        LOADSYM(GetUniqueId) LOADSYM(CommInitRank) LOADSYM(CommDestroy) LOADSYM(AllGather) LOADSYM(AllReduce) LOADSYM(GetErrorString)
+        LOADSYM(GetUniqueId) LOADSYM(CommInitRank) LOADSYM(CommDestroy) LOADSYM(AllGather) LOADSYM(AllReduce) LOADSYM(Broadcast)
+        LOADSYM(GroupStart) LOADSYM(GroupEnd) LOADSYM(GetErrorString)
 #undef LOADSYM
         return true;
     }
@@ -119,6 +124,20 @@ struct annembed_cuda_ctx {
     DevBuf<unsigned char> fired;    // [E] firing counts pushed by k_epoch_out (single rank)
     int KP = 0;                     // padded row length of the tiled kernels (0: generic kernel only)
     bool alias_dirty = false;
+    // cells of the internal numbering (cell_epoch.cuh): consecutive node ranges of at most cell_nodes nodes, cut at the
+    // boundaries of graph-local segments where possible; ranks own whole cells
+    uint32_t cell_nodes = 4096;
+    std::vector<uint32_t> cell_start_h;          // n_cells + 1
+    DevBuf<uint32_t> cell_start;
+    uint32_t n_cells = 0, cell_lo = 0, cell_hi = 0;
+    std::vector<uint32_t> shard_lo;              // first node of every rank's shard (nranks + 1 entries)
+    DevBuf<uint64_t> ext_ptr;                    // per cell: its in-edges whose source lies in another cell
+    DevBuf<uint32_t> ext_slot;
+    uint64_t ext_cnt = 0;                        // owned in-edges whose source lies in another cell
+    uint64_t ext_cnt_global = 0;                 // the same count over the whole graph (identical on every rank)
+    uint32_t cell_map_bytes = 0;                 // largest number of in-edges of a cell (whole graph), rounded up to 16
+    int smem_optin_max = 0;
+    uint32_t last_substeps = 0;
 
     // optimizer context (≙ EntropyOptim, embedder.rs:936-951)
     DevBuf<float> emb_scale, inv_s2;
@@ -487,6 +506,81 @@ __global__ void k_rows_from_internal(uint64_t n, int DP, const uint32_t *__restr
     out[(uint64_t)old_of_new[i] * DP + c] = in[t];
 }
 
+// ---- cells (cell_epoch.cuh) --------------------------------------------------------------------------------------
+// first position of every run of equal keys (segments of the top-level locality label in the sorted order)
+__global__ void k_seg_flags(uint64_t n, const uint32_t *__restrict__ key, unsigned char *__restrict__ flag)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+}
+__device__ __forceinline__ uint32_t cell_of_node(uint32_t n_cells, const uint32_t *__restrict__ cell_start, uint32_t node)
+{
+    uint32_t a = 0, b = n_cells;                 // largest c with cell_start[c] <= node
+    while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (cell_start[mid] <= node) a = mid; else b = mid; }
+    return a;
+}
+// sort key of position `pos` of the locality order: (its cell, a hash of the node) -- the order INSIDE a cell is random.
+// The cell kernel reads intra-cell partners from shared memory, so it needs no finer locality; and the 4 nodes of an
+// aligned group, which share their negative streams (sgd_core.cuh neg_stream_key), must not be graph neighbours: groups
+// of adjacent nodes repelled by the same far nodes at the same time move coherently, which measurably (3 % on the
+// neighbourhood-conservation statistics of the Higgs-shape case) tightens neighbourhoods relative to the reference's
+// independent draws.
+__global__ void k_cell_sort_keys(uint64_t n, uint32_t n_cells, const uint32_t *__restrict__ cell_start,
+                                 const uint32_t *__restrict__ order, unsigned long long *__restrict__ key)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cell_of_node(n_cells, cell_start, (uint32_t)i);
+    key[i] = ((unsigned long long)c << 32) | mix32(order[i] * 0x9E3779B1u + 0x3C6EF372u);
+}
+// in-edge q (destination dst, source src) is external when src lies outside dst's cell
+__global__ void k_ext_flags(uint64_t cnt, uint64_t q_lo, const uint32_t *__restrict__ sorted_dst, const uint32_t *__restrict__ in_src,
+                            uint32_t n_cells, const uint32_t *__restrict__ cell_start, unsigned char *__restrict__ flag)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= cnt) return;
+    const uint32_t c = cell_of_node(n_cells, cell_start, sorted_dst[q_lo + q]);
+    const uint32_t src = in_src[q];
+    flag[q] = (src < cell_start[c] || src >= cell_start[c + 1]) ? 1 : 0;
+}
+// ext_ptr[c] = first entry of ext_slot (ascending slots, relative to in_base) at or after the cell's first in-edge
+__global__ void k_ext_ptr(uint32_t n_cells, const uint32_t *__restrict__ cell_start, const uint64_t *__restrict__ in_ptr_all,
+                          uint64_t in_base, uint64_t cnt, uint64_t ext_cnt, const uint32_t *__restrict__ ext_slot,
+                          uint64_t *__restrict__ ext_ptr)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    const uint64_t qa = in_ptr_all[cell_start[c]];
+    const uint64_t rel = qa <= in_base ? 0 : (qa - in_base >= cnt ? cnt : qa - in_base);
+    uint64_t a = 0, b = ext_cnt;                 // first x with ext_slot[x] >= rel
+    while (a < b) { const uint64_t mid = (a + b) >> 1; if ((uint64_t)ext_slot[mid] < rel) a = mid + 1; else b = mid; }
+    ext_ptr[c] = a;
+}
+// edges of the whole (relabelled) graph whose two ends lie in different cells
+__global__ void __launch_bounds__(256)
+k_count_cross_cell(uint64_t n, const uint64_t *__restrict__ row_ptr2, const uint32_t *__restrict__ col2, uint32_t n_cells,
+                   const uint32_t *__restrict__ cell_start, unsigned long long *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int c = 0;
+    if (i < n) {
+        const uint32_t cc = cell_of_node(n_cells, cell_start, (uint32_t)i);
+        const uint32_t a = cell_start[cc], b = cell_start[cc + 1];
+        for (uint64_t e = row_ptr2[i]; e < row_ptr2[i + 1]; e++) { const uint32_t j = col2[e]; c += (j < a || j >= b) ? 1u : 0u; }
+    }
+    typedef cub::BlockReduce<unsigned int, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const unsigned int tot = BR(tmp).Sum(c);
+    if (threadIdx.x == 0 && tot) atomicAdd(out, (unsigned long long)tot);
+}
+__global__ void k_cell_in_max(uint32_t cell_lo, uint32_t cell_hi, const uint32_t *__restrict__ cell_start,
+                              const uint64_t *__restrict__ in_ptr_all, unsigned int *__restrict__ out_max)
+{
+    const uint32_t c = cell_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cell_hi) return;
+    atomicMax(out_max, (unsigned int)(in_ptr_all[cell_start[c + 1]] - in_ptr_all[cell_start[c]]));
+}
+
 __global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint32_t *__restrict__ out)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -614,6 +708,8 @@ __device__ __forceinline__ int edge_of_firing(const uint32_t (&chb)[(KP + 3) / 4
     for (int w = 0; w < (KP + 3) / 4; w++) m += __popc((S - chb[w]) & 0x80808080u);
     return m;
 }
+
+#include "cell_epoch.cuh"     // the cell-resident form of K4 (uses edge_of_firing)
 
 template <int DP, bool HUB, int KP>
 __global__ void __launch_bounds__(EpochTile<DP, KP>::WARPS * 32, EpochTile<DP, KP>::MINB)
@@ -749,7 +845,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
             P.pe = F_SUB(P_hi, P_lo);
             load_row<DP>(a.y_snap, j, P.yj);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, node, (uint32_t)s, An, w4n, rejector(j), negs);
+            draw_negatives_v2<HUB>(a, a.epoch, node, (uint32_t)s, An, w4n, rejector(j), negs);
             P.use = 0;
 #pragma unroll
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
@@ -805,7 +901,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
             const Philox4 A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
             if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rejector(j), negs);
+            draw_negatives_v2<HUB>(a, a.epoch, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rejector(j), negs);
             apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
@@ -1167,7 +1263,7 @@ __global__ void k_debug_draws(EpochArgs a, uint32_t *__restrict__ counts, uint32
                 const Philox4 A = philox4x32_10(nk, s, a.epoch, 1u, a.k0, a.k1);
                 const Philox4 B = philox4x32_10(nk, s >> 2, a.epoch, 2u, a.k0, a.k1);
                 const GlobalRowRejector rej{a.col, r0, r1, (uint32_t)node, a.col[m]};
-                draw_negatives_v2<HUB>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
+                draw_negatives_v2<HUB>(a, a.epoch, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
             }
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) negs_out[5 * m + q] = negs[q];
         }
@@ -1230,7 +1326,7 @@ extern "C" int annembed_cuda_default_params(annembed_cuda_params *p)
     memset(p, 0, sizeof(*p));
     p->asked_dim = 2; p->dmap_init = 1; p->beta = 1.0; p->b = 1.0; p->scale_rho = 1.0; p->grad_step = 2.0;   // embedparams.rs:107-132
     p->nb_sampling_by_edge = 10; p->nb_grad_batch = 20; p->grad_factor = 4; p->hierarchy_layer = 0; p->hubness_weighting = 0;
-    p->mini_epochs_per_batch = 0; p->seed = 0x5eedULL; p->flags = 0;
+    p->mini_epochs_per_batch = 0; p->seed = 0x5eedULL; p->flags = 0; p->cell_substeps = 0;
     return ANNEMBED_OK;
 }
 
@@ -1282,6 +1378,7 @@ extern "C" int annembed_cuda_create(annembed_cuda_ctx **out, const annembed_cuda
     cudaDeviceGetAttribute(&ctx->l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, device);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    cudaDeviceGetAttribute(&ctx->smem_optin_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (ctx->l2_persist_max > 0 && !(ctx->prm.flags & ANNEMBED_FLAG_NO_L2_PERSIST))
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ctx->l2_persist_max);
     if ((e = ctx->partials.alloc(4096)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -1580,21 +1677,35 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
     return ANNEMBED_OK;
 }
 
-// Internal numbering of the nodes: identity (ANNEMBED_FLAG_NO_RELABEL, tiny graphs) or the nested min-label cells of
-// k_lp_round.  Graph only; built once per set_graph_csr.
+// Internal numbering of the nodes and its cells.
+//  1. locality order: identity (ANNEMBED_FLAG_NO_RELABEL, tiny graphs) or the nested min-label order of k_lp_round;
+//  2. cells: consecutive ranges of at most cell_nodes nodes of that order, starting at multiples of 32 (whole warp tiles),
+//     cut at the boundaries of the top-level label's segments where possible (a connected component of at most
+//     cell_nodes nodes is never split): greedy packing of the segments, on the host (the segment list is short);
+//  3. the order inside every cell is then randomised (k_cell_sort_keys explains why);
+//  4. ranks own whole cells (balanced node counts).  Cells do not depend on the number of ranks.
+// Graph only; built once per set_graph_csr.
 static int build_relabelling(annembed_cuda_ctx *ctx)
 {
     const uint64_t n = ctx->n;
     int rc;
+    const uint32_t CELL = ctx->cell_nodes = (uint32_t)(ctx->DP <= 2 ? CellCfg<2>::CELL : CellCfg<4>::CELL);
     CU(ctx->new_of_old.alloc(n)); CU(ctx->old_of_new.alloc(n));
     k_iota<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p);
     ctx->st.kernel_launches++;
-    if (!(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL) && n >= 1024) {
-        DevBuf<uint32_t> L[2], key, key_s, ord;
-        DevBuf<unsigned char> tmp;
+    std::vector<uint32_t> seg;                       // segment starts of the locality order (empty: none known)
+    const bool relabel = !(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL) && n >= 1024;
+    DevBuf<uint32_t> key, key_s, ord;
+    DevBuf<unsigned char> tmp;
+    size_t tmp_bytes = 0;
+    if (relabel) {
+        DevBuf<uint32_t> L[2];
         CU(L[0].alloc(n)); CU(L[1].alloc(n)); CU(key.alloc(n)); CU(key_s.alloc(n)); CU(ord.alloc(n));
-        size_t tmp_bytes = 0;
         CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key_s.p, ctx->old_of_new.p, ord.p, (int64_t)n, 0, 32, ctx->stream));
+        size_t tb2 = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb2, (unsigned long long *)nullptr, (unsigned long long *)nullptr, ctx->old_of_new.p, ord.p,
+                                           (int64_t)n, 0, 64, ctx->stream));
+        tmp_bytes = std::max(tmp_bytes, tb2);
         CU(tmp.alloc(tmp_bytes));
         k_lp_init<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, L[0].p);
         int cur = 0;
@@ -1607,19 +1718,79 @@ static int build_relabelling(annembed_cuda_ctx *ctx)
             if (round == 1 || round == 2 || round == 4 || round == 8) {
                 // stable sort of the current order by this level's label (least significant level first)
                 k_gather_u32<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, order, L[cur].p, key.p);
-                CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key_s.p, order, order2, (int64_t)n, 0, 32, ctx->stream));
+                size_t tb = tmp_bytes;
+                CU(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key_s.p, order, order2, (int64_t)n, 0, 32, ctx->stream));
                 std::swap(order, order2);
                 ctx->st.kernel_launches += 2;
             }
         }
         if (order != ctx->old_of_new.p)
             CU(cudaMemcpyAsync(ctx->old_of_new.p, order, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        // segments of the top-level label (key_s holds the sorted labels of the last pass)
+        DevBuf<unsigned char> flag; DevBuf<uint32_t> seg_d; DevBuf<unsigned long long> nsel;
+        CU(flag.alloc(n)); CU(seg_d.alloc(n)); CU(nsel.alloc(1));
+        k_seg_flags<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, key_s.p, flag.p);
+        size_t tb3 = 0;
+        thrust::counting_iterator<uint32_t> pos(0);
+        CU(cub::DeviceSelect::Flagged(nullptr, tb3, pos, flag.p, seg_d.p, nsel.p, (int64_t)n, ctx->stream));
+        DevBuf<unsigned char> tmp3; CU(tmp3.alloc(tb3));
+        CU(cub::DeviceSelect::Flagged(tmp3.p, tb3, pos, flag.p, seg_d.p, nsel.p, (int64_t)n, ctx->stream));
+        ctx->st.kernel_launches += 2;
+        unsigned long long nseg = 0;
+        CU(cudaMemcpyAsync(&nseg, nsel.p, sizeof(nseg), cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = sync_stream(ctx))) return rc;
+        if (nseg <= (4u << 20)) {                    // a longer list means no useful segment structure: fixed grid
+            seg.resize(nseg);
+            CU(cudaMemcpyAsync(seg.data(), seg_d.p, nseg * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if ((rc = sync_stream(ctx))) return rc;
+        }
+    }
+    // ---- cells: greedy packing of the segments (fixed grid when there is no segment list)
+    std::vector<uint32_t> &cs = ctx->cell_start_h;
+    cs.clear(); cs.push_back(0);
+    {
+        uint64_t cur = 0;
+        for (size_t i = 0; i < seg.size(); i++) {
+            const uint64_t s0 = seg[i], e0 = i + 1 < seg.size() ? seg[i + 1] : n;
+            if (e0 - cur <= CELL) continue;          // the segment fits in the open cell
+            const uint64_t c = s0 & ~31ull;          // close the open cell in front of it (whole tiles)
+            if (c > cur) { cs.push_back((uint32_t)c); cur = c; }
+            while (e0 - cur > CELL) { cur += CELL; cs.push_back((uint32_t)cur); }
+        }
+        while (n - cur > CELL) { cur += CELL; cs.push_back((uint32_t)cur); }
+        cs.push_back((uint32_t)n);
+    }
+    ctx->n_cells = (uint32_t)cs.size() - 1;
+    CU(ctx->cell_start.alloc(cs.size()));
+    CU(cudaMemcpyAsync(ctx->cell_start.p, cs.data(), cs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (relabel) {
+        // random order inside every cell: sort the positions by (cell, hash of the node)
+        DevBuf<unsigned long long> k64, k64s;
+        CU(k64.alloc(n)); CU(k64s.alloc(n));
+        k_cell_sort_keys<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->n_cells, ctx->cell_start.p, ctx->old_of_new.p, k64.p);
+        size_t tb = tmp_bytes;
+        CU(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k64.p, k64s.p, ctx->old_of_new.p, ord.p, (int64_t)n, 0, 64, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->old_of_new.p, ord.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->st.kernel_launches += 2;
         if ((rc = sync_stream(ctx))) return rc;     // the scratch buffers are released on return
     }
     k_invert_perm<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->new_of_old.p);
     ctx->st.kernel_launches++;
+    // ---- shards: whole cells, balanced by node count
+    ctx->shard_lo.assign(ctx->nranks + 1, (uint32_t)n);
+    std::vector<uint32_t> shard_cell(ctx->nranks + 1, ctx->n_cells);
+    shard_cell[0] = 0; ctx->shard_lo[0] = 0;
+    for (int r = 1; r < ctx->nranks; r++) {
+        const uint64_t target = n * (uint64_t)r / (uint64_t)ctx->nranks;
+        uint32_t c = (uint32_t)(std::lower_bound(cs.begin(), cs.end(), (uint32_t)target) - cs.begin());
+        c = std::max(c, shard_cell[r - 1]);
+        c = std::min(c, ctx->n_cells);
+        shard_cell[r] = c; ctx->shard_lo[r] = cs[c];
+    }
+    ctx->cell_lo = shard_cell[ctx->rank]; ctx->cell_hi = shard_cell[ctx->rank + 1];
+    ctx->lo = ctx->shard_lo[ctx->rank]; ctx->hi = ctx->shard_lo[ctx->rank + 1];
     CU(cudaGetLastError());
-    return ANNEMBED_OK;
+    return sync_stream(ctx);
 }
 
 // device context build, graph part (≙ nothing in the reference: its symmetric move writes y_j under a lock,
@@ -1677,16 +1848,52 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
     // rows of the tiled kernels (rows of at most 16 neighbours): padded length, slot map, byte map of firing counts
     ctx->KP = ctx->kmax <= 6 ? 6 : (ctx->kmax <= 8 ? 8 : (ctx->kmax <= 10 ? 10 : (ctx->kmax <= 16 ? 16 : 0)));
     ctx->rowpack.release(); ctx->erank.release(); ctx->fired.release();
+    ctx->ext_ptr.release(); ctx->ext_slot.release(); ctx->ext_cnt = 0; ctx->cell_map_bytes = 0;
     if (ctx->KP) {
-        CU(ctx->rowpack.alloc(n * (uint64_t)ctx->KP));
-        if (ctx->nranks == 1) {
-            CU(ctx->erank.alloc(n * (uint64_t)ctx->KP));
-            CU(ctx->fired.alloc(E + 64));
-            CU(cudaMemsetAsync(ctx->fired.p, 0, E + 64, ctx->stream));
-            CU(cudaMemsetAsync(ctx->erank.p, 0xff, n * (uint64_t)ctx->KP * sizeof(uint32_t), ctx->stream));
+        // + 32 nodes of padding: the cell kernel copies whole tiles (TMA bulk copies) even for the last, partial one
+        CU(ctx->rowpack.alloc((n + 32) * (uint64_t)ctx->KP));
+        CU(ctx->erank.alloc((n + 32) * (uint64_t)ctx->KP));
+        CU(cudaMemsetAsync(ctx->rowpack.p, 0xff, (n + 32) * (uint64_t)ctx->KP * sizeof(uint2), ctx->stream));
+        CU(cudaMemsetAsync(ctx->erank.p, 0xff, (n + 32) * (uint64_t)ctx->KP * sizeof(uint32_t), ctx->stream));
+        if (cnt) {
             k_erank<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(cnt, qr[0], ctx->KP, ctx->in_src.p, ctx->in_eid.p, ctx->row_ptr2.p, ctx->erank.p);
             ctx->st.kernel_launches++;
         }
+        if (ctx->nranks == 1) {
+            CU(ctx->fired.alloc(E + 64));
+            CU(cudaMemsetAsync(ctx->fired.p, 0, E + 64, ctx->stream));
+        }
+        // cell kernel: in-edges whose source lies outside the destination's cell, grouped by cell; largest byte map
+        CU(ctx->ext_ptr.alloc((uint64_t)ctx->n_cells + 1));
+        CU(ctx->ext_slot.alloc(std::max<uint64_t>(cnt, 1)));
+        if (cnt) {
+            DevBuf<unsigned char> flag, tmp2; DevBuf<unsigned long long> nsel;
+            CU(flag.alloc(cnt)); CU(nsel.alloc(1));
+            k_ext_flags<<<nblocks(cnt, 256), 256, 0, ctx->stream>>>(cnt, qr[0], dst_sorted.p, ctx->in_src.p, ctx->n_cells, ctx->cell_start.p, flag.p);
+            size_t tb = 0;
+            thrust::counting_iterator<uint32_t> pos(0);
+            CU(cub::DeviceSelect::Flagged(nullptr, tb, pos, flag.p, ctx->ext_slot.p, nsel.p, (int64_t)cnt, ctx->stream));
+            CU(tmp2.alloc(tb));
+            CU(cub::DeviceSelect::Flagged(tmp2.p, tb, pos, flag.p, ctx->ext_slot.p, nsel.p, (int64_t)cnt, ctx->stream));
+            unsigned long long nx = 0;
+            CU(cudaMemcpyAsync(&nx, nsel.p, sizeof(nx), cudaMemcpyDeviceToHost, ctx->stream));
+            if ((rc = sync_stream(ctx))) return rc;
+            ctx->ext_cnt = nx;
+            ctx->st.kernel_launches += 2;
+        }
+        k_ext_ptr<<<nblocks((uint64_t)ctx->n_cells + 1, 256), 256, 0, ctx->stream>>>(ctx->n_cells, ctx->cell_start.p, ctx->in_ptr_all.p, qr[0], cnt,
+                                                                                   ctx->ext_cnt, ctx->ext_slot.p, ctx->ext_ptr.p);
+        // whole-graph figures (identical on every rank: they decide the kernel and the launch length)
+        unsigned long long zero2[2] = {0ull, 0ull}, res2[2] = {0ull, 0ull};
+        CU(cudaMemcpyAsync(ctx->errword.p, zero2, sizeof(zero2), cudaMemcpyHostToDevice, ctx->stream));
+        k_cell_in_max<<<nblocks(ctx->n_cells, 256), 256, 0, ctx->stream>>>(0, ctx->n_cells, ctx->cell_start.p, ctx->in_ptr_all.p,
+                                                                        (unsigned int *)ctx->errword.p);
+        k_count_cross_cell<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->row_ptr2.p, ctx->col2.p, ctx->n_cells, ctx->cell_start.p, ctx->errword.p + 1);
+        CU(cudaMemcpyAsync(res2, ctx->errword.p, sizeof(res2), cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = sync_stream(ctx))) return rc;
+        ctx->cell_map_bytes = ((unsigned int)res2[0] + 15u) / 16u * 16u + 16u;
+        ctx->ext_cnt_global = res2[1];
+        ctx->st.kernel_launches += 3;
     }
     if ((rc = sync_stream(ctx))) return rc;
     ctx->have_struct = true;
@@ -1708,7 +1915,7 @@ static int ensure_build(annembed_cuda_ctx *ctx)
         const uint64_t n = ctx->n, E = ctx->E;
         CU(cudaEventRecord(ctx->ev_a, ctx->stream));
         if ((rc = ensure_struct(ctx))) return rc;
-        if (ctx->emb_scale.n != n) { CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); CU(ctx->inv_s2n.alloc(n)); }
+        if (ctx->emb_scale.n != n) { CU(ctx->emb_scale.alloc(n)); CU(ctx->inv_s2.alloc(n)); CU(ctx->inv_s2n.alloc(n + 32)); CU(cudaMemsetAsync(ctx->inv_s2n.p, 0, (n + 32) * sizeof(float), ctx->stream)); }
         if (ctx->cum.n != E) CU(ctx->cum.alloc(E));
         k_row_cumsum<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->row_ptr.p, ctx->proba.p, ctx->row_ptr2.p, ctx->cum.p);
         ctx->st.kernel_launches++;
@@ -2185,6 +2392,9 @@ static uint32_t first_epoch_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter
     return e;
 }
 
+#ifndef ANNEMBED_CELL_SUBSTEPS_LOCAL
+#define ANNEMBED_CELL_SUBSTEPS_LOCAL 16   // sub-steps per launch when (nearly) every edge has both ends in one cell
+#endif
 #ifndef ANNEMBED_FUSED_CHUNKS
 #define ANNEMBED_FUSED_CHUNKS 1   // >1 staggers sub-ranges on two streams (measured: no gain at 8 GPUs, profiles/r01_bench_8gpu_*)
 #endif
@@ -2352,6 +2562,76 @@ static int rank_barrier(annembed_cuda_ctx *ctx)
     return ANNEMBED_OK;
 }
 
+// ---- the cell-resident form of K4 (cell_epoch.cuh) ---------------------------------------------------------------
+static size_t cell_smem_bytes(const annembed_cuda_ctx *ctx)
+{
+    constexpr int W = ANNEMBED_CELL_THREADS / 32;
+    size_t fixed;
+    if (ctx->DP <= 2) fixed = ctx->KP == 6 ? cell_smem_fixed_bytes<2, 6>(W) : (ctx->KP == 8 ? cell_smem_fixed_bytes<2, 8>(W) : cell_smem_fixed_bytes<2, 16>(W));
+    else fixed = ctx->KP == 6 ? cell_smem_fixed_bytes<4, 6>(W) : (ctx->KP == 8 ? cell_smem_fixed_bytes<4, 8>(W) : cell_smem_fixed_bytes<4, 16>(W));
+    return fixed + ctx->cell_map_bytes;
+}
+// The cell kernel serves what the tiled pair serves (b == 1, rows of at most 16 neighbours, byte firing counts) for
+// layouts of dimension <= 4, when the largest in-edge byte map of a cell fits in shared memory beside the positions.
+static bool use_cells(const annembed_cuda_ctx *ctx, float kappa)
+{
+    if (ctx->prm.flags & (ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL | ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS | ANNEMBED_FLAG_REPLAY_IN_EDGES)) return false;
+    if (ctx->prm.b != 1.0 || ctx->KP == 0 || ctx->DP > 4 || !(kappa + 2.0f < (float)EpochTile<2, 6>::MAX_FIRINGS)) return false;
+    return cell_smem_bytes(ctx) <= (size_t)ctx->smem_optin_max;
+}
+// Sub-steps (mini-epochs) per launch.  Inside a launch the partners of the same cell are read at their current
+// positions; partners in other cells and the negatives are as old as the launch.  With every edge inside its cell a
+// whole batch can run in one launch; the more in-edges cross cells, the shorter the launches.
+static uint32_t cell_substeps(const annembed_cuda_ctx *ctx, uint32_t M)
+{
+    uint32_t S = ctx->prm.cell_substeps;
+    if (S == 0) {
+        const double f = ctx->E ? (double)ctx->ext_cnt_global / (double)ctx->E : 0.0;
+        S = f <= 0.01 ? ANNEMBED_CELL_SUBSTEPS_LOCAL : (f <= 0.10 ? 4u : (f <= 0.30 ? 2u : 1u));
+    }
+    return std::max(1u, std::min(std::min(S, M), (uint32_t)ANNEMBED_CELL_MAX_SUBSTEPS));
+}
+
+template <int DP, bool HUB, int KP>
+static cudaError_t launch_cells_kp(annembed_cuda_ctx *ctx, const CellArgs &A)
+{
+    const size_t smem = cell_smem_bytes(ctx);
+    cudaError_t e = cudaFuncSetAttribute(k_cell_epochs<DP, HUB, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_cell_epochs<DP, HUB, KP><<<ctx->cell_hi - ctx->cell_lo, ANNEMBED_CELL_THREADS, smem, ctx->launch_stream>>>(A, ctx->counter.p);
+    return cudaGetLastError();
+}
+template <int DP, bool HUB>
+static cudaError_t launch_cells_dp(annembed_cuda_ctx *ctx, const CellArgs &A)
+{
+    switch (ctx->KP) {
+    case 6: return launch_cells_kp<DP, HUB, 6>(ctx, A);
+    case 8: return launch_cells_kp<DP, HUB, 8>(ctx, A);
+    case 10: return launch_cells_kp<DP, HUB, 10>(ctx, A);
+    default: return launch_cells_kp<DP, HUB, 16>(ctx, A);
+    }
+}
+static cudaError_t launch_cells(annembed_cuda_ctx *ctx, const CellArgs &A, bool hub)
+{
+    if (ctx->cell_hi <= ctx->cell_lo) return cudaSuccess;
+    if (ctx->DP <= 2) return hub ? launch_cells_dp<2, true>(ctx, A) : launch_cells_dp<2, false>(ctx, A);
+    return hub ? launch_cells_dp<4, true>(ctx, A) : launch_cells_dp<4, false>(ctx, A);
+}
+
+// replicate the rows every rank owns (rank-dependent counts): one broadcast per rank, grouped
+static int exchange_rows_nccl(annembed_cuda_ctx *ctx, float *buf)
+{
+    ncclResult_t r = g_nccl.GroupStart();
+    for (int k = 0; k < ctx->nranks && r == ncclSuccess; k++) {
+        const size_t off = (size_t)ctx->shard_lo[k] * ctx->DP, cnt = (size_t)(ctx->shard_lo[k + 1] - ctx->shard_lo[k]) * ctx->DP;
+        if (cnt) r = g_nccl.Broadcast(buf + off, buf + off, cnt, ncclFloat, k, ctx->comm, ctx->stream);
+    }
+    const ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) { ctx->err = std::string("ncclBroadcast (row exchange): ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+    return ANNEMBED_OK;
+}
+
 extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t first_batch, uint32_t n_batches)
 {
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
@@ -2366,7 +2646,12 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     const uint32_t nb = ctx->prm.nb_grad_batch;
     const uint32_t last = std::min<uint64_t>((uint64_t)first_batch + n_batches, (uint64_t)nb + 1);   // exclusive
     size_t n_launch = 0;
-    for (uint32_t iter = first_batch; iter < last; iter++) n_launch += mini_epochs_of_batch(ctx, iter);
+    for (uint32_t iter = first_batch; iter < last; iter++) {
+        const uint32_t M = mini_epochs_of_batch(ctx, iter);
+        const float kappa = (float)((double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)ctx->n) / (double)M);
+        const uint32_t S = use_cells(ctx, kappa) ? cell_substeps(ctx, M) : 1u;
+        n_launch += (M + S - 1) / S;
+    }
     while (ctx->ev.size() < 2 * n_launch + 2 * n_launch * (ctx->nranks > 1)) {
         cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
     }
@@ -2380,35 +2665,51 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     ctx->st.kernel_launches++;
     if (ctx->nranks > 1 && ctx->have_peers && (rc = rank_barrier(ctx))) return rc;    // every replica holds the snapshot
     size_t li = 0;
+    ctx->last_substeps = 0;
     const size_t xoff = 2 * n_launch;
     size_t n_kernels = 0;
     for (uint32_t iter = first_batch; iter < last; iter++) {
         const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
         const uint32_t M = mini_epochs_of_batch(ctx, iter), e0 = first_epoch_of_batch(ctx, iter);
-        for (uint32_t m = 0; m < M; m++, li++) {
+        uint32_t S = 1;
+        {
+            const EpochArgs probe = make_epoch_args(ctx, e0, grad_step, M);
+            if (use_cells(ctx, probe.kappa)) S = cell_substeps(ctx, M);
+        }
+        for (uint32_t m = 0; m < M; m += S, li++) {
             EpochArgs a = make_epoch_args(ctx, e0 + m, grad_step, M);
-            // the fused exchange lives in the tiled in-edge kernel: the same predicate picks the kernel and the exchange
-            const bool fused = ctx->nranks > 1 && ctx->have_peers && use_tiled(ctx, a.kappa);
+            const bool cells = use_cells(ctx, a.kappa);
+            // the fused exchange lives in the tiled in-edge kernel / the cell kernel: the same predicate picks both
+            const bool fused = ctx->nranks > 1 && ctx->have_peers && (cells || use_tiled(ctx, a.kappa));
             if (fused) {
                 for (int r = 0; r < ctx->nranks; r++)
                     if (r != ctx->rank) a.peer_next[a.n_peers++] = ctx->peer_y[r][ctx->cur ^ 1];
             }
             set_l2_window(ctx, a.y_snap, (size_t)ctx->n * ctx->DP * sizeof(float));
             CU(cudaEventRecord(ctx->ev[2 * li], ctx->stream));
-            CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
-            n_kernels += ctx->last_epoch_kernels;
+            if (cells) {
+                CellArgs A;
+                A.e = a;
+                A.e.in_ptr = ctx->in_ptr_all.p;                // indexed by node id
+                A.e.fired = nullptr;
+                A.cell_start = ctx->cell_start.p; A.cell_lo = ctx->cell_lo;
+                A.substeps = std::min(S, M - m);
+                A.ext_ptr = ctx->ext_ptr.p; A.ext_slot = ctx->ext_slot.p;
+                CU(launch_cells(ctx, A, hub));
+                n_kernels += 1;
+                ctx->last_substeps = S;
+            } else {
+                CU(hub ? launch_epoch<true>(ctx, a) : launch_epoch<false>(ctx, a));
+                n_kernels += ctx->last_epoch_kernels;
+            }
             CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
             if (ctx->nranks > 1) {
                 CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
                 if (fused) {
-                    // the in-edge kernel already stored the owned rows into every replica: only a barrier is left
+                    // the kernel already stored the owned rows into every replica: only a barrier is left
                     if ((rc = rank_barrier(ctx))) return rc;
                 } else {
-                    // replicate the updated rows: in-place all-gather of the owned slice of y_next
-                    float *buf = ctx->y[ctx->cur ^ 1].p;
-                    const size_t cnt = (size_t)ctx->n_pad * ctx->DP;
-                    ncclResult_t r = g_nccl.AllGather(buf + (size_t)ctx->rank * cnt, buf, cnt, ncclFloat, ctx->comm, ctx->stream);
-                    if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+                    if ((rc = exchange_rows_nccl(ctx, ctx->y[ctx->cur ^ 1].p))) return rc;
                 }
                 CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream));
             }
@@ -2508,6 +2809,10 @@ extern "C" int annembed_cuda_get_stats(annembed_cuda_ctx *ctx, annembed_cuda_sta
     stats->mini_epochs_per_batch = ctx->have_graph ? eff_mini_epochs(ctx) : ctx->prm.mini_epochs_per_batch;
     stats->l2_persist_max_bytes = (uint64_t)std::max(ctx->l2_persist_max, 0);
     stats->l2_window_max_bytes = (uint64_t)std::max(ctx->l2_window_max, 0);
+    stats->n_cells = ctx->have_struct ? ctx->n_cells : 0;
+    stats->cell_nodes = ctx->cell_nodes;
+    stats->cell_substeps = ctx->last_substeps;
+    stats->cross_cell_edges = ctx->have_struct ? ctx->ext_cnt_global : 0;
     return ANNEMBED_OK;
 }
 extern "C" int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx)

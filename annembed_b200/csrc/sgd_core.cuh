@@ -350,7 +350,7 @@ __host__ __device__ __forceinline__ uint32_t neg_stream_key(const EpochArgs &a, 
 }
 
 template <bool HUB, class Rej>
-__host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t node, uint32_t s, const Philox4 &A,
+__host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t epoch, uint32_t node, uint32_t s, const Philox4 &A,
                                                            uint32_t w4, const Rej &rejected,
                                                            uint32_t (&negs)[ANNEMBED_NB_NEG])
 {
@@ -358,8 +358,8 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
     uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
     if constexpr (HUB) {
         const uint32_t gk = neg_stream_key<HUB>(a, node);
-        const Philox4 C = philox4x32_10(gk, s, a.epoch, 3u, a.k0, a.k1);
-        const Philox4 D = philox4x32_10(gk, s >> 2, a.epoch, 4u, a.k0, a.k1);
+        const Philox4 C = philox4x32_10(gk, s, epoch, 3u, a.k0, a.k1);
+        const Philox4 D = philox4x32_10(gk, s >> 2, epoch, 4u, a.k0, a.k1);
         wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = philox_word(D, s & 3u);
     }
     const uint32_t nsec = (a.n + 3u) >> 2;
@@ -386,7 +386,7 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
             uint32_t k = negs[q];
             bool r = rej[q];
             for (uint32_t t = 0; r && t < ANNEMBED_MAX_REDRAW; t++) {
-                const Philox4 R = philox4x32_10(node, s, a.epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
+                const Philox4 R = philox4x32_10(node, s, epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
                 k = map_negative<HUB>(a, R.x, R.y);
                 r = rejected(k);
             }
@@ -423,12 +423,33 @@ __host__ __device__ __forceinline__ void apply_firing(const EpochArgs &a, uint32
     }
 }
 
+// rows of the layout as a mini-epoch sees them: the global snapshot, or (cell-resident kernel, cell_epoch.cuh) the current
+// positions of the node's own cell for the nodes of that cell and the snapshot for all the others
+struct SnapshotRows {
+    const float *__restrict__ y_snap;
+    template <int DP>
+    __host__ __device__ __forceinline__ void load(uint32_t idx, float (&v)[DP]) const { load_row<DP>(y_snap, idx, v); }
+};
+struct CellRows {
+    const float *__restrict__ y_snap;
+    const float *__restrict__ ycur;     // rows c0 .. c0 + csize of the current sub-step
+    uint32_t c0, csize;
+    template <int DP>
+    __host__ __device__ __forceinline__ void load(uint32_t idx, float (&v)[DP]) const
+    {
+        const uint32_t loc = idx - c0;
+        if (loc < csize) load_row<DP>(ycur, loc, v);
+        else load_row<DP>(y_snap, idx, v);
+    }
+};
+
 // in_rec: {src node, bits(P_lo), bits(P_hi), bits(inv_s2[src])}; p_e is taken as P_hi - P_lo on both sides.
-template <int DP, bool HUB, bool B1 = false>
-__host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &a, uint32_t node)
+// a.in_ptr is indexed by (node - a.lo).  The result is returned in `y` (not stored).
+template <int DP, bool HUB, bool B1, class Rows>
+__host__ __device__ __forceinline__ unsigned int epoch_node_rows(const EpochArgs &a, uint32_t node, const Rows &rows, float (&y)[DP])
 {
-    float y[DP], g[DP];
-    load_row<DP>(a.y_snap, node, y);
+    float g[DP];
+    rows.template load<DP>(node, y);
     const float inv_s2 = a.inv_s2[node];
     const uint64_t r0 = a.row_ptr[node], r1 = a.row_ptr[node + 1];
     const float u = node_uniform(node, a.ukey);
@@ -445,14 +466,14 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
         if (c <= 0) continue;
         const uint32_t j = a.col[m];
         float yj[DP];
-        load_row<DP>(a.y_snap, j, yj);
+        rows.template load<DP>(j, yj);
         const GlobalRowRejector rej{a.col, r0, r1, node, j};
         for (int f = 0; f < c; f++, s++) {
             const uint32_t nk = neg_stream_key<HUB>(a, node);
             const Philox4 A = philox4x32_10(nk, s, a.epoch, 1u, a.k0, a.k1);
             const Philox4 B = philox4x32_10(nk, s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, node, s, A, philox_word(B, s & 3u), rej, negs);
+            draw_negatives_v2<HUB>(a, a.epoch, node, s, A, philox_word(B, s & 3u), rej, negs);
             apply_firing<DP, B1>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
@@ -468,10 +489,19 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &
         const int c = cum_ceil(a.kappa, Ph, us) - cum_ceil(a.kappa, Pl, us);
         if (c <= 0) continue;
         float ys[DP];
-        load_row<DP>(a.y_snap, rec.x, ys);
+        rows.template load<DP>(rec.x, ys);
         const float coef = attract_coeff<B1>(sqdist<DP>(yref, ys), F_SUB(Ph, Pl), as_float(rec.w), a.K);
         apply_in_edge<DP>(y, ys, in_edge_factor(coef, c));
     }
+    return s;
+}
+
+template <int DP, bool HUB, bool B1 = false>
+__host__ __device__ __forceinline__ unsigned int epoch_node_v2(const EpochArgs &a, uint32_t node)
+{
+    float y[DP];
+    const SnapshotRows rows{a.y_snap};
+    const unsigned int s = epoch_node_rows<DP, HUB, B1>(a, node, rows, y);
     store_row<DP>(a.y_next, node, y);
     return s;
 }

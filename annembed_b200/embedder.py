@@ -23,7 +23,7 @@ def _c_params(p: EmbedderParams) -> Params:
                   grad_step=p.grad_step, nb_sampling_by_edge=p.nb_sampling_by_edge, nb_grad_batch=p.nb_grad_batch,
                   grad_factor=p.grad_factor, hierarchy_layer=p.hierarchy_layer,
                   hubness_weighting=int(p.hubness_weighting), mini_epochs_per_batch=p.mini_epochs_per_batch,
-                  seed=p.seed, flags=p.flags, reserved=0)
+                  seed=p.seed, flags=p.flags, cell_substeps=p.cell_substeps)
 
 
 class CudaContext:

@@ -8,6 +8,7 @@ FLAG_GENERIC_EPOCH_KERNEL = 1
 FLAG_NO_L2_PERSIST = 2
 FLAG_NO_RELABEL = 4
 FLAG_REPLAY_IN_EDGES = 8
+FLAG_LEGACY_EPOCH_KERNELS = 16
 
 
 @dataclass
@@ -27,6 +28,7 @@ class EmbedderParams:
     mini_epochs_per_batch: int = 0   # 0 -> graded schedule (finest: ceil(nb_sampling_by_edge / 0.15))
     seed: int = 0x5EED
     flags: int = 0
+    cell_substeps: int = 0           # cell-resident epoch kernel: mini-epochs per launch (0 -> from the cross-cell edge fraction)
 
     # setters/getters named as in embedparams.rs:151-183
     def set_dmap_init(self, val: bool): self.dmap_init = val

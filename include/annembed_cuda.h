@@ -57,11 +57,13 @@ typedef struct annembed_cuda_params {
     uint32_t hubness_weighting;    /* :102 default 0: negatives uniform; 1: alias over set_neg_weights */
     /* ---- device-side additions (no reference counterpart: its RNG is unseeded, embedder.rs:1182) ---- */
     uint32_t mini_epochs_per_batch;/* bulk-synchronous sub-steps per reference batch;
-                                      0 -> graded: ceil(nb_sampling_by_edge / 0.3) (0.3 samples per edge per sub-step)
-                                      in the last third of the batches, 2x / 4x fewer sub-steps in the 2nd / 1st third */
+                                      0 -> ceil(nb_sampling_by_edge / 0.15) (0.15 samples per edge per mini-epoch),
+                                      see eff_mini_epochs / mini_epochs_of_batch in annembed_cuda.cu */
     uint64_t seed;                 /* Philox4x32-10 key */
     uint32_t flags;                /* ANNEMBED_FLAG_* */
-    uint32_t reserved;
+    uint32_t cell_substeps;        /* cell-resident epoch kernel: mini-epochs per launch (partners in other cells and the
+                                      negatives are read from the layout as of the start of the launch);
+                                      0 -> chosen from the fraction of edges that cross cells */
 } annembed_cuda_params;
 
 #define ANNEMBED_FLAG_NONE 0u
@@ -70,6 +72,8 @@ typedef struct annembed_cuda_params {
 #define ANNEMBED_FLAG_NO_RELABEL 4u             /* keep the caller's node order inside the optimizer (no locality relabelling) */
 #define ANNEMBED_FLAG_REPLAY_IN_EDGES 8u        /* single rank: replay the sources' decisions in the in-edge kernel instead of
                                                    consuming the firing counts pushed by the out-edge kernel (cross-check) */
+#define ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS 16u  /* one launch of k_epoch_out + k_epoch_in per mini-epoch instead of the
+                                                   cell-resident kernel (cross-check; also what dimensions > 4 use) */
 
 typedef struct annembed_cuda_stats {
     double   edge_weights_ms;      /* K0+K1 device time, last call */
@@ -88,6 +92,10 @@ typedef struct annembed_cuda_stats {
     uint64_t mini_epochs_per_batch;/* the value in effect (resolved default) */
     uint64_t l2_persist_max_bytes; /* cudaDevAttrMaxPersistingL2CacheSize */
     uint64_t l2_window_max_bytes;  /* cudaDevAttrMaxAccessPolicyWindowSize */
+    uint64_t n_cells;              /* cells of the internal numbering (0 before the first optimize / cross_entropy) */
+    uint64_t cell_nodes;           /* largest cell size */
+    uint64_t cell_substeps;        /* mini-epochs per launch of the cell kernel in the last optimize (0: not used) */
+    uint64_t cross_cell_edges;     /* edges of the graph whose ends lie in different cells */
 } annembed_cuda_stats;
 
 typedef struct annembed_cuda_ctx annembed_cuda_ctx;

@@ -25,6 +25,7 @@ pub const ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL: u32 = 1;
 pub const ANNEMBED_FLAG_NO_L2_PERSIST: u32 = 2;
 pub const ANNEMBED_FLAG_NO_RELABEL: u32 = 4;
 pub const ANNEMBED_FLAG_REPLAY_IN_EDGES: u32 = 8;
+pub const ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS: u32 = 16;
 
 /// mirror of EmbedderParams (src/embedparams.rs:76-103) + the device-side knobs
 #[repr(C)]
@@ -44,7 +45,7 @@ pub struct annembed_cuda_params {
     pub mini_epochs_per_batch: u32,
     pub seed: u64,
     pub flags: u32,
-    pub reserved: u32,
+    pub cell_substeps: u32,
 }
 
 #[repr(C)]
@@ -66,6 +67,10 @@ pub struct annembed_cuda_stats {
     pub mini_epochs_per_batch: u64,
     pub l2_persist_max_bytes: u64,
     pub l2_window_max_bytes: u64,
+    pub n_cells: u64,
+    pub cell_nodes: u64,
+    pub cell_substeps: u64,
+    pub cross_cell_edges: u64,
 }
 
 /// ≙ the statistics logged by get_quality_estimate_from_edge_length (src/embedder.rs:620-753)

@@ -12,6 +12,7 @@ c4s : the same graph embedded in dimension 15
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 import workloads
 
@@ -26,7 +27,7 @@ def make_case(name: str, n: int | None = None, device: str | None = None) -> dic
     if name in ("c1", "c2"):
         n = n or 70000
         x, _ = workloads.gaussian_mixture(n, 784, seed=0, anisotropic=(name == "c2"))
-        idx, dist = workloads.knn_exact(x, 10, device=device)
+        idx, dist = workloads.knn_exact(x, 10, device=device, dtype=torch.float64, chunk=2048)   # fp64: the same lists on any device
         row_ptr, col, dist = workloads.csr_from_knn(idx, dist)
         y0 = workloads.pca_init(x, 2)
         params = dict(asked_dim=2, nb_grad_batch=30 if name == "c1" else 25, scale_rho=1.0, grad_step=1.0)

@@ -123,6 +123,77 @@ extern "C" int64_t hostsim_optimize(uint64_t n, uint32_t d, const uint64_t *row_
     return total;
 }
 
+
+// ---- the cell-resident form (annembed_b200/csrc/cell_epoch.cuh) replayed on the host: identity numbering, cells = a
+// fixed grid of `cell_nodes` nodes, S sub-steps per launch.  Inside a launch the nodes of a cell see the current
+// positions of their own cell; every other row (partners in other cells, negatives) is the layout at the launch start.
+template <int DP, bool HUB>
+static uint64_t run_cells(const EpochArgs &a0, uint32_t cell_nodes, uint32_t substeps, uint32_t k2)
+{
+    const uint32_t n = a0.n;
+    const int64_t ncell = (n + cell_nodes - 1) / cell_nodes;
+    uint64_t tot = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot)
+    for (int64_t c = 0; c < ncell; c++) {
+        const uint32_t c0 = (uint32_t)c * cell_nodes, csize = std::min<uint32_t>(cell_nodes, n - c0);
+        std::vector<float> cur((size_t)csize * DP), nxt((size_t)csize * DP);
+        memcpy(cur.data(), a0.y_snap + (size_t)c0 * DP, cur.size() * sizeof(float));
+        EpochArgs a = a0;
+        for (uint32_t sub = 0; sub < substeps; sub++) {
+            a.epoch = a0.epoch + sub;
+            a.ukey = epoch_ukey(a.epoch, k2);
+            const CellRows rows{a0.y_snap, cur.data(), c0, csize};
+            for (uint32_t i = 0; i < csize; i++) {
+                float y[DP];
+                tot += epoch_node_rows<DP, HUB, false>(a, c0 + i, rows, y);
+                for (int cc = 0; cc < DP; cc++) nxt[(size_t)i * DP + cc] = y[cc];
+            }
+            cur.swap(nxt);
+        }
+        memcpy(a0.y_next + (size_t)c0 * DP, cur.data(), cur.size() * sizeof(float));
+    }
+    return tot;
+}
+
+extern "C" int64_t hostsim_optimize_cells(uint64_t n, uint32_t d, const uint64_t *row_ptr, const uint32_t *col, const float *p,
+                                          const float *emb_scale, float *y, double b, double grad_step0, uint32_t nbs,
+                                          uint32_t nb_batch, uint32_t M, uint64_t seed, const uint32_t *neg_alias,
+                                          uint32_t first_batch, uint32_t n_batches, uint32_t cell_nodes, uint32_t S)
+{
+    const int DP = d <= 2 ? 2 : 4;
+    if (d > 4) return -1;
+    HostCtx h;
+    build(h, n, row_ptr, col, p, emb_scale);
+    std::vector<float> Y[2];
+    Y[0].assign(n * DP, 0.0f); Y[1].assign(n * DP, 0.0f);
+    for (uint64_t i = 0; i < n; i++) for (uint32_t c = 0; c < d; c++) Y[0][i * DP + c] = y[i * d + c];
+    int cur = 0;
+    const uint64_t E = row_ptr[n];
+    int64_t total = 0;
+    for (uint32_t iter = first_batch; iter < first_batch + n_batches && iter <= nb_batch; iter++) {
+        const double gs = grad_step0 * (1.0 - (double)iter / (double)nb_batch);
+        for (uint32_t m = 0; m < M; m += S) {
+            EpochArgs a;
+            memset(&a, 0, sizeof a);
+            a.y_snap = Y[cur].data(); a.y_next = Y[cur ^ 1].data();
+            a.row_ptr = row_ptr; a.col = col; a.p = p; a.inv_s2 = h.inv_s2.data();
+            a.in_ptr = h.in_ptr.data(); a.in_rec = h.in_rec.data(); a.in_base = 0;
+            a.neg_alias = (const uint2 *)neg_alias;
+            a.cum = h.cum.data(); a.k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+            a.n = (uint32_t)n; a.lo = 0; a.hi = (uint32_t)n;
+            a.epoch = (iter - 1) * M + m; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+            a.kappa = (float)((double)nbs * ((double)E / (double)n) / (double)M);
+            a.K.gamma = (float)gs; a.K.b = (float)b; a.K.two_b = (float)(2.0 * b); a.K.b_is_one = b == 1.0;
+            const uint32_t sub = std::min(S, M - m);
+            if (DP == 2) total += (int64_t)(neg_alias ? run_cells<2, true>(a, cell_nodes, sub, a.k2) : run_cells<2, false>(a, cell_nodes, sub, a.k2));
+            else total += (int64_t)(neg_alias ? run_cells<4, true>(a, cell_nodes, sub, a.k2) : run_cells<4, false>(a, cell_nodes, sub, a.k2));
+            cur ^= 1;
+        }
+    }
+    for (uint64_t i = 0; i < n; i++) for (uint32_t c = 0; c < d; c++) y[i * d + c] = Y[cur][i * DP + c];
+    return total;
+}
+
 // the draws of one mini-epoch (same contract as annembed_cuda_debug_draws; v2 sampler)
 extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *p, uint32_t nbs,
                               uint32_t M, uint64_t seed, uint32_t epoch, const uint32_t *neg_alias, uint32_t *counts,
@@ -158,8 +229,8 @@ extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_
                     const Philox4 A = philox4x32_10(nk, s, epoch, 1u, a.k0, a.k1);
                     const Philox4 B = philox4x32_10(nk, s >> 2, epoch, 2u, a.k0, a.k1);
                     const GlobalRowRejector rej{col, r0, r1, (uint32_t)node, col[m]};
-                    if (neg_alias) draw_negatives_v2<true>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
-                    else draw_negatives_v2<false>(a, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
+                    if (neg_alias) draw_negatives_v2<true>(a, a.epoch, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
+                    else draw_negatives_v2<false>(a, a.epoch, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
                 }
                 for (int q = 0; q < 5; q++) negs_out[5 * m + q] = negs[q];
             }

@@ -15,6 +15,7 @@ def lib():
         subprocess.check_call(["make", "-C", _HERE, "-s"])
         _LIB = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
         _LIB.hostsim_optimize.restype = C.c_int64
+        _LIB.hostsim_optimize_cells.restype = C.c_int64
     return _LIB
 
 
@@ -52,6 +53,24 @@ def optimize(row_ptr, col, p, emb_scale, y0, b=1.0, grad_step=2.0, nbs=10, nb_ba
                                   _p(emb_scale, C.c_float), _p(y, C.c_float), C.c_double(b), C.c_double(grad_step),
                                   C.c_uint32(nbs), C.c_uint32(nb_batch), C.c_uint32(M), C.c_uint64(seed),
                                   _p(neg_alias, C.c_uint32), C.c_uint32(first_batch), C.c_uint32(n_batches))
+    return y, int(done)
+
+
+def optimize_cells(row_ptr, col, p, emb_scale, y0, b=1.0, grad_step=2.0, nbs=10, nb_batch=20, M=10, seed=1, neg_alias=None,
+                   first_batch=1, n_batches=None, cell_nodes=4096, substeps=1):
+    """Host replay of the cell-resident epoch kernel (identity numbering, fixed grid of cells, `substeps` per launch)."""
+    row_ptr = np.ascontiguousarray(row_ptr, np.uint64); col = np.ascontiguousarray(col, np.uint32)
+    p = np.ascontiguousarray(p, np.float32); emb_scale = np.ascontiguousarray(emb_scale, np.float32)
+    y = np.array(y0, np.float32, order="C", copy=True)
+    n, d = y.shape
+    if n_batches is None:
+        n_batches = nb_batch
+    done = lib().hostsim_optimize_cells(C.c_uint64(n), C.c_uint32(d), _p(row_ptr, C.c_uint64), _p(col, C.c_uint32), _p(p, C.c_float),
+                                        _p(emb_scale, C.c_float), _p(y, C.c_float), C.c_double(b), C.c_double(grad_step),
+                                        C.c_uint32(nbs), C.c_uint32(nb_batch), C.c_uint32(M), C.c_uint64(seed),
+                                        _p(neg_alias, C.c_uint32), C.c_uint32(first_batch), C.c_uint32(n_batches),
+                                        C.c_uint32(cell_nodes), C.c_uint32(substeps))
+    assert done >= 0
     return y, int(done)
 
 

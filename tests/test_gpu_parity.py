@@ -246,8 +246,9 @@ def test_tiled_epoch_kernel_equals_generic_kernel(d, kmax, hub, M):
     y0 = np.random.default_rng(2).uniform(-1, 1, size=(5000, d)).astype(np.float32)
     outs = []
     for flags in (0, 1):                             # 1 = ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL
+        # cell_substeps=1: one mini-epoch per launch of the cell kernel, i.e. the generic kernel's global snapshots
         ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=3, grad_step=1.0, seed=5, flags=flags,
-                      hubness_weighting=hub, nb_sampling_by_edge=1, mini_epochs_per_batch=M)
+                      hubness_weighting=hub, nb_sampling_by_edge=1, mini_epochs_per_batch=M, cell_substeps=1)
         ctx.edge_weights(want_outputs=False)
         if hub:
             ctx.set_neg_weights(oracle.hubness_weights(row_ptr, col))

@@ -43,21 +43,24 @@ def gaussian_mixture(n: int, dim: int, n_clusters: int = 10, seed: int = 0, sub_
     return x.astype(np.float32), labels.astype(np.int32)
 
 
-def knn_exact(x, k: int, device: str | None = None, chunk: int = 4096) -> tuple[np.ndarray, np.ndarray]:
-    """Exact L2 kNN (self excluded), rows ascending.  Returns (idx int64 (n,k), dist float32 (n,k))."""
+def knn_exact(x, k: int, device: str | None = None, chunk: int = 4096, dtype=torch.float32) -> tuple[np.ndarray, np.ndarray]:
+    """Exact L2 kNN (self excluded), rows ascending.  Returns (idx int64 (n,k), dist float32 (n,k)).
+    dtype=torch.float64 makes the neighbour lists reproducible across devices (the fp32 GEMM form of the squared
+    distance loses ~1 unit in 1e7 to cancellation, enough to reorder near-ties of 784-dimensional points)."""
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
-    xt = torch.as_tensor(x, dtype=torch.float32, device=dev)
+    xt = torch.as_tensor(x, dtype=dtype, device=dev)
     n = xt.shape[0]
-    sq = (xt * xt).sum(1)
     idx_out = torch.empty((n, k), dtype=torch.int64, device=dev)
     d_out = torch.empty((n, k), dtype=torch.float32, device=dev)
+    xt = xt - xt.mean(0, keepdim=True)                    # distances are translation invariant; smaller cancellation
+    sq = (xt * xt).sum(1)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         d2 = sq[s:e, None] + sq[None, :] - 2.0 * (xt[s:e] @ xt.T)
         d2[torch.arange(e - s, device=dev), torch.arange(s, e, device=dev)] = float("inf")
         v, i = torch.topk(d2, k, dim=1, largest=False, sorted=True)
         idx_out[s:e] = i
-        d_out[s:e] = v.clamp_min_(0).sqrt_()
+        d_out[s:e] = v.clamp_min_(0).sqrt_().to(torch.float32)
     return idx_out.cpu().numpy(), d_out.cpu().numpy()
 
 
