@@ -810,32 +810,15 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         const int Tmax = __reduce_max_sync(0xffffffffu, T);
         const uint32_t r4 = (uint32_t)lane & 3u;
         Philox4 blk;
-        uint32_t bw = 0;                 // word r4 of the chunk's fifth-words block
         blk.x = blk.y = blk.z = blk.w = 0u;
         Philox4 An;
-        uint32_t w4n = 0;
         An.x = An.y = An.z = An.w = 0u;
-        auto fetch = [&](int s) {        // executed by the whole warp, s warp-uniform
-            if ((s & 3) == 0) {
-                const uint32_t c = (uint32_t)s >> 2;
-                if (Tmax - s <= 3) {
-                    const bool fifth = r4 == 3u;
-                    blk = philox4x32_10(nkey, fifth ? c : (uint32_t)s + r4, a.epoch, fifth ? 2u : 1u, a.k0, a.k1);
-                    // lane r keeps word r of the fifth-words block held by lane 3 (firings 4c .. 4c+2 only)
-                    const uint32_t b0 = __shfl_sync(0xffffffffu, blk.x, (lane & ~3) + 3);
-                    const uint32_t b1 = __shfl_sync(0xffffffffu, blk.y, (lane & ~3) + 3);
-                    const uint32_t b2 = __shfl_sync(0xffffffffu, blk.z, (lane & ~3) + 3);
-                    bw = r4 == 0u ? b0 : (r4 == 1u ? b1 : b2);
-                } else {
-                    blk = philox4x32_10(nkey, (uint32_t)s + r4, a.epoch, 1u, a.k0, a.k1);
-                    const Philox4 B5 = philox4x32_10(nkey, c, a.epoch, 2u, a.k0, a.k1);
-                    bw = philox_word(B5, r4);
-                }
-            }
+            auto fetch = [&](int s) {        // executed by the whole warp, s warp-uniform
+            if ((s & 3) == 0)             // lane r of an aligned group computes the block of firing s + r (shared stream)
+                blk = philox4x32_10(nkey, (uint32_t)s + r4, a.epoch, 1u, a.k0, a.k1);
             const int src = (lane & ~3) + (s & 3);
             An.x = __shfl_sync(0xffffffffu, blk.x, src); An.y = __shfl_sync(0xffffffffu, blk.y, src);
             An.z = __shfl_sync(0xffffffffu, blk.z, src); An.w = __shfl_sync(0xffffffffu, blk.w, src);
-            w4n = __shfl_sync(0xffffffffu, bw, src);
         };
         auto prepare = [&](int s, Pre &P) {
             const int m = edge_of_firing<KP>(chb, s);          // < row length because ch[last] == T > s
@@ -845,7 +828,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
             P.pe = F_SUB(P_hi, P_lo);
             load_row<DP>(a.y_snap, j, P.yj);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, a.epoch, node, (uint32_t)s, An, w4n, rejector(j), negs);
+            draw_negatives_v2<HUB>(a, a.epoch, node, (uint32_t)s, An, rejector(j), negs);
             P.use = 0;
 #pragma unroll
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
@@ -888,7 +871,6 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
         uint32_t j = 0;
         float pe = 0.0f;
         float yj[DP];
-        Philox4 B;
         for (int s = 0; s < T; s++) {
             const int m = edge_of_firing<KP>(chb, s);
             if (m != m_prev) {
@@ -899,9 +881,8 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
                 m_prev = m;
             }
             const Philox4 A = philox4x32_10(nkey, (uint32_t)s, a.epoch, 1u, a.k0, a.k1);
-            if ((s & 3) == 0) B = philox4x32_10(nkey, (uint32_t)s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, a.epoch, node, (uint32_t)s, A, philox_word(B, (uint32_t)s & 3u), rejector(j), negs);
+            draw_negatives_v2<HUB>(a, a.epoch, node, (uint32_t)s, A, rejector(j), negs);
             apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }
@@ -1261,9 +1242,8 @@ __global__ void k_debug_draws(EpochArgs a, uint32_t *__restrict__ counts, uint32
                 const uint32_t s = (uint32_t)c_lo;              // the node's firing index at which this edge first fires
                 const uint32_t nk = neg_stream_key<HUB>(a, (uint32_t)node);
                 const Philox4 A = philox4x32_10(nk, s, a.epoch, 1u, a.k0, a.k1);
-                const Philox4 B = philox4x32_10(nk, s >> 2, a.epoch, 2u, a.k0, a.k1);
                 const GlobalRowRejector rej{a.col, r0, r1, (uint32_t)node, a.col[m]};
-                draw_negatives_v2<HUB>(a, a.epoch, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
+                draw_negatives_v2<HUB>(a, a.epoch, (uint32_t)node, s, A, rej, negs);
             }
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) negs_out[5 * m + q] = negs[q];
         }
@@ -2357,32 +2337,35 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
     return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
 }
 
-// Mini-epochs per reference batch.  What governs the fidelity of the bulk-synchronous loop is how much of a batch is
-// applied against one snapshot, i.e. samples per edge per mini-epoch (nb_sampling_by_edge / M), not the node degree.
-// At 0.15 samples per edge per mini-epoch (M = 67 for the default 10 samples per edge) the layout statistics of the
-// BASELINE.json configs (70k MNIST / Fashion shapes, k = 10; 1M Higgs shape from a random start, k = 6, with and
-// without hubness; d = 15) are within 1 % of the serial reference's (tests/test_gpu_fidelity.py against
-// tests/golden/fidelity_*.json); at the 0.3 used in round 1 the Higgs-shape case was 4-8 % off
-// (tests/studies/fidelity_configs.py).  The statistics converge monotonically to the reference's as M grows.
-#ifndef ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH
-#define ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH 0.15
+// Mini-epochs per reference batch (mini_epochs_per_batch == 0: the default schedule).
+// What governs the fidelity of the bulk-synchronous loop is how much of a batch is applied against one snapshot, i.e.
+// samples per edge per mini-epoch (nb_sampling_by_edge / M).  Measured against the serial reference loop on the
+// BASELINE.json configs (tools/gpu_schedule_probe.py):
+//  * the neighbourhood statistics of the final layout (get_quality_estimate_from_edge_length, kNN preservation) are set by
+//    the LAST batches: with the last third at 0.075 samples per edge per mini-epoch they are within 1 % of the
+//    reference's whatever the first two thirds use (0.6 .. 0.15 samples per edge gave the same statistics);
+//  * the first two thirds only move the final cross entropy (coarser early mini-epochs end 10-17 % below the reference's).
+// The first two thirds run at kappa = 1 firing per node and mini-epoch (the coarsest level the event form of the cell
+// kernel serves, 0.17 samples per edge at k = 6), the last third at 0.075 samples per edge (and kappa <= 1).
+#ifndef ANNEMBED_SAMPLES_PER_EDGE_LATE
+#define ANNEMBED_SAMPLES_PER_EDGE_LATE 0.075
 #endif
-static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)
+static uint32_t mini_epochs_kappa_one(const annembed_cuda_ctx *ctx)
+{
+    const double deg = ctx->n ? (double)ctx->E / (double)ctx->n : 1.0;
+    return (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge * deg - 1e-9));
+}
+static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)           // the finest level of the schedule
 {
     if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;
-    return (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge / ANNEMBED_SAMPLES_PER_EDGE_PER_MINI_EPOCH));
+    const uint32_t late = (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge / ANNEMBED_SAMPLES_PER_EDGE_LATE));
+    return std::max(late, mini_epochs_kappa_one(ctx));
 }
-// Default (mini_epochs_per_batch == 0) schedule: graded.  The final statistics are set by the last, small-step batches
-// (tests/studies/adaptive_kappa_study.py: coarse-early / fine-late schedules land as close to the serial oracle as the
-// finest level throughout, fine-early / coarse-late ones do not), so the first third of the batches runs with 4x and
-// the second third with 2x fewer (larger) mini-epochs; an explicit mini_epochs_per_batch is used for every batch.
 static uint32_t mini_epochs_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter)
 {
-    const uint32_t base = eff_mini_epochs(ctx);
-    if (ctx->prm.mini_epochs_per_batch) return base;
+    if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;      // explicit: every batch
     const uint32_t nb = ctx->prm.nb_grad_batch;
-    const uint32_t div = (3 * iter <= nb) ? 4u : ((3 * iter <= 2 * nb) ? 2u : 1u);
-    return std::max(1u, (base + div - 1) / div);
+    return (3 * iter > 2 * nb) ? eff_mini_epochs(ctx) : mini_epochs_kappa_one(ctx);
 }
 // global index of the first mini-epoch of batch `iter` (counter word of the Philox streams)
 static uint32_t first_epoch_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter)
@@ -2563,21 +2546,24 @@ static int rank_barrier(annembed_cuda_ctx *ctx)
 }
 
 // ---- the cell-resident form of K4 (cell_epoch.cuh) ---------------------------------------------------------------
-static size_t cell_smem_bytes(const annembed_cuda_ctx *ctx)
+// shared memory of one launch; `events`: the event form of phase A (kappa <= 1), which has no staging buffers
+static size_t cell_smem_bytes(const annembed_cuda_ctx *ctx, bool events)
 {
-    constexpr int W = ANNEMBED_CELL_THREADS / 32;
+    const int W = (events ? ANNEMBED_CELL_THREADS_EVENTS : ANNEMBED_CELL_THREADS) / 32;
+    const int kp = events ? 32 : ctx->KP;
     size_t fixed;
-    if (ctx->DP <= 2) fixed = ctx->KP == 6 ? cell_smem_fixed_bytes<2, 6>(W) : (ctx->KP == 8 ? cell_smem_fixed_bytes<2, 8>(W) : cell_smem_fixed_bytes<2, 16>(W));
-    else fixed = ctx->KP == 6 ? cell_smem_fixed_bytes<4, 6>(W) : (ctx->KP == 8 ? cell_smem_fixed_bytes<4, 8>(W) : cell_smem_fixed_bytes<4, 16>(W));
-    return fixed + ctx->cell_map_bytes;
+    if (ctx->DP <= 2) fixed = kp == 6 ? cell_smem_fixed_bytes<2, 6>(W) : (kp == 8 ? cell_smem_fixed_bytes<2, 8>(W) : cell_smem_fixed_bytes<2, 16>(W));
+    else fixed = kp == 6 ? cell_smem_fixed_bytes<4, 6>(W) : (kp == 8 ? cell_smem_fixed_bytes<4, 8>(W) : cell_smem_fixed_bytes<4, 16>(W));
+    return fixed + (events ? ctx->cell_map_bytes / 8 + 32 : ctx->cell_map_bytes);   // bitmap / byte map of the firing counts
 }
+static bool cell_events(float kappa) { return kappa <= 1.0f; }
 // The cell kernel serves what the tiled pair serves (b == 1, rows of at most 16 neighbours, byte firing counts) for
 // layouts of dimension <= 4, when the largest in-edge byte map of a cell fits in shared memory beside the positions.
 static bool use_cells(const annembed_cuda_ctx *ctx, float kappa)
 {
     if (ctx->prm.flags & (ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL | ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS | ANNEMBED_FLAG_REPLAY_IN_EDGES)) return false;
     if (ctx->prm.b != 1.0 || ctx->KP == 0 || ctx->DP > 4 || !(kappa + 2.0f < (float)EpochTile<2, 6>::MAX_FIRINGS)) return false;
-    return cell_smem_bytes(ctx) <= (size_t)ctx->smem_optin_max;
+    return cell_smem_bytes(ctx, cell_events(kappa)) <= (size_t)ctx->smem_optin_max;
 }
 // Sub-steps (mini-epochs) per launch.  Inside a launch the partners of the same cell are read at their current
 // positions; partners in other cells and the negatives are as old as the launch.  With every edge inside its cell a
@@ -2595,10 +2581,18 @@ static uint32_t cell_substeps(const annembed_cuda_ctx *ctx, uint32_t M)
 template <int DP, bool HUB, int KP>
 static cudaError_t launch_cells_kp(annembed_cuda_ctx *ctx, const CellArgs &A)
 {
-    const size_t smem = cell_smem_bytes(ctx);
-    cudaError_t e = cudaFuncSetAttribute(k_cell_epochs<DP, HUB, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_cell_epochs<DP, HUB, KP><<<ctx->cell_hi - ctx->cell_lo, ANNEMBED_CELL_THREADS, smem, ctx->launch_stream>>>(A, ctx->counter.p);
+    const bool events = cell_events(A.e.kappa);
+    const size_t smem = cell_smem_bytes(ctx, events);
+    cudaError_t e;
+    if (events) {
+        e = cudaFuncSetAttribute(k_cell_epochs<DP, HUB, KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_cell_epochs<DP, HUB, KP, true><<<ctx->cell_hi - ctx->cell_lo, ANNEMBED_CELL_THREADS_EVENTS, smem, ctx->launch_stream>>>(A, ctx->counter.p);
+    } else {
+        e = cudaFuncSetAttribute(k_cell_epochs<DP, HUB, KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_cell_epochs<DP, HUB, KP, false><<<ctx->cell_hi - ctx->cell_lo, ANNEMBED_CELL_THREADS, smem, ctx->launch_stream>>>(A, ctx->counter.p);
+    }
     return cudaGetLastError();
 }
 template <int DP, bool HUB>

@@ -201,31 +201,15 @@ __device__ __forceinline__ unsigned int cell_phase_a(const EpochArgs &a, uint32_
     const int Tmax = __reduce_max_sync(0xffffffffu, T);
     const uint32_t r4 = (uint32_t)lane & 3u;
     Philox4 blk;
-    uint32_t bw = 0;
     blk.x = blk.y = blk.z = blk.w = 0u;
     Philox4 An;
-    uint32_t w4n = 0;
     An.x = An.y = An.z = An.w = 0u;
-    auto fetch = [&](int s) {
-        if ((s & 3) == 0) {
-            const uint32_t c = (uint32_t)s >> 2;
-            if (Tmax - s <= 3) {
-                const bool fifth = r4 == 3u;
-                blk = philox4x32_10(nkey, fifth ? c : (uint32_t)s + r4, epoch, fifth ? 2u : 1u, a.k0, a.k1);
-                const uint32_t b0 = __shfl_sync(0xffffffffu, blk.x, (lane & ~3) + 3);
-                const uint32_t b1 = __shfl_sync(0xffffffffu, blk.y, (lane & ~3) + 3);
-                const uint32_t b2 = __shfl_sync(0xffffffffu, blk.z, (lane & ~3) + 3);
-                bw = r4 == 0u ? b0 : (r4 == 1u ? b1 : b2);
-            } else {
-                blk = philox4x32_10(nkey, (uint32_t)s + r4, epoch, 1u, a.k0, a.k1);
-                const Philox4 B5 = philox4x32_10(nkey, c, epoch, 2u, a.k0, a.k1);
-                bw = philox_word(B5, r4);
-            }
-        }
+    auto fetch = [&](int s) {        // executed by the whole warp, s warp-uniform
+        if ((s & 3) == 0)             // lane r of an aligned group computes the block of firing s + r (shared stream)
+            blk = philox4x32_10(nkey, (uint32_t)s + r4, epoch, 1u, a.k0, a.k1);
         const int src = (lane & ~3) + (s & 3);
         An.x = __shfl_sync(0xffffffffu, blk.x, src); An.y = __shfl_sync(0xffffffffu, blk.y, src);
         An.z = __shfl_sync(0xffffffffu, blk.z, src); An.w = __shfl_sync(0xffffffffu, blk.w, src);
-        w4n = __shfl_sync(0xffffffffu, bw, src);
     };
     auto prepare = [&](int s, Pre &P) {
         const int m = edge_of_firing<KP>(chb, s);
@@ -235,7 +219,7 @@ __device__ __forceinline__ unsigned int cell_phase_a(const EpochArgs &a, uint32_
         P.pe = F_SUB(P_hi, P_lo);
         load_row_cell<DP>(ycur, c0, csize, a.y_snap, j, P.yj);
         uint32_t negs[ANNEMBED_NB_NEG];
-        draw_negatives_v2<HUB>(a, epoch, node, (uint32_t)s, An, w4n, rejected, negs);
+        draw_negatives_v2<HUB>(a, epoch, node, (uint32_t)s, An, rejected, negs);
         P.use = 0;
 #pragma unroll
         for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
@@ -275,6 +259,109 @@ __device__ __forceinline__ unsigned int cell_phase_a(const EpochArgs &a, uint32_
     return (unsigned int)T;
 }
 
+// ---- phase A, event form (kappa <= 1: a node fires at most once per sub-step) -------------------------------------------
+// At the fine levels of the schedule fewer than one node in two fires in a sub-step, so a warp that walks its nodes lane
+// by lane runs the 300 instructions of a firing for a half-empty warp, and pays the row handling for nodes that do
+// nothing.  Here the warp first DECIDES for a batch of 32 or 64 nodes (one hash and one compare per node: the row is
+// not needed for that), compacts the firing nodes into a list in shared memory (ballot + popc, node order), and then
+// runs the firings with lane = list entry.  Same draws, same arithmetic, same result as cell_phase_a.
+template <int DP, bool HUB, int KP>
+__device__ __forceinline__ unsigned int cell_phase_a_events(const EpochArgs &a, uint32_t epoch, uint32_t ukey, uint32_t ycur, uint32_t ymid,
+                                                            uint32_t fmap, uint32_t c0, uint32_t csize, uint64_t Q0, uint32_t n_in,
+                                                            uint32_t n0, uint32_t nb, uint32_t list, int lane)
+{
+    unsigned short *l_id = reinterpret_cast<unsigned short *>(cell_smem + list);          // [128] node - n0
+    float *l_u = reinterpret_cast<float *>(cell_smem + list + 256);                        // [128] the node's uniform
+    uint32_t cnt = 0;
+    for (uint32_t g = 0; g < nb; g += 32u) {
+        const uint32_t i = g + (uint32_t)lane;
+        const bool valid = i < nb;
+        float u = 2.0f;
+        bool fire = false;
+        if (valid) {
+            u = node_uniform(n0 + i, ukey);
+            fire = cum_ceil(a.kappa, 1.0f, u) > 0;               // the row's last cumulative probability is exactly 1
+            if (!fire) {                                          // nothing of its own: the position carries over to phase B
+                float y[DP];
+                load_row<DP>(cell_f(ycur), n0 - c0 + i, y);
+                store_row<DP>(cell_f(ymid), n0 - c0 + i, y);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, fire);
+        if (fire) {
+            const uint32_t e = cnt + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            l_id[e] = (unsigned short)i; l_u[e] = u;
+        }
+        cnt += (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    for (uint32_t e0 = 0; e0 < cnt; e0 += 32u) {
+        if (e0 + (uint32_t)lane >= cnt) continue;                 // no warp-wide operation below
+        const uint32_t node = n0 + l_id[e0 + lane];
+        const float u = l_u[e0 + lane];
+        uint32_t rc[KP];
+        float cm[KP];
+        const uint4 *rp = reinterpret_cast<const uint4 *>(a.rowpack + (size_t)node * KP);
+#pragma unroll
+        for (int h = 0; h < KP / 2; h++) {
+            const uint4 t = __ldg(rp + h);
+            rc[2 * h] = t.x; cm[2 * h] = __uint_as_float(t.y);
+            rc[2 * h + 1] = t.z; cm[2 * h + 1] = __uint_as_float(t.w);
+        }
+        const float inv_s2 = __ldg(a.inv_s2 + node);
+        float y[DP], g[DP], yj[DP];
+        load_row<DP>(cell_f(ycur), node - c0, y);
+        // the edge the single sample point lands on: the first whose count ceil(kappa P_m - u) is 1
+        int m = 0;
+        uint32_t j = rc[0];
+        float P_lo = 0.0f, P_hi = cm[0];
+        {
+            bool found = cum_ceil(a.kappa, cm[0], u) > 0;
+#pragma unroll
+            for (int mm = 1; mm < KP; mm++) {
+                const bool here = !found && cum_ceil(a.kappa, cm[mm], u) > 0;
+                m = here ? mm : m; j = here ? rc[mm] : j; P_hi = here ? cm[mm] : P_hi; P_lo = here ? cm[mm - 1] : P_lo;
+                found |= here;
+            }
+        }
+        {   // destination in this cell: push the count to its in-edge slot
+            const uint64_t loc = (uint64_t)__ldg(a.erank + (size_t)node * KP + m) - Q0;
+            if (loc < (uint64_t)n_in) atomicOr(reinterpret_cast<uint32_t *>(cell_smem + fmap) + ((uint32_t)loc >> 5), 1u << ((uint32_t)loc & 31u));
+        }
+        load_row_cell<DP>(ycur, c0, csize, a.y_snap, j, yj);
+        uint32_t id_lo = node, id_hi = node;
+#pragma unroll
+        for (int mm = 0; mm < KP; mm++) {
+            const uint32_t v = rc[mm] == ANNEMBED_NO_NODE ? node : rc[mm];
+            id_lo = min(id_lo, v); id_hi = max(id_hi, v);
+        }
+        const uint32_t id_span = id_hi - id_lo;
+        auto rejected = [&](uint32_t kk) -> bool {
+            bool r = false;
+            if (kk - id_lo <= id_span) {
+                r = (kk == node);
+#pragma unroll
+                for (int mm = 0; mm < KP; mm++) r |= (kk == rc[mm]);
+            }
+            return r;
+        };
+        const Philox4 An = philox4x32_10(neg_stream_key<HUB>(a, node), 0u, epoch, 1u, a.k0, a.k1);
+        uint32_t negs[ANNEMBED_NB_NEG];
+        draw_negatives_v2<HUB>(a, epoch, node, 0u, An, rejected, negs);
+        float yk[ANNEMBED_NB_NEG][DP];
+#pragma unroll
+        for (int q = 0; q < ANNEMBED_NB_NEG; q++) load_row<DP>(a.y_snap, negs[q] != ANNEMBED_NO_NODE ? negs[q] : node, yk[q]);
+#pragma unroll
+        for (int c = 0; c < DP; c++) g[c] = 0.0f;
+        attract<DP, true>(y, yj, g, F_SUB(P_hi, P_lo), inv_s2, a.K);
+#pragma unroll
+        for (int q = 0; q < ANNEMBED_NB_NEG; q++) repulse<DP, true>(y, yk[q], g, inv_s2, a.K, negs[q] != ANNEMBED_NO_NODE);
+        store_row<DP>(cell_f(ymid), node - c0, y);
+    }
+    __syncwarp();
+    return cnt;
+}
+
 // ---- phase B of one tile (lane = in-edge slot): the moves received through the in-edges -------------------------------
 // Same machinery as InWarp (annembed_cuda.cu): fired slots are compacted into a ring, a full warp of them is turned
 // into affine maps y -> (1+A) y - A y_src evaluated at the owner's position after phase A, composed per owner by a
@@ -304,17 +391,23 @@ struct CellInWarp {
     {
         const bool act = lane < cnt;
         const uint32_t e = (head + (uint32_t)lane) & (QCAP - 1);
+        uint32_t q = 0;
+        int c = 0;
+        if (act) { q = q_q(e); c = (int)q_c(e); }
+        dense_regs(act, q, c);
+    }
+
+    // lane = fired in-edge (slot q of the tile, c firings), in slot order; inactive lanes at the end
+    __device__ __forceinline__ void dense_regs(bool act, uint32_t q, int c)
+    {
         uint32_t own = 32u + (uint32_t)lane;
         float alpha = 1.0f, beta[DP];
 #pragma unroll
         for (int cc = 0; cc < DP; cc++) beta[cc] = 0.0f;
-        int c = 0;
         float pe = 0.0f, is2 = 0.0f, ys[DP];
 #pragma unroll
         for (int cc = 0; cc < DP; cc++) ys[cc] = 0.0f;
-        uint32_t q = 0;
         if (act) {
-            q = q_q(e); c = (int)q_c(e);
             const uint4 r = __ldg(rec0 + q);
             pe = F_SUB(__uint_as_float(r.z), __uint_as_float(r.y)); is2 = __uint_as_float(r.w);
             load_row_cell<DP>(ycur, c0, csize, a.y_snap, r.x, ys);
@@ -434,6 +527,82 @@ __device__ __forceinline__ void cell_phase_b(const EpochArgs &a, uint32_t ycur, 
     __syncwarp();
 }
 
+// ---- phase B, event form: with kappa <= 1 an edge fires at most once per sub-step, so the firing map is a BITMAP (one
+// bit per in-edge slot of the cell, set with shared-memory atomicOr by the sources).  A tile's ~200 slots are 7 words:
+// one load per lane, a warp scan of the popcounts, and lane k picks the k-th set bit with __fns -- the fired in-edges
+// come out in slot order, 32 at a time, straight into the dense stage (no byte sweep, no ring).
+template <int DP>
+__device__ __forceinline__ void cell_phase_b_bits(const EpochArgs &a, uint32_t ycur, uint32_t ymid, uint32_t fmap, uint32_t ring, uint32_t rel,
+                                                  uint32_t c0, uint32_t csize, uint64_t Q0, uint32_t n0, int lane)
+{
+    const uint32_t node = n0 + (uint32_t)lane;
+    const bool valid = node - c0 < csize;
+    const uint32_t nvalid = min(32u, c0 + csize - n0);
+    CellInWarp<DP> W(a, ycur, c0, csize, ring, lane);
+#pragma unroll
+    for (int c = 0; c < DP; c++) W.y[c] = 0.0f;
+    if (valid) load_row<DP>(cell_f(ymid), node - c0, W.y);
+    const uint32_t *relp = reinterpret_cast<const uint32_t *>(cell_smem + rel) + (n0 - c0);
+    const uint32_t my_q0 = relp[valid ? lane : 0];
+    const uint32_t Q1t = relp[nvalid];
+    const uint32_t Q0t = relp[0];
+    W.rel_lo = valid ? my_q0 - Q0t : 0xffffffffu;
+    const uint32_t n_in = Q1t - Q0t;
+    if (n_in == 0) return;
+    W.rec0 = a.in_rec + (Q0 + Q0t - a.in_base);
+    uint32_t *bm = reinterpret_cast<uint32_t *>(cell_smem + fmap);
+    W.t_alpha(lane) = 1.0f;
+#pragma unroll
+    for (int c = 0; c < DP; c++) W.t_beta(c, lane) = 0.0f;
+    __syncwarp();
+    const uint32_t w_first = Q0t >> 5, w_last = (Q1t - 1u) >> 5;          // words that hold the tile's bits
+    bool any = false;
+    for (uint32_t wb = w_first; wb <= w_last; wb += 32u) {                  // 32 words = 1024 slots per round (hubs: several)
+        const uint32_t w = wb + (uint32_t)lane;
+        uint32_t bits = 0;
+        if (w <= w_last) {
+            bits = bm[w];
+            if (w == w_first) bits &= 0xffffffffu << (Q0t & 31u);           // bits below / above belong to the neighbouring tiles
+            if (w == w_last) bits &= 0xffffffffu >> (31u - ((Q1t - 1u) & 31u));
+            if (bits) atomicAnd(bm + w, ~bits);                             // consumed
+        }
+        // inclusive scan of the popcounts over the lanes
+        const uint32_t pc = (uint32_t)__popc(bits);
+        uint32_t incl = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t k0 = 0; k0 < tot; k0 += 32u) {                        // entries k0 .. k0+31 of this round, in slot order
+            const uint32_t k = k0 + (uint32_t)lane;
+            const bool act = k < tot;
+            // the word that holds entry k: the first lane whose inclusive count exceeds k (binary search by shuffles)
+            int o = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, o + step - 1);
+                o += (v <= k) ? step : 0;
+            }
+            o = min(o, 31);
+            const uint32_t wbits = __shfl_sync(0xffffffffu, bits, o);
+            const uint32_t before = __shfl_sync(0xffffffffu, incl - pc, o);
+            uint32_t q = 0;
+            if (act) q = ((wb + (uint32_t)o) << 5) + __fns(wbits, 0u, (int)(k - before) + 1) - Q0t;
+            W.dense_regs(act, q, act ? 1 : 0);
+            any = true;
+        }
+    }
+    if (valid && any) {
+        const float at = W.t_alpha(lane);
+#pragma unroll
+        for (int c = 0; c < DP; c++) W.y[c] = F_FMA(at, W.y[c], W.t_beta(c, lane));
+        store_row<DP>(cell_f(ymid), node - c0, W.y);
+    }
+    __syncwarp();
+}
+
 #ifndef ANNEMBED_CELL_THREADS
 #define ANNEMBED_CELL_THREADS 768
 #endif
@@ -448,18 +617,25 @@ __host__ __device__ constexpr uint32_t cell_smem_fixed_bytes(int nwarps)
 {
     return (uint32_t)(CellCfg<DP>::Y_BYTES + CellCfg<DP>::REL_BYTES + nwarps * (CellCfg<DP>::RING_WORDS * 4 + CellStage<KP>::BYTES + 8));
 }
-template <int DP, bool HUB, int KP>
-__global__ void __launch_bounds__(ANNEMBED_CELL_THREADS, ANNEMBED_CELL_MINB)
+#ifndef ANNEMBED_CELL_THREADS_EVENTS
+#define ANNEMBED_CELL_THREADS_EVENTS 512
+#endif
+// EVENTS: every sub-step of the launch has kappa <= 1 and runs the event form of phase A (no staging buffers)
+#ifndef ANNEMBED_CELL_MINB_EVENTS
+#define ANNEMBED_CELL_MINB_EVENTS 2
+#endif
+template <int DP, bool HUB, int KP, bool EVENTS>
+__global__ void __launch_bounds__(EVENTS ? ANNEMBED_CELL_THREADS_EVENTS : ANNEMBED_CELL_THREADS, EVENTS ? ANNEMBED_CELL_MINB_EVENTS : ANNEMBED_CELL_MINB)
 k_cell_epochs(CellArgs A, unsigned long long *sample_counter)
 {
     using CFG = CellCfg<DP>;
-    using ST = CellStage<KP>;
+    using ST = CellStage<EVENTS ? 32 : KP>;                       // KP = 32: staging off
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rel = CFG::Y_BYTES;
     const uint32_t ring = rel + CFG::REL_BYTES + (uint32_t)warp * CFG::RING_WORDS * 4u;
     const uint32_t stage = rel + CFG::REL_BYTES + (uint32_t)nwarps * CFG::RING_WORDS * 4u + (uint32_t)warp * ST::BYTES;
     const uint32_t bar = rel + CFG::REL_BYTES + (uint32_t)nwarps * (CFG::RING_WORDS * 4u + ST::BYTES) + (uint32_t)warp * 8u;
-    const uint32_t fmap = cell_smem_fixed_bytes<DP, KP>(nwarps);
+    const uint32_t fmap = cell_smem_fixed_bytes<DP, EVENTS ? 32 : KP>(nwarps);
 
     const EpochArgs &a = A.e;
     const uint32_t cell = A.cell_lo + blockIdx.x;
@@ -481,7 +657,8 @@ k_cell_epochs(CellArgs A, unsigned long long *sample_counter)
         uint32_t *relp = reinterpret_cast<uint32_t *>(cell_smem + rel);
         for (uint32_t i = threadIdx.x; i <= csize; i += blockDim.x) relp[i] = (uint32_t)(__ldg(a.in_ptr + c0 + i) - Q0);
         uint4 *fz = reinterpret_cast<uint4 *>(cell_smem + fmap);
-        for (uint32_t i = threadIdx.x; i < (n_in + 15u) / 16u; i += blockDim.x) fz[i] = make_uint4(0, 0, 0, 0);
+        const uint32_t map_bytes = EVENTS ? ((n_in + 31u) >> 5) * 4u : n_in;     // bitmap / byte map
+        for (uint32_t i = threadIdx.x; i < (map_bytes + 15u) / 16u; i += blockDim.x) fz[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     if constexpr (ST::ON) {                                       // stage the warp's first tile
@@ -505,20 +682,36 @@ k_cell_epochs(CellArgs A, unsigned long long *sample_counter)
             const uint4 rec = __ldg(a.in_rec + qq);
             const float us = node_uniform(rec.x, ukey);
             const int c = cum_ceil(a.kappa, __uint_as_float(rec.z), us) - cum_ceil(a.kappa, __uint_as_float(rec.y), us);
-            if (c > 0) cell_smem[fmap + (uint32_t)((uint64_t)qq + a.in_base - Q0)] = (unsigned char)c;
+            if (c > 0) {
+                const uint32_t loc = (uint32_t)((uint64_t)qq + a.in_base - Q0);
+                if constexpr (EVENTS) atomicOr(reinterpret_cast<uint32_t *>(cell_smem + fmap) + (loc >> 5), 1u << (loc & 31u));
+                else cell_smem[fmap + loc] = (unsigned char)c;
+            }
         }
-        for (uint32_t t = warp; t < ntiles; t += nwarps) {
-            // the tile this warp works on after this one: the next of this sub-step, or its first of the next sub-step
-            const uint32_t tn = t + nwarps < ntiles ? t + nwarps : (uint32_t)warp;
-            const bool more = t + nwarps < ntiles || sub + 1 < A.substeps;
-            const uint32_t nn = c0 + 32u * tn;
-            applied += cell_phase_a<DP, HUB, KP>(a, epoch, ukey, ycur, ymid, fmap, c0, csize, Q0, n_in, c0 + 32u * t, lane, stage, bar, parity,
-                                                 more ? (const void *)(a.rowpack + (size_t)nn * KP) : nullptr, a.erank + (size_t)nn * KP,
-                                                 a.inv_s2 + nn);
+        if constexpr (EVENTS) {
+            // batches of 32 nodes, or of 64 when fewer than half of them fire
+            const uint32_t bn = a.kappa <= 0.5f ? 64u : 32u;
+            for (uint32_t b0 = (uint32_t)warp * bn; b0 < csize; b0 += (uint32_t)nwarps * bn) {
+                const unsigned int fired = cell_phase_a_events<DP, HUB, KP>(a, epoch, ukey, ycur, ymid, fmap, c0, csize, Q0, n_in, c0 + b0,
+                                                                            min(bn, csize - b0), ring, lane);
+                applied += lane == 0 ? fired : 0u;                 // warp-uniform count, summed over the lanes at the end
+            }
+        } else {
+            for (uint32_t t = warp; t < ntiles; t += nwarps) {
+                // the tile this warp works on after this one: the next of this sub-step, or its first of the next sub-step
+                const uint32_t tn = t + nwarps < ntiles ? t + nwarps : (uint32_t)warp;
+                const bool more = t + nwarps < ntiles || sub + 1 < A.substeps;
+                const uint32_t nn = c0 + 32u * tn;
+                applied += cell_phase_a<DP, HUB, KP>(a, epoch, ukey, ycur, ymid, fmap, c0, csize, Q0, n_in, c0 + 32u * t, lane, stage, bar, parity,
+                                                     more ? (const void *)(a.rowpack + (size_t)nn * KP) : nullptr, a.erank + (size_t)nn * KP,
+                                                     a.inv_s2 + nn);
+            }
         }
         __syncthreads();
-        for (uint32_t t = warp; t < ntiles; t += nwarps)
-            cell_phase_b<DP>(a, ycur, ymid, fmap, ring, rel, c0, csize, Q0, c0 + 32u * t, lane);
+        for (uint32_t t = warp; t < ntiles; t += nwarps) {
+            if constexpr (EVENTS) cell_phase_b_bits<DP>(a, ycur, ymid, fmap, ring, rel, c0, csize, Q0, c0 + 32u * t, lane);
+            else cell_phase_b<DP>(a, ycur, ymid, fmap, ring, rel, c0, csize, Q0, c0 + 32u * t, lane);
+        }
         __syncthreads();
         const uint32_t tmp = ycur; ycur = ymid; ymid = tmp;
     }

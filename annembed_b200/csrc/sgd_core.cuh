@@ -312,13 +312,25 @@ __host__ __device__ __forceinline__ int cum_ceil(float kappa, float P, float u)
 }
 
 // the 5 accepted negatives of firing s of `node` (v2 streams: counter (node, sub, epoch, tag))
-//   tag 1: sub = s          words x,y,z,w -> negatives 0..3
-//   tag 2: sub = s >> 2     word (s & 3)  -> negative 4        (one call serves 4 consecutive firings)
-//   tag 3,4: sub = s        accept words of the hubness alias sampler
+//   tag 1: sub = s          words x,y,z,w -> negatives 0..3; negative 4 from fifth_word(block): ONE Philox block per firing
+//   tag 3: sub = s          accept words of the hubness alias sampler (fifth accept word likewise)
 //   tag 0x80000000|q<<8|t   redraw t of negative q after a rejection (embedder.rs:1246-1252)
 __host__ __device__ __forceinline__ uint32_t philox_word(const Philox4 &B, uint32_t i)
 {
     return (i & 2u) ? ((i & 1u) ? B.w : B.z) : ((i & 1u) ? B.y : B.x);
+}
+
+// Fifth 32-bit word of a firing: a mix of the block's four words (rotations + the multiply-xorshift finaliser of
+// node_uniform).  The negatives use the top ~24 bits of each word; the fifth word also depends on the 32 low bits that
+// no other negative sees, so given the first four negatives it is still uniform for every practical purpose
+// (chi-square of the accepted negatives: tests/test_host.py).
+__host__ __device__ __forceinline__ uint32_t fifth_word(const Philox4 &A)
+{
+    uint32_t x = A.x ^ ((A.y << 8) | (A.y >> 24)) ^ ((A.z << 16) | (A.z >> 16)) ^ ((A.w << 24) | (A.w >> 8));
+    x ^= x >> 16; x *= 0x21F0AAADu;
+    x ^= x >> 15; x *= 0x735A2D97u;
+    x ^= x >> 15;
+    return x + 0x9E3779B9u;
 }
 
 struct GlobalRowRejector {          // nodeparam.rs:83-85 linear scan of the origin's row in global memory
@@ -349,18 +361,34 @@ __host__ __device__ __forceinline__ uint32_t neg_stream_key(const EpochArgs &a, 
     return node & ~3u;
 }
 
+// redraws of the rejected negatives (embedder.rs:1246-1252: the reference loops until accepted; bounded here)
+template <bool HUB, class Rej>
+__host__ __device__ __forceinline__ void redraw_negatives(const EpochArgs &a, uint32_t epoch, uint32_t node, uint32_t s, const Rej &rejected,
+                                                          const bool (&rej)[ANNEMBED_NB_NEG], uint32_t (&negs)[ANNEMBED_NB_NEG])
+{
+#pragma unroll
+    for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
+        uint32_t k = negs[q];
+        bool r = rej[q];
+        for (uint32_t t = 0; r && t < ANNEMBED_MAX_REDRAW; t++) {
+            const Philox4 R = philox4x32_10(node, s, epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
+            k = map_negative<HUB>(a, R.x, R.y);
+            r = rejected(k);
+        }
+        negs[q] = r ? ANNEMBED_NO_NODE : k;
+    }
+}
+
 template <bool HUB, class Rej>
 __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t epoch, uint32_t node, uint32_t s, const Philox4 &A,
-                                                           uint32_t w4, const Rej &rejected,
-                                                           uint32_t (&negs)[ANNEMBED_NB_NEG])
+                                                           const Rej &rejected, uint32_t (&negs)[ANNEMBED_NB_NEG])
 {
-    uint32_t wi[ANNEMBED_NB_NEG] = {A.x, A.y, A.z, A.w, w4};
+    uint32_t wi[ANNEMBED_NB_NEG] = {A.x, A.y, A.z, A.w, fifth_word(A)};
     uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
     if constexpr (HUB) {
         const uint32_t gk = neg_stream_key<HUB>(a, node);
         const Philox4 C = philox4x32_10(gk, s, epoch, 3u, a.k0, a.k1);
-        const Philox4 D = philox4x32_10(gk, s >> 2, epoch, 4u, a.k0, a.k1);
-        wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = philox_word(D, s & 3u);
+        wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = fifth_word(C);
     }
     const uint32_t nsec = (a.n + 3u) >> 2;
     // first draw of the 5 negatives, branch-free; the redraws (probability ~ (deg+2)/n per negative) are a rare path
@@ -380,19 +408,7 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
         any_rej |= rej[q];
         negs[q] = k;
     }
-    if (any_rej) {
-#pragma unroll
-        for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-            uint32_t k = negs[q];
-            bool r = rej[q];
-            for (uint32_t t = 0; r && t < ANNEMBED_MAX_REDRAW; t++) {
-                const Philox4 R = philox4x32_10(node, s, epoch, 0x80000000u | ((uint32_t)q << 8) | t, a.k0, a.k1);
-                k = map_negative<HUB>(a, R.x, R.y);
-                r = rejected(k);
-            }
-            negs[q] = r ? ANNEMBED_NO_NODE : k;
-        }
-    }
+    if (any_rej) redraw_negatives<HUB>(a, epoch, node, s, rejected, rej, negs);
 }
 
 // one firing of `node` on edge (node -> j): attraction against the local copy of y_j, then 5 repulsions
@@ -471,9 +487,8 @@ __host__ __device__ __forceinline__ unsigned int epoch_node_rows(const EpochArgs
         for (int f = 0; f < c; f++, s++) {
             const uint32_t nk = neg_stream_key<HUB>(a, node);
             const Philox4 A = philox4x32_10(nk, s, a.epoch, 1u, a.k0, a.k1);
-            const Philox4 B = philox4x32_10(nk, s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<HUB>(a, a.epoch, node, s, A, philox_word(B, s & 3u), rej, negs);
+            draw_negatives_v2<HUB>(a, a.epoch, node, s, A, rej, negs);
             apply_firing<DP, B1>(a, node, y, yj, g, pe, inv_s2, negs);
         }
     }

@@ -227,10 +227,9 @@ extern "C" void hostsim_draws(uint64_t n, const uint64_t *row_ptr, const uint32_
                     const uint32_t s = (uint32_t)c_lo;
                     const uint32_t nk = neg_alias ? neg_stream_key<true>(a, (uint32_t)node) : neg_stream_key<false>(a, (uint32_t)node);
                     const Philox4 A = philox4x32_10(nk, s, epoch, 1u, a.k0, a.k1);
-                    const Philox4 B = philox4x32_10(nk, s >> 2, epoch, 2u, a.k0, a.k1);
                     const GlobalRowRejector rej{col, r0, r1, (uint32_t)node, col[m]};
-                    if (neg_alias) draw_negatives_v2<true>(a, a.epoch, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
-                    else draw_negatives_v2<false>(a, a.epoch, (uint32_t)node, s, A, philox_word(B, s & 3u), rej, negs);
+                    if (neg_alias) draw_negatives_v2<true>(a, a.epoch, (uint32_t)node, s, A, rej, negs);
+                    else draw_negatives_v2<false>(a, a.epoch, (uint32_t)node, s, A, rej, negs);
                 }
                 for (int q = 0; q < 5; q++) negs_out[5 * m + q] = negs[q];
             }

@@ -65,9 +65,8 @@ static unsigned epoch_node_var(const EpochArgs &a, const Var &v, const uint32_t 
         for (int f = 0; f < c; f++, s++) {
             const uint32_t nk = node & ~3u;
             const Philox4 A = philox4x32_10(nk, s, a.epoch, 1u, a.k0, a.k1);
-            const Philox4 B = philox4x32_10(nk, s >> 2, a.epoch, 2u, a.k0, a.k1);
             uint32_t negs[ANNEMBED_NB_NEG];
-            draw_negatives_v2<false>(a, a.epoch, node, s, A, philox_word(B, s & 3u), rej, negs);
+            draw_negatives_v2<false>(a, a.epoch, node, s, A, rej, negs);
             apply_firing<DP, true>(a, node, y, yj, g, pe, inv_s2, negs);
         }
         if (m - r0 < 16) { fired[m - r0] = true; for (int cc = 0; cc < DP; cc++) part[m - r0][cc] = yj[cc]; }

@@ -61,7 +61,9 @@ def run(row_ptr, col, dist, y0, hub=False, batches=2, **kw):
     return y, st
 
 
-@pytest.mark.parametrize("d,kmax,hub,M,nbs", [(2, 6, False, 3, 2), (2, 10, True, 2, 3), (3, 8, False, 2, 2), (2, 16, False, 4, 10), (4, 6, True, 3, 1)])
+# the last four cases have kappa = nbs * mean degree / M below 1 (and below 1/2): the event form of phase A
+@pytest.mark.parametrize("d,kmax,hub,M,nbs", [(2, 6, False, 3, 2), (2, 10, True, 2, 3), (3, 8, False, 2, 2), (2, 16, False, 4, 10), (4, 6, True, 3, 1),
+                                              (2, 6, False, 5, 1), (2, 6, True, 9, 1), (3, 8, False, 12, 1), (2, 16, False, 40, 3)])
 def test_one_substep_per_launch_equals_the_per_mini_epoch_kernels(d, kmax, hub, M, nbs):
     row_ptr, col, dist = random_graph(9000, 2, kmax, seed=81)         # an expander: most edges cross the 4096-node cells
     y0 = np.random.default_rng(8).uniform(-1, 1, size=(9000, d)).astype(np.float32)
@@ -75,13 +77,13 @@ def test_one_substep_per_launch_equals_the_per_mini_epoch_kernels(d, kmax, hub, 
     np.testing.assert_array_equal(ya, yb)
 
 
-@pytest.mark.parametrize("d,hub", [(2, False), (2, True), (4, False)])
-def test_closed_cells_one_substep_equals_the_per_mini_epoch_kernels(d, hub):
+@pytest.mark.parametrize("d,hub,M", [(2, False, 3), (2, True, 3), (4, False, 3), (2, False, 24), (2, True, 12)])
+def test_closed_cells_one_substep_equals_the_per_mini_epoch_kernels(d, hub, M):
     bs = 3008 if d <= 2 else 1504                                     # whole tiles, below the cell size (4096 / 2048 nodes)
     row_ptr, col, dist = block_graph(5, bs, 3, 6, seed=5)             # 5 components -> 5 closed cells
     n = 5 * bs
     y0 = np.random.default_rng(9).uniform(-1, 1, size=(n, d)).astype(np.float32)
-    kw = dict(asked_dim=d, seed=22, nb_sampling_by_edge=3, mini_epochs_per_batch=3)
+    kw = dict(asked_dim=d, seed=22, nb_sampling_by_edge=3, mini_epochs_per_batch=M)     # M = 12, 24: kappa below 1, 1/2
     ya, sa = run(row_ptr, col, dist, y0, hub, cell_substeps=1, **kw)
     yb, sb = run(row_ptr, col, dist, y0, hub, flags=LEGACY, **kw)
     assert sa["n_cells"] == 5 and sa["cross_cell_edges"] == 0, (sa["n_cells"], sa["cross_cell_edges"])
@@ -90,35 +92,35 @@ def test_closed_cells_one_substep_equals_the_per_mini_epoch_kernels(d, hub):
     # the default launch length on closed cells is longer than one sub-step, and it is a different (equally valid)
     # realisation: the negatives are read from the layout at the start of the launch
     yc, sc = run(row_ptr, col, dist, y0, hub, **kw)
-    assert sc["cell_substeps"] == 3 and sc["epoch_launches"] == 2
+    assert sc["cell_substeps"] == min(M, 16) and sc["epoch_launches"] == 2 * ((M + 15) // 16)
     assert sc["positive_samples"] == sa["positive_samples"]
     assert np.isfinite(yc).all() and np.abs(yc - ya).max() > 0
 
 
-@pytest.mark.parametrize("d,S,kmax", [(2, 2, 6), (2, 3, 10), (4, 2, 6)])
-def test_several_substeps_match_the_host_replay(d, S, kmax):
+@pytest.mark.parametrize("d,S,kmax,nbs,M", [(2, 2, 6, 2, 2), (2, 3, 10, 3, 3), (4, 2, 6, 2, 2), (2, 4, 6, 1, 8), (2, 3, 10, 1, 15)])
+def test_several_substeps_match_the_host_replay(d, S, kmax, nbs, M):
     """One launch of S sub-steps against tests/hostsim (identity numbering: ANNEMBED_FLAG_NO_RELABEL, fixed grid of cells).
     The dynamics are chaotic, so the comparison is on quantiles as in test_epoch_kernel_matches_host_replay."""
     n = 10000
     row_ptr, col, dist = random_graph(n, 3, kmax, seed=83)
     y0 = np.random.default_rng(3).uniform(-2, 2, size=(n, d)).astype(np.float32)
-    ctx = A.CudaContext(A.EmbedderParams(asked_dim=d, dmap_init=False, grad_step=1.0, nb_grad_batch=4, nb_sampling_by_edge=S,
-                                         mini_epochs_per_batch=S, seed=99, flags=NO_RELABEL, cell_substeps=S))
+    ctx = A.CudaContext(A.EmbedderParams(asked_dim=d, dmap_init=False, grad_step=1.0, nb_grad_batch=4, nb_sampling_by_edge=nbs,
+                                         mini_epochs_per_batch=M, seed=99, flags=NO_RELABEL, cell_substeps=S))
     ctx.set_graph_csr(row_ptr, col, dist)
     scale, p = ctx.edge_weights()
     es = ctx.get_embedded_scales()
     ctx.set_embedding(y0)
-    ctx.optimize_batches(1, 1)
+    ctx.optimize_batches(1, 1)                       # M mini-epochs in launches of S sub-steps
     y, st = ctx.get_embedding(), ctx.get_stats()
-    assert st["epoch_launches"] == 1 and st["cell_substeps"] == S
+    assert st["epoch_launches"] == (M + S - 1) // S and st["cell_substeps"] == S
     cell_nodes = int(st["cell_nodes"])
     assert cell_nodes == (4096 if d <= 2 else 2048)
-    y_host, done = hs.optimize_cells(row_ptr, col, p, es, y0, 1.0, 1.0, S, 4, S, 99, None, 1, 1, cell_nodes=cell_nodes, substeps=S)
+    y_host, done = hs.optimize_cells(row_ptr, col, p, es, y0, 1.0, 1.0, nbs, 4, M, 99, None, 1, 1, cell_nodes=cell_nodes, substeps=S)
     assert st["positive_samples"] == done
     err = np.abs(y - y_host).max(axis=1)
-    assert np.median(err) < 1e-6 and np.quantile(err, 0.99) < 1e-3, (np.median(err), np.quantile(err, 0.99), err.max())
+    assert np.median(err) < 1e-6 and np.quantile(err, 0.98) < 1e-3, (np.median(err), np.quantile(err, 0.98), err.max())
     # and it is NOT the flat (one global snapshot per mini-epoch) semantics: the cells do see their own moves
-    y_flat, _ = hs.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, S, 4, S, 99, None, 1, 1)
+    y_flat, _ = hs.optimize(row_ptr, col, p, es, y0, 1.0, 1.0, nbs, 4, M, 99, None, 1, 1)
     assert np.quantile(np.abs(y - y_flat).max(axis=1), 0.9) > 1e-4
     ctx.close()
 

@@ -2,6 +2,6 @@ set -x
 mkdir -p gpurun_out
 TAG=${1:-r02_cell}
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cell_epochs -s 1 -c 1 -f -o gpurun_out/${TAG} \
-    python bench.py --steps 1 --warmup 0 --batches 2 --mini-epochs 67 --no-e2e --no-cpu-baseline > gpurun_out/ncu_${TAG}.log 2>&1
+    python bench.py --steps 1 --warmup 0 --batches 2 --mini-epochs ${2:-67} --no-e2e --no-cpu-baseline > gpurun_out/ncu_${TAG}.log 2>&1
 tail -3 gpurun_out/ncu_${TAG}.log
 ls -la gpurun_out/
