@@ -12,7 +12,7 @@ SOURCES = ["annembed_cuda.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "annembed_cuda.h")]
 
 NVCC_FLAGS = [
-    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-split-compile", "0",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

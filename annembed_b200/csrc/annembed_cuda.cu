@@ -893,6 +893,8 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
     if (lane == 0 && applied) atomicAdd(sample_counter + (blockIdx.x & 255), (unsigned long long)applied);
 }
 
+#include "async_sweep.cuh"    // the asynchronous form of K4 (default on one rank)
+
 #ifndef ANNEMBED_WARPS_IN
 #define ANNEMBED_WARPS_IN 4
 #endif
@@ -1665,6 +1667,12 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
 //  3. the order inside every cell is then randomised (k_cell_sort_keys explains why);
 //  4. ranks own whole cells (balanced node counts).  Cells do not depend on the number of ranks.
 // Graph only; built once per set_graph_csr.
+__global__ void k_hash_keys(uint64_t n, uint32_t salt, uint32_t *__restrict__ key)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key[i] = mix32((uint32_t)i * 0x9E3779B1u + salt);
+}
+static bool use_async(const annembed_cuda_ctx *ctx);
 static int build_relabelling(annembed_cuda_ctx *ctx)
 {
     const uint64_t n = ctx->n;
@@ -1674,10 +1682,26 @@ static int build_relabelling(annembed_cuda_ctx *ctx)
     k_iota<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p);
     ctx->st.kernel_launches++;
     std::vector<uint32_t> seg;                       // segment starts of the locality order (empty: none known)
-    const bool relabel = !(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL) && n >= 1024;
+    bool relabel = !(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL) && n >= 1024;
     DevBuf<uint32_t> key, key_s, ord;
     DevBuf<unsigned char> tmp;
     size_t tmp_bytes = 0;
+    if (relabel && use_async(ctx)) {
+        // Asynchronous form: a RANDOM internal order (sort by a hash of the caller's id).  The nodes a warp visits together
+        // (a tile), the 4 nodes that share a negative stream and the 4 nodes of a negative's sector must all be unrelated
+        // nodes, whatever structure the caller's numbering has: neighbours that move at the same moment, or against the
+        // same negatives, move coherently and shift the layout statistics.  The whole layout is the working
+        // set of the negatives anyway, so a locality order would buy no cache hits.
+        CU(key.alloc(n)); CU(key_s.alloc(n)); CU(ord.alloc(n));
+        k_hash_keys<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, 0x7F4A7C15u, key.p);
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key_s.p, ctx->old_of_new.p, ord.p, (int64_t)n, 0, 32, ctx->stream));
+        CU(tmp.alloc(tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key_s.p, ctx->old_of_new.p, ord.p, (int64_t)n, 0, 32, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->old_of_new.p, ord.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->st.kernel_launches += 2;
+        if ((rc = sync_stream(ctx))) return rc;
+        relabel = false;                             // no locality order, no segments: fixed grid of cells below
+    }
     if (relabel) {
         DevBuf<uint32_t> L[2];
         CU(L[0].alloc(n)); CU(L[1].alloc(n)); CU(key.alloc(n)); CU(key_s.alloc(n)); CU(ord.alloc(n));
@@ -2337,12 +2361,29 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
     return d2h(ctx, out, ctx->emb_scale.p, ctx->n * sizeof(float));
 }
 
-// Mini-epochs per reference batch (mini_epochs_per_batch == 0: the default schedule).
+// ---- schedule -------------------------------------------------------------------------------------------------------
+// Asynchronous form (one rank, default): a batch is `M` sweeps over the nodes, every node fires kappa = nb_sampling_by_edge
+// * mean degree / M times per sweep.  Default kappa = ANNEMBED_ASYNC_KAPPA = 1: one sample per visit of a node, as spread
+// out in time as the reference's independent edge draws.  Measured on the BASELINE.json configs against the serial
+// reference loop (tools/gpu_fidelity_probe.py): at 1 firing per visit every layout statistic is within
+// 0.5 % of the reference's, at 2 (the node's samples come in bursts of two) kNN preservation is 6 % off, at 4, 15 %.
+#ifndef ANNEMBED_ASYNC_KAPPA
+#define ANNEMBED_ASYNC_KAPPA 0.25
+#endif
+#ifndef ANNEMBED_ASYNC_THIN
+#define ANNEMBED_ASYNC_THIN 4u           // thinned sub-sweeps per launch (kappa = 1 per launch in total)
+#endif
+static bool use_async(const annembed_cuda_ctx *ctx)
+{
+    return ctx->nranks == 1 &&
+           !(ctx->prm.flags & (ANNEMBED_FLAG_BULK_SYNCHRONOUS | ANNEMBED_FLAG_REPLAY_IN_EDGES | ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS));
+}
+// Bulk-synchronous form (ANNEMBED_FLAG_BULK_SYNCHRONOUS, and every multi-rank run): mini-epochs per reference batch.
 // What governs the fidelity of the bulk-synchronous loop is how much of a batch is applied against one snapshot, i.e.
 // samples per edge per mini-epoch (nb_sampling_by_edge / M).  Measured against the serial reference loop on the
 // BASELINE.json configs (tools/gpu_schedule_probe.py):
 //  * the neighbourhood statistics of the final layout (get_quality_estimate_from_edge_length, kNN preservation) are set by
-//    the LAST batches: with the last third at 0.075 samples per edge per mini-epoch they are within 1 % of the
+//    the LAST batches: with the last third at 0.075 samples per edge per mini-epoch they are within 1-2 % of the
 //    reference's whatever the first two thirds use (0.6 .. 0.15 samples per edge gave the same statistics);
 //  * the first two thirds only move the final cross entropy (coarser early mini-epochs end 10-17 % below the reference's).
 // The first two thirds run at kappa = 1 firing per node and mini-epoch (the coarsest level the event form of the cell
@@ -2350,22 +2391,24 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
 #ifndef ANNEMBED_SAMPLES_PER_EDGE_LATE
 #define ANNEMBED_SAMPLES_PER_EDGE_LATE 0.075
 #endif
-static uint32_t mini_epochs_kappa_one(const annembed_cuda_ctx *ctx)
+static uint32_t mini_epochs_kappa(const annembed_cuda_ctx *ctx, double kappa)
 {
     const double deg = ctx->n ? (double)ctx->E / (double)ctx->n : 1.0;
-    return (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge * deg - 1e-9));
+    return (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge * deg / kappa - 1e-9));
 }
 static uint32_t eff_mini_epochs(const annembed_cuda_ctx *ctx)           // the finest level of the schedule
 {
     if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;
+    if (use_async(ctx)) return mini_epochs_kappa(ctx, ANNEMBED_ASYNC_KAPPA);
     const uint32_t late = (uint32_t)std::max<double>(1.0, std::ceil((double)ctx->prm.nb_sampling_by_edge / ANNEMBED_SAMPLES_PER_EDGE_LATE));
-    return std::max(late, mini_epochs_kappa_one(ctx));
+    return std::max(late, mini_epochs_kappa(ctx, 1.0));
 }
 static uint32_t mini_epochs_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter)
 {
     if (ctx->prm.mini_epochs_per_batch) return ctx->prm.mini_epochs_per_batch;      // explicit: every batch
+    if (use_async(ctx)) return eff_mini_epochs(ctx);
     const uint32_t nb = ctx->prm.nb_grad_batch;
-    return (3 * iter > 2 * nb) ? eff_mini_epochs(ctx) : mini_epochs_kappa_one(ctx);
+    return (3 * iter > 2 * nb) ? eff_mini_epochs(ctx) : mini_epochs_kappa(ctx, 1.0);
 }
 // global index of the first mini-epoch of batch `iter` (counter word of the Philox streams)
 static uint32_t first_epoch_of_batch(const annembed_cuda_ctx *ctx, uint32_t iter)
@@ -2612,6 +2655,95 @@ static cudaError_t launch_cells(annembed_cuda_ctx *ctx, const CellArgs &A, bool 
     return hub ? launch_cells_dp<4, true>(ctx, A) : launch_cells_dp<4, false>(ctx, A);
 }
 
+// ---- the asynchronous form of K4 (async_sweep.cuh) ---------------------------------------------------------------
+static bool async_tiled(const annembed_cuda_ctx *ctx, float kappa)
+{
+    return !(ctx->prm.flags & ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL) && ctx->prm.b == 1.0 && ctx->KP != 0 &&
+           kappa + 2.0f < (float)EpochTile<2, 6>::MAX_FIRINGS;
+}
+// Nodes in flight are capped at a fraction of n (persistent warps; large graphs fill the machine): what a sample misses of
+// the other nodes' moves is the samples in flight, and the layout statistics feel it when that is more than a few per
+// cent of the nodes (measured against the serial reference, DESIGN.md 4: the kNN-preservation rate moves by -0.09 %
+// per per cent of the nodes in flight in dimension 2, by +0.35 % per per cent in dimension 15).
+static unsigned int async_blocks(const annembed_cuda_ctx *ctx, uint64_t units, unsigned int nodes_in_flight_per_block, int DP)
+{
+    const uint64_t div = DP <= 4 ? ANNEMBED_ASYNC_WINDOW_DIV : ANNEMBED_ASYNC_WINDOW_DIV_WIDE;
+    const uint64_t window = std::max<uint64_t>(nodes_in_flight_per_block, ctx->n / div);
+    const uint64_t cap = std::max<uint64_t>(1, window / nodes_in_flight_per_block);
+    return (unsigned int)std::min<uint64_t>(units, cap);
+}
+// visiting order of a sweep's tiles (TileOrder, async_sweep.cuh): multiplier ~ tiles / golden ratio, coprime with tiles
+static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; }
+static TileOrder tile_order(uint64_t tiles, uint64_t warps_total)
+{
+    TileOrder o;
+    o.tiles = (uint32_t)tiles;
+    uint32_t mul = (uint32_t)std::max<double>(1.0, std::floor((double)tiles * 0.6180339887498949));
+    while (mul > 1 && gcd_u32(mul, o.tiles) != 1) mul--;
+    o.mul = tiles > 1 ? mul : 0u;
+    o.step = tiles ? (uint32_t)((warps_total * (uint64_t)o.mul) % tiles) : 0u;
+    return o;
+}
+template <int DP, bool HUB, int KP>
+static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a, uint32_t subs)
+{
+    const uint64_t owned = (uint64_t)(a.hi - a.lo);
+#ifndef ANNEMBED_ASYNC_POISSON
+    if (a.kappa <= 1.0f) {
+        using TE = EventTile<DP, KP>;
+        // persistent warps: at most the resident blocks, the in-flight window, and ~8 firing tiles per warp and sub-sweep
+        const uint64_t tiles = (owned + 31) / 32;
+        const unsigned int resident = (unsigned int)(ctx->sm_count * TE::MINB);
+        const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa / 8.0) / TE::WARPS);
+        const unsigned int nb = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(want, resident), async_blocks(ctx, tiles, TE::WARPS * 32 * TE::VISITS, DP));
+        k_sweep_events<DP, HUB, KP><<<nb, TE::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, tile_order(tiles, (uint64_t)nb * TE::WARPS), subs,
+                                                                                ctx->counter.p);
+        return cudaGetLastError();
+    }
+#endif
+    (void)subs;                                      // several firings per visit: one sweep per launch
+    using TL = EpochTile<DP, KP>;
+    const uint64_t tiles = (owned + 31) / 32;
+    const unsigned int nb = async_blocks(ctx, (tiles + TL::WARPS - 1) / TL::WARPS, TL::WARPS * 32, DP);
+    k_sweep_async<DP, HUB, KP><<<nb, TL::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, tile_order(tiles, (uint64_t)nb * TL::WARPS), ctx->counter.p);
+    return cudaGetLastError();
+}
+template <int DP, bool HUB>
+static cudaError_t launch_async_dp(annembed_cuda_ctx *ctx, const EpochArgs &a, uint32_t subs)
+{
+    if (a.hi <= a.lo) return cudaSuccess;
+    if (async_tiled(ctx, a.kappa)) {
+        switch (ctx->KP) {
+        case 6: return launch_async_kp<DP, HUB, 6>(ctx, a, subs);
+        case 8: return launch_async_kp<DP, HUB, 8>(ctx, a, subs);
+        case 10: return launch_async_kp<DP, HUB, 10>(ctx, a, subs);
+        default: return launch_async_kp<DP, HUB, 16>(ctx, a, subs);
+        }
+    }
+    const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;
+    const unsigned int nb = async_blocks(ctx, (tiles + 3) / 4, 128, DP);
+    k_sweep_async_generic<DP, HUB><<<nb, 128, 0, ctx->launch_stream>>>(a, ctx->y[0].p, tile_order(tiles, (uint64_t)nb * 4), ctx->counter.p);
+    return cudaGetLastError();
+}
+template <bool HUB>
+static cudaError_t launch_async(annembed_cuda_ctx *ctx, const EpochArgs &a, uint32_t subs)
+{
+    switch (ctx->DP) {
+    case 2: return launch_async_dp<2, HUB>(ctx, a, subs);
+    case 4: return launch_async_dp<4, HUB>(ctx, a, subs);
+    case 8: return launch_async_dp<8, HUB>(ctx, a, subs);
+    case 16: return launch_async_dp<16, HUB>(ctx, a, subs);
+    default: return launch_async_dp<32, HUB>(ctx, a, subs);
+    }
+}
+// sub-sweeps per launch of the asynchronous form: the default schedule runs its ANNEMBED_ASYNC_THIN thinned sub-sweeps of a
+// sweep in one launch (k_sweep_events); an explicit mini_epochs_per_batch makes every sweep its own launch
+static uint32_t async_subs(const annembed_cuda_ctx *ctx, float kappa)
+{
+    if (ctx->prm.mini_epochs_per_batch || !async_tiled(ctx, kappa) || kappa > 1.0f) return 1u;
+    return ANNEMBED_ASYNC_THIN;
+}
+
 // replicate the rows every rank owns (rank-dependent counts): one broadcast per rank, grouped
 static int exchange_rows_nccl(annembed_cuda_ctx *ctx, float *buf)
 {
@@ -2643,7 +2775,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     for (uint32_t iter = first_batch; iter < last; iter++) {
         const uint32_t M = mini_epochs_of_batch(ctx, iter);
         const float kappa = (float)((double)ctx->prm.nb_sampling_by_edge * ((double)ctx->E / (double)ctx->n) / (double)M);
-        const uint32_t S = use_cells(ctx, kappa) ? cell_substeps(ctx, M) : 1u;
+        const uint32_t S = use_async(ctx) ? async_subs(ctx, kappa) : (use_cells(ctx, kappa) ? cell_substeps(ctx, M) : 1u);
         n_launch += (M + S - 1) / S;
     }
     while (ctx->ev.size() < 2 * n_launch + 2 * n_launch * (ctx->nranks > 1)) {
@@ -2666,12 +2798,23 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
         const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
         const uint32_t M = mini_epochs_of_batch(ctx, iter), e0 = first_epoch_of_batch(ctx, iter);
         uint32_t S = 1;
+        const bool async = use_async(ctx);
         {
             const EpochArgs probe = make_epoch_args(ctx, e0, grad_step, M);
-            if (use_cells(ctx, probe.kappa)) S = cell_substeps(ctx, M);
+            if (async) S = async_subs(ctx, probe.kappa);
+            else if (use_cells(ctx, probe.kappa)) S = cell_substeps(ctx, M);
         }
         for (uint32_t m = 0; m < M; m += S, li++) {
             EpochArgs a = make_epoch_args(ctx, e0 + m, grad_step, M);
+            if (async) {                                       // one sweep over the single layout buffer y[0]
+                a.y_snap = ctx->y[0].p; a.y_next = ctx->y[0].p; a.fired = nullptr;
+                set_l2_window(ctx, a.y_snap, (size_t)ctx->n * ctx->DP * sizeof(float));
+                CU(cudaEventRecord(ctx->ev[2 * li], ctx->stream));
+                CU(hub ? launch_async<true>(ctx, a, std::min(S, M - m)) : launch_async<false>(ctx, a, std::min(S, M - m)));
+                CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
+                n_kernels += 1;
+                continue;
+            }
             const bool cells = use_cells(ctx, a.kappa);
             // the fused exchange lives in the tiled in-edge kernel / the cell kernel: the same predicate picks both
             const bool fused = ctx->nranks > 1 && ctx->have_peers && (cells || use_tiled(ctx, a.kappa));

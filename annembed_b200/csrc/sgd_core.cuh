@@ -379,24 +379,24 @@ __host__ __device__ __forceinline__ void redraw_negatives(const EpochArgs &a, ui
     }
 }
 
+// first draw of the 5 negatives from the index words of block A (and the accept words of block C, hubness sampler), then
+// the rare redraws.  `rot` distinguishes the 4 members of the group that shares A / C: each takes a different row of the
+// drawn sector (rotated by two random bits of the word).
 template <bool HUB, class Rej>
-__host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t epoch, uint32_t node, uint32_t s, const Philox4 &A,
-                                                           const Rej &rejected, uint32_t (&negs)[ANNEMBED_NB_NEG])
+__host__ __device__ __forceinline__ void draw_negatives_core(const EpochArgs &a, uint32_t epoch, uint32_t node, uint32_t s, uint32_t rot,
+                                                             const Philox4 &A, const Philox4 &C, const Rej &rejected,
+                                                             uint32_t (&negs)[ANNEMBED_NB_NEG])
 {
     uint32_t wi[ANNEMBED_NB_NEG] = {A.x, A.y, A.z, A.w, fifth_word(A)};
     uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
-    if constexpr (HUB) {
-        const uint32_t gk = neg_stream_key<HUB>(a, node);
-        const Philox4 C = philox4x32_10(gk, s, epoch, 3u, a.k0, a.k1);
-        wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = fifth_word(C);
-    }
+    if constexpr (HUB) { wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = fifth_word(C); }
     const uint32_t nsec = (a.n + 3u) >> 2;
-    // first draw of the 5 negatives, branch-free; the redraws (probability ~ (deg+2)/n per negative) are a rare path
+    // branch-free; the redraws (probability ~ (deg+2)/n per negative) are a rare path
     bool any_rej = false;
     bool rej[ANNEMBED_NB_NEG];
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-        uint32_t k = (below32(wi[q], nsec) << 2) | ((node + wi[q]) & 3u);      // random sector, row rotated by 2 random bits
+        uint32_t k = (below32(wi[q], nsec) << 2) | ((rot + wi[q]) & 3u);       // random sector, row rotated by 2 random bits
         bool out_of_range = k >= a.n;
         if constexpr (HUB) {
             if (!out_of_range) {                                               // alias method on the shared sector's entry
@@ -409,6 +409,17 @@ __host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, u
         negs[q] = k;
     }
     if (any_rej) redraw_negatives<HUB>(a, epoch, node, s, rejected, rej, negs);
+}
+
+// bulk-synchronous kernels and the multi-firing sweep: the group is the 4 nodes of an aligned id quadruple (neg_stream_key)
+template <bool HUB, class Rej>
+__host__ __device__ __forceinline__ void draw_negatives_v2(const EpochArgs &a, uint32_t epoch, uint32_t node, uint32_t s, const Philox4 &A,
+                                                           const Rej &rejected, uint32_t (&negs)[ANNEMBED_NB_NEG])
+{
+    Philox4 C;
+    C.x = C.y = C.z = C.w = 0u;
+    if constexpr (HUB) C = philox4x32_10(neg_stream_key<HUB>(a, node), s, epoch, 3u, a.k0, a.k1);
+    draw_negatives_core<HUB>(a, epoch, node, s, node, A, C, rejected, negs);
 }
 
 // one firing of `node` on edge (node -> j): attraction against the local copy of y_j, then 5 repulsions

@@ -9,6 +9,7 @@ FLAG_NO_L2_PERSIST = 2
 FLAG_NO_RELABEL = 4
 FLAG_REPLAY_IN_EDGES = 8
 FLAG_LEGACY_EPOCH_KERNELS = 16
+FLAG_BULK_SYNCHRONOUS = 32
 
 
 @dataclass

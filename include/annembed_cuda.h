@@ -56,9 +56,9 @@ typedef struct annembed_cuda_params {
     uint32_t hierarchy_layer;      /* :100 default 0 */
     uint32_t hubness_weighting;    /* :102 default 0: negatives uniform; 1: alias over set_neg_weights */
     /* ---- device-side additions (no reference counterpart: its RNG is unseeded, embedder.rs:1182) ---- */
-    uint32_t mini_epochs_per_batch;/* bulk-synchronous sub-steps per reference batch;
-                                      0 -> ceil(nb_sampling_by_edge / 0.15) (0.15 samples per edge per mini-epoch),
-                                      see eff_mini_epochs / mini_epochs_of_batch in annembed_cuda.cu */
+    uint32_t mini_epochs_per_batch;/* sweeps over the nodes (asynchronous form) / bulk-synchronous mini-epochs per
+                                      reference batch; 0 -> the default schedule, see eff_mini_epochs /
+                                      mini_epochs_of_batch in annembed_cuda.cu */
     uint64_t seed;                 /* Philox4x32-10 key */
     uint32_t flags;                /* ANNEMBED_FLAG_* */
     uint32_t cell_substeps;        /* cell-resident epoch kernel: mini-epochs per launch (partners in other cells and the
@@ -73,7 +73,11 @@ typedef struct annembed_cuda_params {
 #define ANNEMBED_FLAG_REPLAY_IN_EDGES 8u        /* single rank: replay the sources' decisions in the in-edge kernel instead of
                                                    consuming the firing counts pushed by the out-edge kernel (cross-check) */
 #define ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS 16u  /* one launch of k_epoch_out + k_epoch_in per mini-epoch instead of the
-                                                   cell-resident kernel (cross-check; also what dimensions > 4 use) */
+                                                   cell-resident kernel (cross-check; also what dimensions > 4 use);
+                                                   implies the bulk-synchronous form */
+#define ANNEMBED_FLAG_BULK_SYNCHRONOUS 32u      /* one rank: the deterministic snapshot kernels (bit-reproducible for a seed)
+                                                   instead of the asynchronous sweep (async_sweep.cuh), which like the
+                                                   reference's threaded loop depends on the interleaving of the threads */
 
 typedef struct annembed_cuda_stats {
     double   edge_weights_ms;      /* K0+K1 device time, last call */

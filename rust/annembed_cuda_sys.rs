@@ -26,6 +26,7 @@ pub const ANNEMBED_FLAG_NO_L2_PERSIST: u32 = 2;
 pub const ANNEMBED_FLAG_NO_RELABEL: u32 = 4;
 pub const ANNEMBED_FLAG_REPLAY_IN_EDGES: u32 = 8;
 pub const ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS: u32 = 16;
+pub const ANNEMBED_FLAG_BULK_SYNCHRONOUS: u32 = 32;
 
 /// mirror of EmbedderParams (src/embedparams.rs:76-103) + the device-side knobs
 #[repr(C)]

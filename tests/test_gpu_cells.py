@@ -17,8 +17,9 @@ from tests.studies import hostsim_binding as hs
 
 pytestmark = pytest.mark.gpu
 
-LEGACY = 16   # ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS
+LEGACY = 16   # ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS (implies the bulk-synchronous form)
 NO_RELABEL = 4
+BULK = 32     # ANNEMBED_FLAG_BULK_SYNCHRONOUS: the cell kernel is the bulk-synchronous form's kernel on one rank
 
 
 def block_graph(nblocks, bsize, kmin, kmax, seed):
@@ -49,6 +50,7 @@ def block_graph(nblocks, bsize, kmin, kmax, seed):
 
 
 def run(row_ptr, col, dist, y0, hub=False, batches=2, **kw):
+    kw["flags"] = kw.get("flags", 0) | BULK
     ctx = A.CudaContext(A.EmbedderParams(dmap_init=False, grad_step=1.0, nb_grad_batch=3, hubness_weighting=hub, **kw))
     ctx.set_graph_csr(row_ptr, col, dist)
     ctx.edge_weights(want_outputs=False)
@@ -105,7 +107,7 @@ def test_several_substeps_match_the_host_replay(d, S, kmax, nbs, M):
     row_ptr, col, dist = random_graph(n, 3, kmax, seed=83)
     y0 = np.random.default_rng(3).uniform(-2, 2, size=(n, d)).astype(np.float32)
     ctx = A.CudaContext(A.EmbedderParams(asked_dim=d, dmap_init=False, grad_step=1.0, nb_grad_batch=4, nb_sampling_by_edge=nbs,
-                                         mini_epochs_per_batch=M, seed=99, flags=NO_RELABEL, cell_substeps=S))
+                                         mini_epochs_per_batch=M, seed=99, flags=NO_RELABEL | BULK, cell_substeps=S))
     ctx.set_graph_csr(row_ptr, col, dist)
     scale, p = ctx.edge_weights()
     es = ctx.get_embedded_scales()

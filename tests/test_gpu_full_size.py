@@ -51,9 +51,9 @@ def test_c3_11m_properties(higgs_graph):
         assert abs(st["positive_samples"] - expect) <= 2 * M * n * 0.51 + 1
         y = ctx.get_embedding()
         assert np.isfinite(y).all()
-        sums.append(checksum(y))
+        ce = ctx.cross_entropy()
+        sums.append((st["positive_samples"], ce))
         if rep == 1:
-            ce = ctx.cross_entropy()
             es = ctx.get_embedded_scales()
             ce_ref = oracle.cross_entropy(row_ptr, col, p, es, y, 1.0)        # K5 at full size vs the oracle
             assert abs(ce - ce_ref) <= 1e-6 * abs(ce_ref)
@@ -61,7 +61,10 @@ def test_c3_11m_properties(higgs_graph):
             ctx.optimize_batches(40, 1)                 # last batch: grad_step == 0
             np.testing.assert_array_equal(ctx.get_embedding(), before)
         ctx.close()
-    assert sums[0] == sums[1]                            # bit-identical reruns
+    # two asynchronous runs: the same samples (firing decisions are keyed by seed, node and sweep), two interleavings of
+    # the warps -- like two runs of the reference -- hence two realisations with the same cross entropy to a fraction of a %
+    assert sums[0][0] == sums[1][0]
+    assert abs(sums[0][1] - sums[1][1]) <= 5e-3 * sums[1][1]
 
 
 def test_c4_dim15_short_run():

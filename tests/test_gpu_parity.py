@@ -196,9 +196,12 @@ def test_device_draws_match_host_build_bit_for_bit():
     assert np.corrcoef(freq, w / w.sum())[0, 1] > 0.9
 
 
-@pytest.mark.parametrize("d,hub,flags", [(2, False, 4), (2, False, 4 | 8), (2, True, 4), (5, False, 4), (15, False, 4), (15, False, 4 | 8)])
+BULK = 32    # ANNEMBED_FLAG_BULK_SYNCHRONOUS: the deterministic snapshot kernels (the default on one rank is the asynchronous sweep)
+
+
+@pytest.mark.parametrize("d,hub,flags", [(2, False, 4 | BULK), (2, False, 4 | 8), (2, True, 4 | BULK), (5, False, 4 | BULK), (15, False, 4 | BULK), (15, False, 4 | 8)])
 def test_epoch_kernel_matches_host_replay(d, hub, flags):
-    """K4 against the host build of the same mini-epoch body: same draws, same order, fp32 rounding apart.
+    """Bulk-synchronous K4 against the host build of the same mini-epoch body: same draws, same order, fp32 rounding apart.
     ONE mini-epoch is compared: the dynamics are chaotic (repulsion coefficients up to 2 triple a perturbation per
     close negative), so rounding differences between nvcc's fma contraction and the host build grow afterwards."""
     row_ptr, col, dist = random_graph(4000, 3, 10, seed=71)
@@ -245,7 +248,7 @@ def test_tiled_epoch_kernel_equals_generic_kernel(d, kmax, hub, M):
     row_ptr, col, dist = random_graph(5000, 2, kmax, seed=72)
     y0 = np.random.default_rng(2).uniform(-1, 1, size=(5000, d)).astype(np.float32)
     outs = []
-    for flags in (0, 1):                             # 1 = ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL
+    for flags in (BULK, BULK | 1):                   # 1 = ANNEMBED_FLAG_GENERIC_EPOCH_KERNEL
         # cell_substeps=1: one mini-epoch per launch of the cell kernel, i.e. the generic kernel's global snapshots
         ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=3, grad_step=1.0, seed=5, flags=flags,
                       hubness_weighting=hub, nb_sampling_by_edge=1, mini_epochs_per_batch=M, cell_substeps=1)
@@ -272,7 +275,7 @@ def test_pushed_firing_counts_equal_replayed_decisions(d, kmax, hub, M, nbs):
     row_ptr, col, dist = random_graph(6000, 2, kmax, seed=74)
     y0 = np.random.default_rng(4).uniform(-1, 1, size=(6000, d)).astype(np.float32)
     outs = []
-    for flags in (0, 8):                             # 8 = ANNEMBED_FLAG_REPLAY_IN_EDGES
+    for flags in (BULK, 8):                          # 8 = ANNEMBED_FLAG_REPLAY_IN_EDGES (implies the bulk-synchronous form)
         ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=3, grad_step=1.0, seed=6, flags=flags,
                       hubness_weighting=hub, nb_sampling_by_edge=nbs, mini_epochs_per_batch=M)
         ctx.edge_weights(want_outputs=False)
@@ -308,7 +311,7 @@ def test_relabelling_is_invisible_at_the_boundary():
 
 def test_rows_longer_than_16_use_the_generic_kernel():
     row_ptr, col, dist = random_graph(3000, 17, 40, seed=73)
-    ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=3, grad_step=1.0, mini_epochs_per_batch=60, flags=4)
+    ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=3, grad_step=1.0, mini_epochs_per_batch=60, flags=4 | BULK)
     scale, p = ctx.edge_weights()
     es = ctx.get_embedded_scales()
     y0 = np.random.default_rng(2).uniform(-1, 1, size=(3000, 2)).astype(np.float32)
@@ -321,8 +324,9 @@ def test_rows_longer_than_16_use_the_generic_kernel():
 
 
 def test_optimize_is_deterministic_and_schedule_matches_reference():
+    """The bulk-synchronous form is bit-reproducible for a seed; both forms follow the reference's batch schedule."""
     row_ptr, col, dist = random_graph(3000, 5, 9, seed=81)
-    kw = dict(nb_grad_batch=5, grad_step=1.0, seed=7)
+    kw = dict(nb_grad_batch=5, grad_step=1.0, seed=7, flags=BULK)
     y0 = np.random.default_rng(3).uniform(-.5, .5, size=(3000, 2)).astype(np.float32)
     outs = []
     for _ in range(2):
@@ -346,6 +350,87 @@ def test_optimize_is_deterministic_and_schedule_matches_reference():
     ctx2.set_embedding(y0)
     ctx2.optimize(want_ce=False)
     assert np.abs(ctx2.get_embedding() - before).max() > 1e-3
+
+
+# ------------------------------------------------------------------ K4, asynchronous form (the default on one rank)
+def _async_vs_snapshot(n, d, kmin, kmax, hub, M, flags_async, seed_graph=77):
+    row_ptr, col, dist = random_graph(n, kmin, kmax, seed=seed_graph)
+    y0 = np.random.default_rng(6).uniform(-1, 1, size=(n, d)).astype(np.float32)
+    outs = []
+    # flag 4 (no relabelling) on both sides: the draws are keyed by the internal node ids, and the two forms number the
+    # nodes differently (random order / locality order)
+    for flags in (flags_async | 4, BULK | 1 | 4):
+        ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=2, grad_step=2e-5, seed=13, flags=flags,
+                      hubness_weighting=hub, nb_sampling_by_edge=1, mini_epochs_per_batch=M)
+        ctx.edge_weights(want_outputs=False)
+        if hub:
+            ctx.set_neg_weights(oracle.hubness_weights(row_ptr, col))
+        ctx.set_embedding(y0)
+        ctx.optimize_batches(1, 1)                   # M sweeps / M mini-epochs at gamma = 1e-5
+        st = ctx.get_stats()
+        outs.append((ctx.get_embedding().astype(np.float64), st["positive_samples"], st["epoch_launches"]))
+        ctx.close()
+    return y0, outs
+
+
+# rows: (d, kmin, kmax, hub, M, flags).  kmin == kmax and M == k: kappa == 1 exactly, every node fires once per sweep (the
+# pipelined kernel k_sweep_events with full visits); M < k: several firings per visit (k_sweep_async); flags 1: thread per node
+@pytest.mark.parametrize("d,kmin,kmax,hub,M,flags", [(2, 6, 6, False, 6, 0), (3, 8, 8, True, 8, 0), (4, 16, 16, False, 16, 0), (15, 6, 6, False, 6, 0),
+                                                     (15, 10, 10, True, 10, 0),
+                                                     (2, 6, 6, False, 2, 0), (2, 3, 10, True, 3, 0), (15, 4, 10, True, 3, 0),
+                                                     (2, 6, 6, False, 6, 1), (2, 17, 30, False, 30, 0), (5, 2, 7, True, 2, 1)])
+def test_async_sweeps_apply_the_same_samples_as_the_snapshot_kernels(d, kmin, kmax, hub, M, flags):
+    """The asynchronous sweep (async_sweep.cuh) draws exactly the samples of the bulk-synchronous mini-epoch with the same
+    seed (same firing decisions, same negatives); only the positions a sample reads differ (current instead of the
+    snapshot).  With a tiny gradient step every move is small against the distances, so the two agree to first order:
+    the difference is a small fraction of the move.  Checks the pipelined kernel, the multi-firing kernel, the wide-row
+    paths and the thread-per-node kernel against k_epoch_generic (itself checked against the host build), and that the
+    atomic publication loses nothing (sample counts equal, moves equal)."""
+    y0, ((ya, sa, la), (yb, sb, lb)) = _async_vs_snapshot(6000, d, kmin, kmax, hub, M, flags)
+    assert sa == sb and la == lb == M
+    move = np.abs(yb - y0).max(axis=1)
+    err = np.abs(ya - yb).max(axis=1)
+    assert np.median(move) > 1e-6
+    assert np.median(err) < 0.02 * np.median(move) and np.quantile(err, 0.999) < 0.05 * np.quantile(move, 0.999), \
+        (np.median(err), np.median(move), np.quantile(err, 0.999), np.quantile(move, 0.999))
+
+
+@pytest.mark.parametrize("d,kmin,kmax,hub,M", [(2, 6, 6, False, 24), (2, 3, 10, True, 30), (3, 2, 8, False, 9), (15, 6, 6, False, 13), (2, 16, 16, False, 100)])
+def test_thinned_sweeps_draw_the_same_law_as_the_snapshot_kernels(d, kmin, kmax, hub, M):
+    """Firing probability kappa below 1 per sweep: a tile of 32 nodes fires as a whole with probability kappa (k_sweep_events),
+    where the bulk-synchronous mini-epoch lets every node fire with probability kappa.  Different realisations of the
+    same law: the sample count is binomial around the same expectation and the moves have the same distribution."""
+    n = 20000
+    y0, ((ya, sa, la), (yb, sb, lb)) = _async_vs_snapshot(n, d, kmin, kmax, hub, M, 0, seed_graph=79)
+    assert la == lb == M
+    tiles, kappa = n / 32, sb / (M * n)                       # bulk count: every node, probability kappa, M times
+    sigma = 32 * np.sqrt(M * tiles * kappa * (1 - kappa))       # async count: 32 x Binomial(M tiles, kappa)
+    assert abs(sa - M * n * kappa) < 5 * sigma + 0.01 * sb, (sa, sb, sigma)
+    ma, mb = np.abs(ya - y0).max(axis=1), np.abs(yb - y0).max(axis=1)
+    assert np.isfinite(ya).all() and np.median(mb) > 1e-7
+    for q in (0.5, 0.9, 0.99):
+        assert abs(np.quantile(ma, q) / np.quantile(mb, q) - 1) < 0.1, (q, np.quantile(ma, q), np.quantile(mb, q))
+
+
+def test_async_runs_are_statistically_reproducible():
+    """Two asynchronous runs differ in the interleaving of the warps (like two runs of the reference); they are two
+    realisations of the same optimisation: same sample count, cross entropies within 1 %."""
+    row_ptr, col, dist = random_graph(20000, 6, 6, seed=78)
+    y0 = np.random.default_rng(7).uniform(-1, 1, size=(20000, 2)).astype(np.float32)
+    res = []
+    for _ in range(2):
+        ctx = ctx_for(row_ptr, col, dist, nb_grad_batch=10, grad_step=1.0, seed=3)
+        ctx.edge_weights(want_outputs=False)
+        ctx.set_embedding(y0)
+        ce0, ce1 = ctx.optimize()
+        st = ctx.get_stats()
+        res.append((ce1, st["positive_samples"], st["mini_epochs_per_batch"], st["epoch_launches"]))
+        assert ce1 < ce0 and np.isfinite(ctx.get_embedding()).all()
+        ctx.close()
+    # default schedule: nb_sampling_by_edge * mean degree launches per batch, each of 4 thinned sub-sweeps (firing probability 1/4)
+    assert res[0][1] == res[1][1] and res[0][2] == 240 and res[0][3] == 600
+    assert abs(res[0][1] / (10 * 10 * len(col)) - 1) < 0.02      # 10 batches x 10 samples per edge (binomial over the firing tiles)
+    assert abs(res[0][0] - res[1][0]) < 0.01 * res[0][0]
 
 
 # ------------------------------------------------------------------ ABI behaviour (T9)
@@ -448,7 +533,7 @@ def test_in_edge_scan_across_many_rounds_for_a_hub():
     dist = np.sort(rng.gamma(2.0, 1.0, size=(n, k)).astype(np.float32), axis=1)
     y0 = rng.uniform(-1, 1, size=(n, 2)).astype(np.float32)
     outs = []
-    for flags in (0, 1):
+    for flags in (BULK, BULK | 1):
         ctx = ctx_for(row_ptr, col.reshape(-1), dist.reshape(-1), nb_grad_batch=3, grad_step=1.0, seed=9, flags=flags,
                       nb_sampling_by_edge=1, mini_epochs_per_batch=1)
         ctx.edge_weights(want_outputs=False)
