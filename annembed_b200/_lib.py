@@ -33,6 +33,7 @@ class Stats(C.Structure):
         ("edge_updates", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("model_bytes", C.c_double),
         ("mini_epochs_per_batch", C.c_uint64), ("l2_persist_max_bytes", C.c_uint64), ("l2_window_max_bytes", C.c_uint64),
         ("n_cells", C.c_uint64), ("cell_nodes", C.c_uint64), ("cell_substeps", C.c_uint64), ("cross_cell_edges", C.c_uint64),
+        ("cross_rank_edges", C.c_uint64), ("exchanges", C.c_uint64),
     ]
 
     def as_dict(self):

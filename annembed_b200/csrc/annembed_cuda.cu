@@ -135,6 +135,7 @@ struct annembed_cuda_ctx {
     DevBuf<uint32_t> ext_slot;
     uint64_t ext_cnt = 0;                        // owned in-edges whose source lies in another cell
     uint64_t ext_cnt_global = 0;                 // the same count over the whole graph (identical on every rank)
+    uint64_t cross_rank_edges = 0;               // edges whose ends are owned by different ranks (whole graph)
     uint32_t cell_map_bytes = 0;                 // largest number of in-edges of a cell (whole graph), rounded up to 16
     int smem_optin_max = 0;
     uint32_t last_substeps = 0;
@@ -1550,6 +1551,7 @@ extern "C" int annembed_cuda_comm_import_layouts(annembed_cuda_ctx *ctx, const u
     CU(ctx->barrier_buf.alloc(4));
     CU(cudaMemsetAsync(ctx->barrier_buf.p, 0, 4 * sizeof(float), ctx->stream));
     ctx->have_peers = true;
+    ctx->have_struct = false; ctx->have_build = false;      // the internal numbering depends on the form of K4 (use_async)
     return sync_stream(ctx);
 }
 
@@ -1667,6 +1669,34 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
 //  3. the order inside every cell is then randomised (k_cell_sort_keys explains why);
 //  4. ranks own whole cells (balanced node counts).  Cells do not depend on the number of ranks.
 // Graph only; built once per set_graph_csr.
+struct ShardBounds { uint32_t lo[9]; uint32_t nranks; };
+// sort key of position `pos` of the locality order: (the rank that owns it, a hash of the node)
+__global__ void k_shard_sort_keys(uint64_t n, ShardBounds sb, const uint32_t *__restrict__ order, unsigned long long *__restrict__ key)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r = 0;
+    for (uint32_t q = 1; q < sb.nranks; q++) r += (uint32_t)i >= sb.lo[q] ? 1u : 0u;
+    key[i] = ((unsigned long long)r << 32) | mix32(order[i] * 0x9E3779B1u + 0x7F4A7C15u);
+}
+__global__ void __launch_bounds__(256)
+k_count_cross_rank(uint64_t n, ShardBounds sb, const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, unsigned long long *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int c = 0;
+    if (i < n) {
+        uint32_t ri = 0;
+        for (uint32_t q = 1; q < sb.nranks; q++) ri += (uint32_t)i >= sb.lo[q] ? 1u : 0u;
+        for (uint64_t m = row_ptr[i]; m < row_ptr[i + 1]; m++) {
+            uint32_t rj = 0;
+            for (uint32_t q = 1; q < sb.nranks; q++) rj += col[m] >= sb.lo[q] ? 1u : 0u;
+            c += rj != ri ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
 __global__ void k_hash_keys(uint64_t n, uint32_t salt, uint32_t *__restrict__ key)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1686,7 +1716,8 @@ static int build_relabelling(annembed_cuda_ctx *ctx)
     DevBuf<uint32_t> key, key_s, ord;
     DevBuf<unsigned char> tmp;
     size_t tmp_bytes = 0;
-    if (relabel && use_async(ctx)) {
+    const bool async_form = use_async(ctx);
+    if (relabel && async_form && ctx->nranks == 1) {
         // Asynchronous form: a RANDOM internal order (sort by a hash of the caller's id).  The nodes a warp visits together
         // (a tile), the 4 nodes that share a negative stream and the 4 nodes of a negative's sector must all be unrelated
         // nodes, whatever structure the caller's numbering has: neighbours that move at the same moment, or against the
@@ -1778,8 +1809,6 @@ static int build_relabelling(annembed_cuda_ctx *ctx)
         ctx->st.kernel_launches += 2;
         if ((rc = sync_stream(ctx))) return rc;     // the scratch buffers are released on return
     }
-    k_invert_perm<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->new_of_old.p);
-    ctx->st.kernel_launches++;
     // ---- shards: whole cells, balanced by node count
     ctx->shard_lo.assign(ctx->nranks + 1, (uint32_t)n);
     std::vector<uint32_t> shard_cell(ctx->nranks + 1, ctx->n_cells);
@@ -1793,6 +1822,28 @@ static int build_relabelling(annembed_cuda_ctx *ctx)
     }
     ctx->cell_lo = shard_cell[ctx->rank]; ctx->cell_hi = shard_cell[ctx->rank + 1];
     ctx->lo = ctx->shard_lo[ctx->rank]; ctx->hi = ctx->shard_lo[ctx->rank + 1];
+    if (async_form && ctx->nranks > 1 && n >= 1024 && !(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL)) {
+        // Asynchronous form on several ranks: the ranks keep the graph-local parts of the locality order (few edges
+        // cross ranks), the order INSIDE a rank's part is random (see the single-rank case above)
+        ShardBounds sb;
+        memset(&sb, 0, sizeof sb);
+        sb.nranks = (uint32_t)ctx->nranks;
+        for (int r = 0; r <= ctx->nranks && r <= 8; r++) sb.lo[r] = ctx->shard_lo[r];
+        DevBuf<unsigned long long> k64, k64s;
+        DevBuf<uint32_t> ord2;
+        DevBuf<unsigned char> tmp2;
+        CU(k64.alloc(n)); CU(k64s.alloc(n)); CU(ord2.alloc(n));
+        k_shard_sort_keys<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, sb, ctx->old_of_new.p, k64.p);
+        size_t tb = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, k64.p, k64s.p, ctx->old_of_new.p, ord2.p, (int64_t)n, 0, 64, ctx->stream));
+        CU(tmp2.alloc(tb));
+        CU(cub::DeviceRadixSort::SortPairs(tmp2.p, tb, k64.p, k64s.p, ctx->old_of_new.p, ord2.p, (int64_t)n, 0, 64, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->old_of_new.p, ord2.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->st.kernel_launches += 2;
+        if ((rc = sync_stream(ctx))) return rc;
+    }
+    k_invert_perm<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->new_of_old.p);
+    ctx->st.kernel_launches++;
     CU(cudaGetLastError());
     return sync_stream(ctx);
 }
@@ -1820,6 +1871,20 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
                                                                  ctx->row_ptr2.p, ctx->col2.p);
         ctx->st.kernel_launches += 3;
         if ((rc = sync_stream(ctx))) return rc;
+        ctx->cross_rank_edges = 0;
+        if (ctx->nranks > 1) {
+            ShardBounds sb;
+            memset(&sb, 0, sizeof sb);
+            sb.nranks = (uint32_t)ctx->nranks;
+            for (int r = 0; r <= ctx->nranks && r <= 8; r++) sb.lo[r] = ctx->shard_lo[r];
+            unsigned long long zero = 0ull, res = 0ull;
+            CU(cudaMemcpyAsync(ctx->errword.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream));
+            k_count_cross_rank<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, sb, ctx->row_ptr2.p, ctx->col2.p, ctx->errword.p);
+            CU(cudaMemcpyAsync(&res, ctx->errword.p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+            if ((rc = sync_stream(ctx))) return rc;
+            ctx->cross_rank_edges = res;
+            ctx->st.kernel_launches++;
+        }
     }
     CU(ctx->in_ptr_all.alloc(n + 2));
     DevBuf<uint32_t> eid, dst_sorted, eid_sorted;
@@ -2373,9 +2438,11 @@ extern "C" int annembed_cuda_get_embedded_scales(annembed_cuda_ctx *ctx, float *
 #ifndef ANNEMBED_ASYNC_THIN
 #define ANNEMBED_ASYNC_THIN 4u           // thinned sub-sweeps per launch (kappa = 1 per launch in total)
 #endif
+// several ranks: needs the peers' replicas (annembed_cuda_comm_import_layouts); without them the bulk-synchronous form
+// with the NCCL all-gather runs
 static bool use_async(const annembed_cuda_ctx *ctx)
 {
-    return ctx->nranks == 1 &&
+    return (ctx->nranks == 1 || ctx->have_peers) &&
            !(ctx->prm.flags & (ANNEMBED_FLAG_BULK_SYNCHRONOUS | ANNEMBED_FLAG_REPLAY_IN_EDGES | ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS));
 }
 // Bulk-synchronous form (ANNEMBED_FLAG_BULK_SYNCHRONOUS, and every multi-rank run): mini-epochs per reference batch.
@@ -2674,6 +2741,15 @@ static unsigned int async_blocks(const annembed_cuda_ctx *ctx, uint64_t units, u
 }
 // visiting order of a sweep's tiles (TileOrder, async_sweep.cuh): multiplier ~ tiles / golden ratio, coprime with tiles
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; }
+static PeerMap peer_map(const annembed_cuda_ctx *ctx)
+{
+    PeerMap pm;
+    memset(&pm, 0, sizeof pm);
+    pm.nranks = (uint32_t)ctx->nranks;
+    for (int r = 0; r < ctx->nranks && r < 8; r++) { pm.y[r] = ctx->nranks > 1 ? ctx->peer_y[r][0] : ctx->y[0].p; pm.lo[r] = ctx->shard_lo[r]; }
+    pm.lo[std::min(ctx->nranks, 8)] = (uint32_t)ctx->n;
+    return pm;
+}
 static TileOrder tile_order(uint64_t tiles, uint64_t warps_total)
 {
     TileOrder o;
@@ -2696,7 +2772,9 @@ static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a, u
         const unsigned int resident = (unsigned int)(ctx->sm_count * TE::MINB);
         const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa / 8.0) / TE::WARPS);
         const unsigned int nb = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(want, resident), async_blocks(ctx, tiles, TE::WARPS * 32 * TE::VISITS, DP));
-        k_sweep_events<DP, HUB, KP><<<nb, TE::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, tile_order(tiles, (uint64_t)nb * TE::WARPS), subs,
+        cudaError_t e = cudaFuncSetAttribute(k_sweep_events<DP, HUB, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TE::SMEM);
+        if (e != cudaSuccess) return e;
+        k_sweep_events<DP, HUB, KP><<<nb, TE::WARPS * 32, TE::SMEM, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * TE::WARPS), subs,
                                                                                 ctx->counter.p);
         return cudaGetLastError();
     }
@@ -2705,7 +2783,7 @@ static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a, u
     using TL = EpochTile<DP, KP>;
     const uint64_t tiles = (owned + 31) / 32;
     const unsigned int nb = async_blocks(ctx, (tiles + TL::WARPS - 1) / TL::WARPS, TL::WARPS * 32, DP);
-    k_sweep_async<DP, HUB, KP><<<nb, TL::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, tile_order(tiles, (uint64_t)nb * TL::WARPS), ctx->counter.p);
+    k_sweep_async<DP, HUB, KP><<<nb, TL::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * TL::WARPS), ctx->counter.p);
     return cudaGetLastError();
 }
 template <int DP, bool HUB>
@@ -2722,7 +2800,7 @@ static cudaError_t launch_async_dp(annembed_cuda_ctx *ctx, const EpochArgs &a, u
     }
     const uint64_t tiles = ((uint64_t)(a.hi - a.lo) + 31) / 32;
     const unsigned int nb = async_blocks(ctx, (tiles + 3) / 4, 128, DP);
-    k_sweep_async_generic<DP, HUB><<<nb, 128, 0, ctx->launch_stream>>>(a, ctx->y[0].p, tile_order(tiles, (uint64_t)nb * 4), ctx->counter.p);
+    k_sweep_async_generic<DP, HUB><<<nb, 128, 0, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * 4), ctx->counter.p);
     return cudaGetLastError();
 }
 template <bool HUB>
@@ -2735,6 +2813,15 @@ static cudaError_t launch_async(annembed_cuda_ctx *ctx, const EpochArgs &a, uint
     case 16: return launch_async_dp<16, HUB>(ctx, a, subs);
     default: return launch_async_dp<32, HUB>(ctx, a, subs);
     }
+}
+// Several ranks, asynchronous form: the owners' rows are copied to all replicas every X launches (X samples per node).
+// In between a rank reads the other ranks' nodes as of the last exchange: harmless for the negatives (measured with the
+// cell kernel: up to 2 samples per edge), a loss of fidelity for the positive edges that cross ranks -- the fewer of
+// those, the longer the period.
+static uint32_t async_exchange_every(const annembed_cuda_ctx *ctx)
+{
+    const double f = ctx->E ? (double)ctx->cross_rank_edges / (double)ctx->E : 0.0;
+    return f <= 0.02 ? 8u : (f <= 0.10 ? 4u : (f <= 0.30 ? 2u : 1u));
 }
 // sub-sweeps per launch of the asynchronous form: the default schedule runs its ANNEMBED_ASYNC_THIN thinned sub-sweeps of a
 // sweep in one launch (k_sweep_events); an explicit mini_epochs_per_batch makes every sweep its own launch
@@ -2793,7 +2880,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     size_t li = 0;
     ctx->last_substeps = 0;
     const size_t xoff = 2 * n_launch;
-    size_t n_kernels = 0;
+    size_t n_kernels = 0, n_exchanges = 0;
     for (uint32_t iter = first_batch; iter < last; iter++) {
         const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
         const uint32_t M = mini_epochs_of_batch(ctx, iter), e0 = first_epoch_of_batch(ctx, iter);
@@ -2813,6 +2900,18 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
                 CU(hub ? launch_async<true>(ctx, a, std::min(S, M - m)) : launch_async<false>(ctx, a, std::min(S, M - m)));
                 CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
                 n_kernels += 1;
+                if (ctx->nranks > 1) {
+                    const bool last_launch = iter + 1 == last && m + S >= M;
+                    CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
+                    if ((li + 1) % async_exchange_every(ctx) == 0 || last_launch) {
+                        n_exchanges++;
+                        // every rank has finished its launch (its reductions on the peers' replicas have landed), then the
+                        // owners' rows go to all replicas
+                        if ((rc = rank_barrier(ctx))) return rc;
+                        if ((rc = exchange_rows_nccl(ctx, ctx->y[0].p))) return rc;
+                    }
+                    CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream));
+                }
                 continue;
             }
             const bool cells = use_cells(ctx, a.kappa);
@@ -2842,6 +2941,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
             CU(cudaEventRecord(ctx->ev[2 * li + 1], ctx->stream));
             if (ctx->nranks > 1) {
                 CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
+                n_exchanges++;
                 if (fused) {
                     // the kernel already stored the owned rows into every replica: only a barrier is left
                     if ((rc = rank_barrier(ctx))) return rc;
@@ -2869,7 +2969,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
         if (ctx->nranks > 1) { CU(cudaEventElapsedTime(&t, ctx->ev[xoff + 2 * i], ctx->ev[xoff + 2 * i + 1])); xms += t; }
     }
     ctx->st.optimize_ms = ms; ctx->st.epoch_kernel_ms = kms; ctx->st.exchange_ms = xms;
-    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_kernels;
+    ctx->st.epoch_launches = n_launch; ctx->st.kernel_launches += n_kernels; ctx->st.exchanges = n_exchanges;
     ctx->st.positive_samples = cnt; ctx->st.edge_updates = 6 * cnt;
     ctx->st.model_bytes = (double)cnt * (12.0 + 36.0 * (double)ctx->prm.asked_dim);
     return ANNEMBED_OK;
@@ -2950,6 +3050,7 @@ extern "C" int annembed_cuda_get_stats(annembed_cuda_ctx *ctx, annembed_cuda_sta
     stats->cell_nodes = ctx->cell_nodes;
     stats->cell_substeps = ctx->last_substeps;
     stats->cross_cell_edges = ctx->have_struct ? ctx->ext_cnt_global : 0;
+    stats->cross_rank_edges = ctx->have_struct ? ctx->cross_rank_edges : 0;
     return ANNEMBED_OK;
 }
 extern "C" int annembed_cuda_reset_stats(annembed_cuda_ctx *ctx)

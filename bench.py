@@ -60,7 +60,8 @@ def parse():
 
 def workload_name(a):
     return (f"synthetic {a.nodes}x28 Higgs-shape mixture, cluster-blocked exact kNN k={a.knn}, shuffled node ids, "
-            f"0.5% duplicate rows; embed dim {a.dim}; {a.batches} batches x 10 samples/edge; scale_rho 0.75, grad_step 1")
+            f"0.5% duplicate rows (disconnected 4096-node blocks: no long-range edges, no hubs); embed dim {a.dim}; "
+            f"{a.batches} batches x 10 samples/edge; scale_rho 0.75, grad_step 1")
 
 
 def make_inputs(a, device):
@@ -133,6 +134,30 @@ def hbm_peak():
         return float(v["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def bulk(a, world):
+    """True when the bulk-synchronous (snapshot) form of K4 runs: ANNEMBED_FLAG_BULK_SYNCHRONOUS / REPLAY / LEGACY, or several
+    ranks without peer memory (--no-fused)."""
+    return bool(a.flags & (32 | 16 | 8)) or (world > 1 and a.no_fused)
+
+
+def kernel_name(a, world):
+    if bulk(a, world):
+        return "K4, bulk-synchronous form: k_cell_epochs / k_epoch_out + k_epoch_in per mini-epoch"
+    return "K4, asynchronous form: k_sweep_events (one launch = 4 thinned sub-sweeps, one sample per node in expectation)"
+
+
+def parallelism_name(a, world, st):
+    if world == 1:
+        return "single GPU"
+    if bulk(a, world):
+        return f"node-sharded x{world}, replicated layout, bulk-synchronous; " + (
+            "NCCL all-gather per mini-epoch" if a.no_fused else "fused exchange: peer-memory row stores + 4-byte all-reduce per mini-epoch")
+    return (f"node-sharded x{world} (graph-local parts), replicated layout, asynchronous sweeps; moves of nodes owned elsewhere are "
+            f"reduced into the owner's replica over NVLink (red.global on peer memory), owners' rows all-gathered every "
+            f"{max(1, int(st['epoch_launches']) // max(1, int(st['exchanges'])))} launches ({int(st['exchanges'])} exchanges per embed, "
+            f"{int(st['cross_rank_edges'])} cross-rank edges)")
 
 
 def ncu_traffic():
@@ -242,8 +267,11 @@ def run_ours(a):
            "edge_weights_ms": 0.0, "build_ms": 0.0, "cross_entropy_ms": 0.0, "model_bytes": 0.0}
     barrier()
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(a.steps):
+        ts = time.perf_counter()
         ce = step()
+        step_ms.append(round(1e3 * (time.perf_counter() - ts), 2))
         st = ctx.get_stats()
         for k in agg:
             agg[k] += st[k]
@@ -308,7 +336,7 @@ def run_ours(a):
         per_launch_bytes = agg["model_bytes"] / max(1, agg["epoch_launches"])
         per_launch_s = 1e-3 * agg["epoch_kernel_ms"] / max(1, agg["epoch_launches"])
         achieved = per_launch_bytes / per_launch_s / 1e9
-        # the committed ncu capture is of the default workload (C3: 11M nodes, k=6, d=2, uniform negatives, graded schedule)
+        # the committed ncu capture is of the default workload (C3: 11M nodes, k=6, d=2, uniform negatives, default schedule)
         c3 = a.nodes == 11_000_000 and a.knn == 6 and a.dim == 2 and not a.hubness and not a.mini_epochs and a.batches == 40 and world == 1
         traffic = ncu_traffic() if c3 else None
         line = {
@@ -318,18 +346,17 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "mini_epochs_per_batch": int(mini), "flags": a.flags,
                        "l2_persist_max_bytes": int(st["l2_persist_max_bytes"]), "l2_window_max_bytes": int(st["l2_window_max_bytes"]),
                        "l2": "inputs larger than L2 (graph + transposed index > 2 GB per pass); no flush needed",
-                       "parallelism": (f"node-sharded x{world}, replicated layout, " + ("NCCL all-gather per mini-epoch" if a.no_fused else
-                                       "fused exchange: peer-memory row stores from the in-edge kernel + 4-byte all-reduce per mini-epoch")) if world > 1 else "single GPU",
+                       "parallelism": parallelism_name(a, world, st),
                        "positive_samples_per_step": samples / a.steps, "input_build_s": t_in,
                        "cross_entropy_last_step": list(ce)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                         "peak_source": peak_src, "kernel": "k_epoch (K4)",
+                         "peak_source": peak_src, "kernel": kernel_name(a, world),
                          "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": 1e3 * per_launch_s,
                          "model": "positive samples x (12 + 36 d) bytes (SURVEY.md 8d)"},
             "breakdown_ms_per_step": {k: agg[k] / a.steps for k in ("edge_weights_ms", "build_ms", "optimize_ms", "epoch_kernel_ms",
                                                                       "exchange_ms", "cross_entropy_ms")},
-            "gpu_launches": int(launches_all),
+            "gpu_launches": int(launches_all), "ms_steps": step_ms,
             "clocks": clk,
         }
         if e2e is not None:

@@ -100,6 +100,8 @@ typedef struct annembed_cuda_stats {
     uint64_t cell_nodes;           /* largest cell size */
     uint64_t cell_substeps;        /* mini-epochs per launch of the cell kernel in the last optimize (0: not used) */
     uint64_t cross_cell_edges;     /* edges of the graph whose ends lie in different cells */
+    uint64_t cross_rank_edges;     /* edges of the graph whose ends are owned by different ranks (0 on one rank) */
+    uint64_t exchanges;            /* row exchanges between the ranks in the last optimize (0 on one rank) */
 } annembed_cuda_stats;
 
 typedef struct annembed_cuda_ctx annembed_cuda_ctx;

@@ -72,6 +72,8 @@ pub struct annembed_cuda_stats {
     pub cell_nodes: u64,
     pub cell_substeps: u64,
     pub cross_cell_edges: u64,
+    pub cross_rank_edges: u64,
+    pub exchanges: u64,
 }
 
 /// ≙ the statistics logged by get_quality_estimate_from_edge_length (src/embedder.rs:620-753)

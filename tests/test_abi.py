@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # annembed_cuda_params: 2 u32, 4 f64, 6 u32 (+pad), u64, 2 u32
     assert C.sizeof(_lib.Params) == 8 + 32 + 24 + 8 + 8
-    assert C.sizeof(_lib.Stats) == 20 * 8
+    assert C.sizeof(_lib.Stats) == 22 * 8
     p = _lib.Params()
     assert A.load().annembed_cuda_default_params(C.byref(p)) == 0
     # EmbedderParams::default(), embedparams.rs:107-132
