@@ -147,6 +147,7 @@ struct annembed_cuda_ctx {
     DevBuf<uint32_t> in_src, in_eid; // structure of the transposed index (graph only)
     uint64_t in_cnt = 0;
     bool have_struct = false;
+    bool struct_async = false;     // the structures were built for the asynchronous form (no transposed index)
     uint64_t in_base = 0;
     DevBuf<uint2> neg_alias_old, neg_alias;   // alias table in the caller's / in the internal numbering
     DevBuf<float> yapi, y0;        // current and initial layout in the caller's node order
@@ -582,6 +583,11 @@ __global__ void k_cell_in_max(uint32_t cell_lo, uint32_t cell_hi, const uint32_t
     atomicMax(out_max, (unsigned int)(in_ptr_all[cell_start[c + 1]] - in_ptr_all[cell_start[c]]));
 }
 
+__global__ void k_in_degree(uint64_t E, const uint32_t *__restrict__ col, uint32_t *__restrict__ cnt)
+{
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < E) atomicAdd(cnt + col[m], 1u);
+}
 __global__ void k_degree_u32(uint64_t n, const uint64_t *__restrict__ ptr, uint32_t *__restrict__ out)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1886,6 +1892,24 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
             ctx->st.kernel_launches++;
         }
     }
+    ctx->KP = ctx->kmax <= 6 ? 6 : (ctx->kmax <= 8 ? 8 : (ctx->kmax <= 10 ? 10 : (ctx->kmax <= 16 ? 16 : 0)));
+    if (use_async(ctx)) {
+        // the asynchronous form publishes the destination's move with an atomic: no transposed index, no in-edge records,
+        // no slot maps -- only the padded rows (filled by ensure_build)
+        ctx->rowpack.release(); ctx->erank.release(); ctx->fired.release(); ctx->in_rec.release(); ctx->in_src.release(); ctx->in_eid.release();
+        ctx->in_ptr_all.release(); ctx->ext_ptr.release(); ctx->ext_slot.release();
+        ctx->in_cnt = 0; ctx->in_base = 0; ctx->ext_cnt = 0; ctx->ext_cnt_global = 0; ctx->cell_map_bytes = 0;
+        if (ctx->KP) {
+            CU(ctx->rowpack.alloc((n + 32) * (uint64_t)ctx->KP));
+            CU(cudaMemsetAsync(ctx->rowpack.p, 0xff, (n + 32) * (uint64_t)ctx->KP * sizeof(uint2), ctx->stream));
+        }
+        if ((rc = sync_stream(ctx))) return rc;
+        ctx->have_struct = true;
+        ctx->struct_async = true;
+        ctx->alias_dirty = ctx->have_alias;
+        return ANNEMBED_OK;
+    }
+    ctx->struct_async = false;
     CU(ctx->in_ptr_all.alloc(n + 2));
     DevBuf<uint32_t> eid, dst_sorted, eid_sorted;
     DevBuf<unsigned char> tmp;
@@ -1915,7 +1939,6 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
         ctx->st.kernel_launches++;
     }
     // rows of the tiled kernels (rows of at most 16 neighbours): padded length, slot map, byte map of firing counts
-    ctx->KP = ctx->kmax <= 6 ? 6 : (ctx->kmax <= 8 ? 8 : (ctx->kmax <= 10 ? 10 : (ctx->kmax <= 16 ? 16 : 0)));
     ctx->rowpack.release(); ctx->erank.release(); ctx->fired.release();
     ctx->ext_ptr.release(); ctx->ext_slot.release(); ctx->ext_cnt = 0; ctx->cell_map_bytes = 0;
     if (ctx->KP) {
@@ -2025,18 +2048,14 @@ extern "C" int annembed_cuda_get_hubness_counts(annembed_cuda_ctx *ctx, uint32_t
     REQUIRE(counts, ANNEMBED_ERR_INVALID_ARG, "null output");
     REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "get_hubness_counts: graph not set");
     CU(cudaSetDevice(ctx->device));
-    // in-degree of every node = segment lengths of the transposed index (graph only)
-    {
-        int rc0 = ensure_struct(ctx);
-        if (rc0) return rc0;
-    }
-    DevBuf<uint32_t> t, t_old; CU(t.alloc(ctx->n)); CU(t_old.alloc(ctx->n));
-    k_degree_u32<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->in_ptr_all.p, t.p);        // internal numbering
-    k_gather_u32<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->new_of_old.p, t.p, t_old.p);
-    ctx->st.kernel_launches += 2;
+    // in-degree of every node (fromhnsw/hubness.rs:39-76): a histogram of the neighbour lists, caller's numbering
+    DevBuf<uint32_t> t; CU(t.alloc(ctx->n));
+    CU(cudaMemsetAsync(t.p, 0, ctx->n * sizeof(uint32_t), ctx->stream));
+    k_in_degree<<<nblocks(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->col.p, t.p);
+    ctx->st.kernel_launches += 1;
     int rc;
     if ((rc = sync_stream(ctx))) return rc;
-    return d2h(ctx, counts, t_old.p, ctx->n * sizeof(uint32_t));
+    return d2h(ctx, counts, t.p, ctx->n * sizeof(uint32_t));
 }
 
 extern "C" int annembed_cuda_set_embedding(annembed_cuda_ctx *ctx, const float *y)
@@ -2545,7 +2564,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.y_next = ctx->y[ctx->cur ^ 1].p;
     // everything below is in the internal numbering
     a.row_ptr = ctx->row_ptr2.p; a.col = ctx->col2.p; a.p = nullptr; a.inv_s2 = ctx->inv_s2n.p;
-    a.in_ptr = ctx->in_ptr_all.p + ctx->lo; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
+    a.in_ptr = ctx->in_ptr_all.p ? ctx->in_ptr_all.p + ctx->lo : nullptr; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
     a.neg_alias = ctx->neg_alias.p;
     a.cum = ctx->cum.p;
     a.rowpack = ctx->rowpack.p; a.erank = ctx->erank.p;
@@ -2772,9 +2791,7 @@ static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a, u
         const unsigned int resident = (unsigned int)(ctx->sm_count * TE::MINB);
         const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa / 8.0) / TE::WARPS);
         const unsigned int nb = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(want, resident), async_blocks(ctx, tiles, TE::WARPS * 32 * TE::VISITS, DP));
-        cudaError_t e = cudaFuncSetAttribute(k_sweep_events<DP, HUB, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TE::SMEM);
-        if (e != cudaSuccess) return e;
-        k_sweep_events<DP, HUB, KP><<<nb, TE::WARPS * 32, TE::SMEM, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * TE::WARPS), subs,
+        k_sweep_events<DP, HUB, KP><<<nb, TE::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * TE::WARPS), subs,
                                                                                 ctx->counter.p);
         return cudaGetLastError();
     }

@@ -372,17 +372,15 @@ __global__ void __launch_bounds__(128) k_sweep_async_generic(EpochArgs a, float 
 // u_i(s) lands on (cumulative row probability).  A tile that does not fire costs a dozen warp-uniform instructions and no
 // memory access; a tile that fires is read with full-width coalesced loads.  The sub-sweeps of one launch follow each
 // other inside the persistent warps without any grid-wide synchronisation (nothing in the asynchronous form needs one).
-// The work on the firing tiles is pipelined three deep across the warp's visits:
-//   load    visit v+2: the tile's rows (KP/2 16-byte streaming loads per node), positions and scales;
-//   gather  visit v+1: rows have arrived -> edge, negatives (rejection against the row in registers), then the 6 row
-//                      gathers (y_j + 5 negatives) are issued and the row registers are dead;
+// The work on the firing tiles is pipelined across the warp's visits:
+//   stage   visits v+1 .. v+3: the tile's rows ({neighbour, cumulative probability} pairs, 32 x KP x 8 bytes, contiguous),
+//                      positions and scales are copied into a per-warp ring in shared memory by TMA bulk copies
+//                      (cp.async.bulk, completion on an mbarrier): no register is tied up by data in flight;
+//   gather  visit v+1: rows have arrived -> edge, negatives (rejection against the row), then the 6 row gathers
+//                      (y_j + 5 negatives) are issued into registers and the ring slot is handed back to the TMA;
 //   apply   visit v  : gathers have arrived -> attraction, reduction on y_j, 5 repulsions, reduction of the node's move.
-// Two register sets of gathered rows alternate (PA / PB) for layouts of dimension <= 4, one set of tile rows.  The firing
-// tiles are found 32 at a time (every lane tests one candidate of the warp's visiting sequence, one ballot).
-// Measured and dropped (profiles/r02_ab_tma_vs_ldg.txt): staging the tile rows through shared memory with TMA bulk copies
-// (cp.async.bulk + mbarrier, 3 slots per warp) instead of the `load` stage's register set -- 7.6 % slower on the C3
-// workload: the rows are consumed once, by the thread that would have loaded them, and the slot hand-over costs more
-// issue slots than the 15 registers it frees are worth at 5 resident blocks.
+// Two register sets of gathered rows alternate (PA / PB) for layouts of dimension <= 4.  The firing tiles are found 32 at
+// a time (every lane tests one candidate of the warp's visiting sequence, one ballot).
 #ifndef ANNEMBED_EVENTS_MINB
 #define ANNEMBED_EVENTS_MINB 5
 #endif
@@ -390,7 +388,13 @@ template <int DP, int KP>
 struct EventTile {
     static constexpr int WARPS = 4;
     static constexpr int MINB = DP <= 2 ? (KP <= 8 ? ANNEMBED_EVENTS_MINB : 4) : (DP <= 4 ? 3 : (DP <= 8 ? 2 : 1));
-    static constexpr int VISITS = DP <= 4 ? 3 : 2;       // visits a warp has in flight (in-flight window of the launch)
+    static constexpr int VISITS = DP <= 4 ? 3 : 2;       // visits a warp has in flight past the staging ring (in-flight window)
+    // staging ring of one warp: NS slots of {rows, positions, scales, meta}, then NS mbarriers
+    static constexpr int NS = 3;
+    static constexpr int ROW_B = 32 * KP * 8, Y_B = 32 * DP * 4, S2_B = 128, META_B = 16;
+    static constexpr int SLOT_B = ROW_B + Y_B + S2_B + META_B;
+    static constexpr int WARP_B = NS * SLOT_B + ((NS * 8 + 15) / 16) * 16;
+    static constexpr int SMEM = WARPS * WARP_B;
 };
 
 __device__ __forceinline__ bool tile_fires(uint32_t tile, uint32_t ukey, float kappa)
@@ -404,18 +408,23 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
 {
     static_assert(KP % 2 == 0, "rows are padded to an even number of entries (16-byte loads)");
     using TL = EventTile<DP, KP>;
+    extern __shared__ __align__(128) unsigned char ev_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t w0 = blockIdx.x * TL::WARPS + wib, wtot = gridDim.x * TL::WARPS;
+    unsigned char *wsm = ev_smem + (size_t)wib * TL::WARP_B;
+    const uint32_t wsa = (uint32_t)__cvta_generic_to_shared(wsm);
+    auto slot_ptr = [&](uint32_t s) { return wsm + (size_t)s * TL::SLOT_B; };
+    auto slot_addr = [&](uint32_t s) { return wsa + s * TL::SLOT_B; };
+    auto bar_addr = [&](uint32_t s) { return wsa + TL::NS * TL::SLOT_B + 8u * s; };
+    if (lane == 0) {
+#pragma unroll
+        for (uint32_t s = 0; s < (uint32_t)TL::NS; s++) mbar_init(bar_addr(s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncwarp();
     unsigned int applied = 0;
 
-    struct Rows {                        // one visit, stage `load`
-        uint32_t node;                   // ANNEMBED_NO_NODE: lane beyond the end of the numbering
-        uint32_t rc[KP];
-        float cm[KP];
-        float y[DP];
-        float inv_s2;
-        uint32_t epoch, ukey;
-    };
     struct Pre {                         // one visit, stage `gather`
         uint32_t node, j;                // node == NO_NODE: idle lane
         float pe, inv_s2;
@@ -425,7 +434,7 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
     // ---- the warp's visits: sub-sweep `sub`, positions idx = w0, w0 + wtot, ... of the visiting order, firing tiles only.
     // Window of 32 candidates: lane l holds position base_idx + l * wtot, i.e. tile base_tile + l * ord.step (mod tiles).
     uint32_t sub = 0;
-    uint32_t base_idx = w0;              // < tiles + 32 wtot < 2^32 (tiles <= 2^27)
+    uint64_t base_idx = w0;
     uint32_t base_tile = ord.first(w0);
     uint32_t epoch = a.epoch, ukey = a.ukey;
     const uint32_t lane_off = (uint32_t)(((uint64_t)lane * ord.step) % ord.tiles);
@@ -435,7 +444,7 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
         uint32_t t = base_tile + lane_off;
         t = t >= ord.tiles ? t - ord.tiles : t;
         my_tile = t;
-        const bool fire = base_idx + (uint32_t)lane * wtot < ord.tiles && tile_fires(t, ukey, a.kappa);
+        const bool fire = base_idx + (uint64_t)lane * wtot < ord.tiles && tile_fires(t, ukey, a.kappa);
         pend = __ballot_sync(0xffffffffu, fire);
     };
     if (subs > 0) scan_window();
@@ -448,7 +457,7 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
                 return true;
             }
             if (sub >= subs) return false;
-            base_idx += 32u * wtot;
+            base_idx += 32ull * wtot;
             if (base_idx >= ord.tiles) {
                 if (++sub >= subs) return false;
                 base_idx = w0; base_tile = ord.first(w0);
@@ -460,53 +469,71 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
             scan_window();
         }
     };
-    auto next_visit = [&](Rows &R) -> bool {
+    // stage the next firing tile into slot s (meta: {tile, epoch, ukey, valid})
+    auto stage = [&](uint32_t s) {
         uint32_t tile = 0;
-        if (!next_tile(tile)) return false;
-        const uint64_t n0 = (uint64_t)a.lo + (uint64_t)tile * 32;
-        const bool valid = n0 + lane < a.hi;
-        const uint32_t node = (uint32_t)n0 + (valid ? lane : 0);
-        const uint4 *rp = reinterpret_cast<const uint4 *>(a.rowpack + (size_t)node * KP);
-#pragma unroll
-        for (int h = 0; h < KP / 2; h++) {
-            const uint4 t = __ldcs(rp + h);
-            R.rc[2 * h] = t.x; R.cm[2 * h] = __uint_as_float(t.y);
-            R.rc[2 * h + 1] = t.z; R.cm[2 * h + 1] = __uint_as_float(t.w);
+        const bool ok = next_tile(tile);
+        if (lane == 0) {
+            uint4 meta;
+            meta.x = tile; meta.y = epoch; meta.z = ukey; meta.w = ok ? 1u : 0u;
+            *reinterpret_cast<uint4 *>(slot_ptr(s) + TL::ROW_B + TL::Y_B + TL::S2_B) = meta;
+            if (ok) {
+                const uint64_t n0 = (uint64_t)a.lo + (uint64_t)tile * 32;
+                mbar_expect_tx(bar_addr(s), TL::ROW_B + TL::Y_B + TL::S2_B);
+                tma_load_1d(slot_addr(s), a.rowpack + (size_t)n0 * KP, TL::ROW_B, bar_addr(s));
+                tma_load_1d(slot_addr(s) + TL::ROW_B, Y + (size_t)n0 * DP, TL::Y_B, bar_addr(s));
+                tma_load_1d(slot_addr(s) + TL::ROW_B + TL::Y_B, a.inv_s2 + n0, TL::S2_B, bar_addr(s));
+            }
         }
-        load_row_cg<DP>(Y, node, R.y);
-        R.inv_s2 = __ldcs(a.inv_s2 + node);
-        R.node = valid ? node : ANNEMBED_NO_NODE;
-        R.epoch = epoch; R.ukey = ukey;
-        return true;
+        __syncwarp();
     };
-    auto gather = [&](const Rows &R, Pre &P) {
-        const bool act = R.node != ANNEMBED_NO_NODE;
-        const uint32_t node = act ? R.node : a.lo;
-        const float u = node_uniform(node, R.ukey);
+    // visit number v lives in slot v % NS, phase (v / NS) & 1 of its mbarrier
+    auto gather = [&](uint32_t v, Pre &P) -> bool {
+        const uint32_t s = v % TL::NS;
+        const uint4 meta = *reinterpret_cast<const uint4 *>(slot_ptr(s) + TL::ROW_B + TL::Y_B + TL::S2_B);
+        if (meta.w == 0u) return false;
+        mbar_wait(bar_addr(s), (v / TL::NS) & 1u);
+        const uint64_t n0 = (uint64_t)a.lo + (uint64_t)meta.x * 32;
+        const bool act = n0 + lane < a.hi;
+        const uint32_t node = (uint32_t)n0 + lane;             // staged rows cover the whole tile (arrays are padded)
+        uint32_t rc[KP];
+        float cm[KP];
+        {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(slot_ptr(s)) + (size_t)lane * (KP / 2);
+#pragma unroll
+            for (int h = 0; h < KP / 2; h++) {
+                const uint4 t = rp[h];
+                rc[2 * h] = t.x; cm[2 * h] = __uint_as_float(t.y);
+                rc[2 * h + 1] = t.z; cm[2 * h + 1] = __uint_as_float(t.w);
+            }
+        }
+        load_row<DP>(reinterpret_cast<const float *>(slot_ptr(s) + TL::ROW_B), (uint32_t)lane, P.y);
+        P.inv_s2 = reinterpret_cast<const float *>(slot_ptr(s) + TL::ROW_B + TL::Y_B)[lane];
+        const uint32_t vepoch = meta.y;
+        const float u = node_uniform(node, meta.z);
+        __syncwarp();                                           // every lane has read the slot:
+        stage(s);                                               // hand it back to the TMA for visit v + NS
         // the edge the node's sample point u lands on: the first edge whose cumulative probability exceeds u
         int m = 0;
 #pragma unroll
-        for (int mm = 0; mm < KP; mm++) m += cum_ceil(1.0f, R.cm[mm], u) <= 0 ? 1 : 0;      // pads have cum == 1 > u
-        uint32_t j = R.rc[0];
-        float P_hi = R.cm[0], P_lo = 0.0f;
+        for (int mm = 0; mm < KP; mm++) m += cum_ceil(1.0f, cm[mm], u) <= 0 ? 1 : 0;           // pads have cum == 1 > u
+        uint32_t j = rc[0];
+        float P_hi = cm[0], P_lo = 0.0f;
 #pragma unroll
         for (int mm = 1; mm < KP; mm++) {
             const bool t = m >= mm;
-            j = t ? R.rc[mm] : j; P_hi = t ? R.cm[mm] : P_hi; P_lo = t ? R.cm[mm - 1] : P_lo;
+            j = t ? rc[mm] : j; P_hi = t ? cm[mm] : P_hi; P_lo = t ? cm[mm - 1] : P_lo;
         }
         const bool fires = act && j != ANNEMBED_NO_NODE;
         P.node = fires ? node : ANNEMBED_NO_NODE;
-        P.j = fires ? j : node;
+        P.j = fires ? j : a.lo;
         P.pe = F_SUB(P_hi, P_lo);
-        P.inv_s2 = R.inv_s2;
-#pragma unroll
-        for (int c = 0; c < DP; c++) P.y[c] = R.y[c];
         load_row_cg<DP>(Y, P.j, P.yj);
         uint32_t id_lo = node, id_hi = node;
 #pragma unroll
         for (int mm = 0; mm < KP; mm++) {
-            const uint32_t v = R.rc[mm] == ANNEMBED_NO_NODE ? node : R.rc[mm];
-            id_lo = min(id_lo, v); id_hi = max(id_hi, v);
+            const uint32_t vv = rc[mm] == ANNEMBED_NO_NODE ? node : rc[mm];
+            id_lo = min(id_lo, vv); id_hi = max(id_hi, vv);
         }
         const uint32_t id_span = id_hi - id_lo;
         auto rejected = [&](uint32_t kk) -> bool {
@@ -514,20 +541,21 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
             if (kk - id_lo <= id_span) {
                 r = (kk == node);
 #pragma unroll
-                for (int mm = 0; mm < KP; mm++) r |= (kk == R.rc[mm]);
+                for (int mm = 0; mm < KP; mm++) r |= (kk == rc[mm]);
             }
             return r;
         };
-        const Philox4 A = philox4x32_10(neg_stream_key<HUB>(a, node), 0u, R.epoch, 1u, a.k0, a.k1);
+        const Philox4 A = philox4x32_10(neg_stream_key<HUB>(a, node), 0u, vepoch, 1u, a.k0, a.k1);
         uint32_t negs[ANNEMBED_NB_NEG];
-        draw_negatives_v2<HUB>(a, R.epoch, node, 0u, A, rejected, negs);
+        draw_negatives_v2<HUB>(a, vepoch, node, 0u, A, rejected, negs);
         P.use = 0;
 #pragma unroll
         for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
             const bool ok = negs[q] != ANNEMBED_NO_NODE;
             P.use |= ok ? (1u << q) : 0u;
-            load_row_cg<DP>(Y, ok ? negs[q] : node, P.yk[q]);
+            load_row_cg<DP>(Y, ok ? negs[q] : a.lo, P.yk[q]);
         }
+        return true;
     };
     auto apply = [&](Pre &P) {
         if (P.node == ANNEMBED_NO_NODE) return;
@@ -544,26 +572,23 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
         applied++;
     };
 
-    Rows R;
-    bool more = next_visit(R);
+#pragma unroll
+    for (uint32_t s = 0; s < (uint32_t)TL::NS; s++) stage(s);                // visits 0 .. NS-1
+    uint32_t v = 0;
     if constexpr (DP <= 4) {
         Pre PA, PB;
         PA.node = PB.node = ANNEMBED_NO_NODE;
-        bool haveA = false, haveB = false;
-        if (more) { gather(R, PA); haveA = true; more = next_visit(R); }
+        bool haveA = gather(v, PA);
         while (haveA) {
-            if (more) { gather(R, PB); haveB = true; more = next_visit(R); } else haveB = false;
+            const bool haveB = gather(v + 1, PB);
             apply(PA);
-            if (more) { gather(R, PA); haveA = true; more = next_visit(R); } else haveA = false;
+            haveA = haveB && gather(v + 2, PA);
             if (haveB) apply(PB);
+            v += 2;
         }
-    } else {                             // wide rows: one set of gathered rows; the next visit's tile rows load during apply
+    } else {                             // wide rows: one set of gathered rows
         Pre PA;
-        while (more) {
-            gather(R, PA);
-            more = next_visit(R);
-            apply(PA);
-        }
+        while (gather(v, PA)) { apply(PA); v++; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) applied += __shfl_xor_sync(0xffffffffu, applied, o);
