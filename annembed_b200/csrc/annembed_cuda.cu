@@ -1826,6 +1826,11 @@ static int build_relabelling(annembed_cuda_ctx *ctx)
         c = std::min(c, ctx->n_cells);
         shard_cell[r] = c; ctx->shard_lo[r] = cs[c];
     }
+    if (async_form && ctx->nranks > 1) {
+        // asynchronous form: equal parts of the locality order (whole tiles), so that the row exchange is ONE in-place
+        // ncclAllGather; a part boundary may cut one cell
+        for (int r = 1; r < ctx->nranks; r++) ctx->shard_lo[r] = (uint32_t)std::min<uint64_t>(n, (uint64_t)r * ctx->n_pad);
+    }
     ctx->cell_lo = shard_cell[ctx->rank]; ctx->cell_hi = shard_cell[ctx->rank + 1];
     ctx->lo = ctx->shard_lo[ctx->rank]; ctx->hi = ctx->shard_lo[ctx->rank + 1];
     if (async_form && ctx->nranks > 1 && n >= 1024 && !(ctx->prm.flags & ANNEMBED_FLAG_NO_RELABEL)) {
@@ -2842,10 +2847,16 @@ static uint32_t async_exchange_every(const annembed_cuda_ctx *ctx)
 }
 // sub-sweeps per launch of the asynchronous form: the default schedule runs its ANNEMBED_ASYNC_THIN thinned sub-sweeps of a
 // sweep in one launch (k_sweep_events); an explicit mini_epochs_per_batch makes every sweep its own launch
+// One launch runs several sweeps' worth of sub-sweeps back to back inside its persistent warps (a warp always visits the
+// same tiles, so the order of a node's samples is kept; the warps drift against each other, which the asynchronous form
+// does not mind): ANNEMBED_ASYNC_SWEEPS_PER_LAUNCH sweeps on one rank, the sweeps between two row exchanges on several.
+#ifndef ANNEMBED_ASYNC_SWEEPS_PER_LAUNCH
+#define ANNEMBED_ASYNC_SWEEPS_PER_LAUNCH 4u
+#endif
 static uint32_t async_subs(const annembed_cuda_ctx *ctx, float kappa)
 {
     if (ctx->prm.mini_epochs_per_batch || !async_tiled(ctx, kappa) || kappa > 1.0f) return 1u;
-    return ANNEMBED_ASYNC_THIN;
+    return ANNEMBED_ASYNC_THIN * (ctx->nranks > 1 ? async_exchange_every(ctx) : ANNEMBED_ASYNC_SWEEPS_PER_LAUNCH);
 }
 
 // replicate the rows every rank owns (rank-dependent counts): one broadcast per rank, grouped
@@ -2859,6 +2870,15 @@ static int exchange_rows_nccl(annembed_cuda_ctx *ctx, float *buf)
     const ncclResult_t r2 = g_nccl.GroupEnd();
     if (r == ncclSuccess) r = r2;
     if (r != ncclSuccess) { ctx->err = std::string("ncclBroadcast (row exchange): ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
+    return ANNEMBED_OK;
+}
+
+// asynchronous form: the parts are equal (n_pad rows per rank): one in-place all-gather of the owners' rows
+static int exchange_rows_allgather(annembed_cuda_ctx *ctx, float *buf)
+{
+    const size_t cnt = (size_t)ctx->n_pad * ctx->DP;
+    ncclResult_t r = g_nccl.AllGather(buf + (size_t)ctx->rank * cnt, buf, cnt, ncclFloat, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather (row exchange): ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
     return ANNEMBED_OK;
 }
 
@@ -2920,12 +2940,15 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
                 if (ctx->nranks > 1) {
                     const bool last_launch = iter + 1 == last && m + S >= M;
                     CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
-                    if ((li + 1) % async_exchange_every(ctx) == 0 || last_launch) {
+                    // default schedule: a launch holds the sweeps between two exchanges; explicit schedule (one sweep per
+                    // launch): every async_exchange_every launches.  No barrier: the owner's replica accumulates every
+                    // reduction whenever it lands, a late one simply travels with the next exchange.
+                    const uint32_t every = S > 1 ? 1u : async_exchange_every(ctx);
+                    if ((li + 1) % every == 0 || last_launch) {
                         n_exchanges++;
-                        // every rank has finished its launch (its reductions on the peers' replicas have landed), then the
-                        // owners' rows go to all replicas
-                        if ((rc = rank_barrier(ctx))) return rc;
-                        if ((rc = exchange_rows_nccl(ctx, ctx->y[0].p))) return rc;
+                        // (the last one closes the run: every rank's reductions must have landed before the rows travel)
+                        if (last_launch && (rc = rank_barrier(ctx))) return rc;
+                        if ((rc = exchange_rows_allgather(ctx, ctx->y[0].p))) return rc;
                     }
                     CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream));
                 }

@@ -67,6 +67,6 @@ def test_asynchronous_sharded_is_the_same_optimisation(tmp_path, world, n, d):
     assert np.isfinite(multi["y"]).all() and multi["y"].shape == y.shape
     assert abs(float(multi["samples"][0]) / st["positive_samples"] - 1) < 0.02
     assert abs(float(multi["samples"][0]) / (4 * 10 * E) - 1) < 0.02
-    assert multi["ce"][0] == ce[0]                                     # the same initial layout, the same K5
+    assert abs(multi["ce"][0] / ce[0] - 1) < 1e-12                     # the same initial layout, the same K5 (fp64 partial sums per rank)
     assert abs(multi["ce"][1] / ce[1] - 1) < 0.03 and multi["ce"][1] < multi["ce"][0]
     assert 0 < int(multi["exchanges"]) <= int(multi["launches"]) and int(multi["cross_rank_edges"]) > 0

@@ -427,8 +427,8 @@ def test_async_runs_are_statistically_reproducible():
         res.append((ce1, st["positive_samples"], st["mini_epochs_per_batch"], st["epoch_launches"]))
         assert ce1 < ce0 and np.isfinite(ctx.get_embedding()).all()
         ctx.close()
-    # default schedule: nb_sampling_by_edge * mean degree launches per batch, each of 4 thinned sub-sweeps (firing probability 1/4)
-    assert res[0][1] == res[1][1] and res[0][2] == 240 and res[0][3] == 600
+    # default schedule: 4 * nb_sampling_by_edge * mean degree thinned sub-sweeps per batch (firing probability 1/4), 16 per launch
+    assert res[0][1] == res[1][1] and res[0][2] == 240 and res[0][3] == 150
     assert abs(res[0][1] / (10 * 10 * len(col)) - 1) < 0.02      # 10 batches x 10 samples per edge (binomial over the firing tiles)
     assert abs(res[0][0] - res[1][0]) < 0.01 * res[0][0]
 
