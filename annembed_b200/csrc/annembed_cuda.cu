@@ -2791,10 +2791,10 @@ static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a, u
 #ifndef ANNEMBED_ASYNC_POISSON
     if (a.kappa <= 1.0f) {
         using TE = EventTile<DP, KP>;
-        // persistent warps: at most the resident blocks, the in-flight window, and ~8 firing tiles per warp and sub-sweep
+        // persistent warps: at most the resident blocks, the in-flight window, and ~8 firing tiles per warp and launch
         const uint64_t tiles = (owned + 31) / 32;
         const unsigned int resident = (unsigned int)(ctx->sm_count * TE::MINB);
-        const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa / 8.0) / TE::WARPS);
+        const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa * (double)subs / 8.0) / TE::WARPS);
         const unsigned int nb = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(want, resident), async_blocks(ctx, tiles, TE::WARPS * 32 * TE::VISITS, DP));
         k_sweep_events<DP, HUB, KP><<<nb, TE::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * TE::WARPS), subs,
                                                                                 ctx->counter.p);
@@ -2874,10 +2874,10 @@ static int exchange_rows_nccl(annembed_cuda_ctx *ctx, float *buf)
 }
 
 // asynchronous form: the parts are equal (n_pad rows per rank): one in-place all-gather of the owners' rows
-static int exchange_rows_allgather(annembed_cuda_ctx *ctx, float *buf)
+static int exchange_rows_allgather(annembed_cuda_ctx *ctx, float *buf, cudaStream_t stream)
 {
     const size_t cnt = (size_t)ctx->n_pad * ctx->DP;
-    ncclResult_t r = g_nccl.AllGather(buf + (size_t)ctx->rank * cnt, buf, cnt, ncclFloat, ctx->comm, ctx->stream);
+    ncclResult_t r = g_nccl.AllGather(buf + (size_t)ctx->rank * cnt, buf, cnt, ncclFloat, ctx->comm, stream);
     if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather (row exchange): ") + g_nccl.GetErrorString(r); return ANNEMBED_ERR_COMM; }
     return ANNEMBED_OK;
 }
@@ -2918,6 +2918,7 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
     ctx->last_substeps = 0;
     const size_t xoff = 2 * n_launch;
     size_t n_kernels = 0, n_exchanges = 0;
+    bool forked = false;
     for (uint32_t iter = first_batch; iter < last; iter++) {
         const double grad_step = ctx->prm.grad_step * (1.0 - (double)iter / (double)nb);   // embedder.rs:875
         const uint32_t M = mini_epochs_of_batch(ctx, iter), e0 = first_epoch_of_batch(ctx, iter);
@@ -2939,18 +2940,36 @@ extern "C" int annembed_cuda_optimize_batches(annembed_cuda_ctx *ctx, uint32_t f
                 n_kernels += 1;
                 if (ctx->nranks > 1) {
                     const bool last_launch = iter + 1 == last && m + S >= M;
-                    CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
                     // default schedule: a launch holds the sweeps between two exchanges; explicit schedule (one sweep per
                     // launch): every async_exchange_every launches.  No barrier: the owner's replica accumulates every
-                    // reduction whenever it lands, a late one simply travels with the next exchange.
+                    // reduction whenever it lands, a late one simply travels with the next exchange.  The exchange runs on
+                    // the second stream, UNDER the next launch: a sweep reads the other ranks' rows at whatever age they
+                    // have and only ever writes rows through reductions on their owners, so rows that change under it (or
+                    // travel while they are reduced into) are part of the asynchronous semantics.
                     const uint32_t every = S > 1 ? 1u : async_exchange_every(ctx);
-                    if ((li + 1) % every == 0 || last_launch) {
+                    const bool xchg = (li + 1) % every == 0 || last_launch;
+                    if (xchg && !last_launch) {
                         n_exchanges++;
-                        // (the last one closes the run: every rank's reductions must have landed before the rows travel)
-                        if (last_launch && (rc = rank_barrier(ctx))) return rc;
-                        if ((rc = exchange_rows_allgather(ctx, ctx->y[0].p))) return rc;
+                        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                        CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream2));
+                        if ((rc = exchange_rows_allgather(ctx, ctx->y[0].p, ctx->stream2))) return rc;
+                        CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream2));
+                        forked = true;
+                    } else {
+                        if (last_launch && forked) {               // join the exchanges in flight
+                            CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+                        }
+                        CU(cudaEventRecord(ctx->ev[xoff + 2 * li], ctx->stream));
+                        if (xchg) {
+                            // the last exchange closes the run: every rank's reductions must have landed before the rows travel
+                            n_exchanges++;
+                            if ((rc = rank_barrier(ctx))) return rc;
+                            if ((rc = exchange_rows_allgather(ctx, ctx->y[0].p, ctx->stream))) return rc;
+                        }
+                        CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream));
                     }
-                    CU(cudaEventRecord(ctx->ev[xoff + 2 * li + 1], ctx->stream));
                 }
                 continue;
             }
