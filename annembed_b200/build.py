@@ -12,9 +12,13 @@ SOURCES = ["annembed_cuda.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "annembed_cuda.h")]
 
 NVCC_FLAGS = [
-    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-split-compile", "0",
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",
 ]
+# Development builds: `-split-compile 0` halves the build time (1.5 instead of 3.5 minutes), but the code ptxas generates
+# for k_sweep_events was then seen to vary from build to build of the SAME source (96 registers with or without 160 bytes of
+# spills: 27 % difference in time per embed, profiles/r02_ab_build_flags.txt).  The shipped library is built without it.
+FAST_BUILD_FLAGS = ["-split-compile", "0"]
 
 
 def _nvcc() -> str:
@@ -37,9 +41,12 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), ou
     target = out or LIB
     if not force and out is None and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    # `verbose` prints the resource usage of every kernel afterwards (cuobjdump), not ptxas -v
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
+    if verbose:
+        cuobjdump = os.path.join(os.path.dirname(_nvcc()), "cuobjdump")
+        subprocess.call([cuobjdump, "--dump-resource-usage", target])
     return target
 
 

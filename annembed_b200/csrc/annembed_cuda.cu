@@ -463,14 +463,18 @@ __global__ void k_relabel_rows(uint64_t n, const uint32_t *__restrict__ old_of_n
     for (uint64_t m = 0; m < k; m++) col2[w0 + m] = new_of_old[col[r0 + m]];
 }
 // rows of the tiled kernels: KP entries {neighbour, bits(cumulative probability)} per node, pads {NO_NODE, 1.0f}
-__global__ void k_rowpack(uint64_t n, int KP, const uint64_t *__restrict__ row_ptr2, const uint32_t *__restrict__ col2,
+// Rows padded to KP {neighbour, cumulative probability} pairs: [node][KP].  `interleave` (per tile of 32 nodes
+// [pair h = m / 2][lane][m & 1]: the h-th 16-byte load of a warp reads 512 contiguous bytes) was measured and is not used:
+// the L1 already merges the three loads of a lane, +0.5 % (profiles/r02_ab_row_layout.txt).
+__global__ void k_rowpack(uint64_t n, int KP, int interleave, const uint64_t *__restrict__ row_ptr2, const uint32_t *__restrict__ col2,
                           const float *__restrict__ cum, uint2 *__restrict__ rowpack)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * (uint64_t)KP) return;
     const uint64_t i = t / KP; const uint64_t m = t % KP;
     const uint64_t r0 = row_ptr2[i], k = row_ptr2[i + 1] - r0;
-    rowpack[t] = m < k ? make_uint2(col2[r0 + m], __float_as_uint(cum[r0 + m])) : make_uint2(ANNEMBED_NO_NODE, __float_as_uint(1.0f));
+    const uint64_t w = interleave ? ((((i >> 5) * (uint64_t)(KP / 2) + (m >> 1)) * 32 + (i & 31)) * 2 + (m & 1)) : t;
+    rowpack[w] = m < k ? make_uint2(col2[r0 + m], __float_as_uint(cum[r0 + m])) : make_uint2(ANNEMBED_NO_NODE, __float_as_uint(1.0f));
 }
 // erank[src * KP + m] = position q of out-edge m of src in the transposed index
 __global__ void k_erank(uint64_t cnt, uint64_t q_lo, int KP, const uint32_t *__restrict__ in_src, const uint32_t *__restrict__ in_eid,
@@ -2022,7 +2026,8 @@ static int ensure_build(annembed_cuda_ctx *ctx)
         k_gather_f32<<<nblocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->old_of_new.p, ctx->inv_s2.p, ctx->inv_s2n.p);
         ctx->st.kernel_launches += 2;
         if (ctx->KP) {
-            k_rowpack<<<nblocks(n * (uint64_t)ctx->KP, 256), 256, 0, ctx->stream>>>(n, ctx->KP, ctx->row_ptr2.p, ctx->col2.p, ctx->cum.p, ctx->rowpack.p);
+            k_rowpack<<<nblocks(n * (uint64_t)ctx->KP, 256), 256, 0, ctx->stream>>>(n, ctx->KP, 0, ctx->row_ptr2.p, ctx->col2.p, ctx->cum.p,
+                                                                                    ctx->rowpack.p);
             ctx->st.kernel_launches++;
         }
         if (ctx->in_cnt) {

@@ -1,4 +1,4 @@
-// K4, asynchronous form (the default on one rank): k_sweep_async / k_sweep_async_generic.
+// K4, asynchronous form (the default): k_sweep_events / k_sweep_async / k_sweep_async_generic.
 //
 // The reference loop (gradient_iteration_threaded, embedder.rs:1311-1315 -> ce_optim_edge_shannon :1167-1302) is
 // asynchronous itself: every rayon thread reads the two ends and the negatives at whatever position they have,
@@ -7,21 +7,21 @@
 // publishes its moves at once with float atomics (red.global.add: +g on y_j after the attraction, the node's own
 // accumulated move at the end of its firings).  Atomic adds instead of the reference's read-modify-write under a row
 // lock: no concurrent move is ever lost (the reference loses the moves that land between its read and its write).
-// What a sample can miss is bounded by the samples in flight (<= the resident threads, a few 10^5, against the 10^7-10^8
-// samples of a batch), not by a mini-epoch: there is no snapshot, no in-edge replay, no second kernel.
+// What a sample can miss is bounded by the samples in flight, not by a mini-epoch: there is no snapshot, no in-edge
+// replay, no second kernel.
 //
-// Sampling is the systematic per-node sampler of sgd_core.cuh (node i fires ceil(kappa - u_i) times per sweep, edge m
-// with expectation kappa p_m -- the reference's edge law, embedder.rs:858,987); a sweep visits the nodes in index order
-// (the internal, locality-relabelled order), `sweeps per batch` = mini_epochs_per_batch.  Negatives: the shared-sector
-// draws of draw_negatives_v2 (uniform or hubness alias).
+// Sampling is the systematic per-node sampler of sgd_core.cuh: the edge of a firing node is the one its uniform u_i(sweep)
+// lands on in the cumulative row probability -- the reference's edge law (embedder.rs:858,987).  Negatives: the
+// shared-sector draws of draw_negatives_v2 (uniform or hubness alias).
 //
-// In-flight bound: on small graphs the whole node set would be resident at once and a sweep would degenerate into one
-// bulk-synchronous mini-epoch.  The launch therefore caps the resident nodes at n / ANNEMBED_ASYNC_WINDOW_DIV
-// (persistent warps striding over the tiles); large graphs fill the machine.
+// Three things decide whether the layout statistics match the reference's (each measured against the oracle fixtures,
+// DESIGN.md 4): the internal order of the nodes is RANDOM (nodes in flight together, or sharing negatives, must not be
+// graph neighbours: build_relabelling); the nodes in flight are capped at a fraction of n (async_blocks); a node's
+// samples must arrive irregularly, like the reference's independent draws (thinned sub-sweeps, k_sweep_events below).
 //
 // The result depends on the interleaving of the warps: runs are NOT bit-reproducible (neither are the reference's:
 // unseeded thread-local RNG, embedder.rs:1182).  ANNEMBED_FLAG_BULK_SYNCHRONOUS selects the deterministic
-// snapshot kernels instead (also what several ranks use).
+// snapshot kernels instead.
 #pragma once
 
 #ifndef ANNEMBED_ASYNC_WINDOW_DIV
@@ -42,6 +42,13 @@ struct TileOrder {
     __device__ __forceinline__ uint32_t first(uint32_t w) const { return (uint32_t)(((uint64_t)w * mul) % tiles); }
     __device__ __forceinline__ uint32_t next(uint32_t t) const { const uint32_t v = t + step; return v >= tiles ? v - tiles : v; }
 };
+
+// the node's padded row: KP/2 16-byte loads (the three loads of a lane hit the same two sectors: the L1 merges them)
+template <int KP>
+__device__ __forceinline__ const uint4 *async_row_ptr(const uint2 *rowpack, uint32_t node)
+{
+    return reinterpret_cast<const uint4 *>(rowpack + (size_t)node * KP);
+}
 
 template <int DP>
 __device__ __forceinline__ void load_row_cg(const float *Y, uint32_t idx, float (&v)[DP])
@@ -114,7 +121,7 @@ k_sweep_async(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, unsigned long lo
         float inv_s2 = 1.0f;
         int T = 0;
         {
-            const uint4 *rp = reinterpret_cast<const uint4 *>(a.rowpack + (size_t)(valid ? node : (uint32_t)n0) * KP);
+            const uint4 *rp = async_row_ptr<KP>(a.rowpack, valid ? node : (uint32_t)n0);
 #pragma unroll
             for (int h = 0; h < KP / 2; h++) {
                 const uint4 t = __ldcs(rp + h);
@@ -466,7 +473,7 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
         const uint64_t n0 = (uint64_t)a.lo + (uint64_t)tile * 32;
         const bool valid = n0 + lane < a.hi;
         const uint32_t node = (uint32_t)n0 + (valid ? lane : 0);
-        const uint4 *rp = reinterpret_cast<const uint4 *>(a.rowpack + (size_t)node * KP);
+        const uint4 *rp = async_row_ptr<KP>(a.rowpack, node);
 #pragma unroll
         for (int h = 0; h < KP / 2; h++) {
             const uint4 t = __ldcs(rp + h);
@@ -486,7 +493,7 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
         // the edge the node's sample point u lands on: the first edge whose cumulative probability exceeds u
         int m = 0;
 #pragma unroll
-        for (int mm = 0; mm < KP; mm++) m += cum_ceil(1.0f, R.cm[mm], u) <= 0 ? 1 : 0;      // pads have cum == 1 > u
+        for (int mm = 0; mm < KP; mm++) m += R.cm[mm] <= u ? 1 : 0;     // == (cum_ceil(1, cm, u) <= 0); pads have cum == 1 > u
         uint32_t j = R.rc[0];
         float P_hi = R.cm[0], P_lo = 0.0f;
 #pragma unroll
@@ -502,20 +509,11 @@ k_sweep_events(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t subs, 
 #pragma unroll
         for (int c = 0; c < DP; c++) P.y[c] = R.y[c];
         load_row_cg<DP>(Y, P.j, P.yj);
-        uint32_t id_lo = node, id_hi = node;
-#pragma unroll
-        for (int mm = 0; mm < KP; mm++) {
-            const uint32_t v = R.rc[mm] == ANNEMBED_NO_NODE ? node : R.rc[mm];
-            id_lo = min(id_lo, v); id_hi = max(id_hi, v);
-        }
-        const uint32_t id_span = id_hi - id_lo;
+        // rejection test against the row in registers (the internal order is random: no id range worth a pre-test)
         auto rejected = [&](uint32_t kk) -> bool {
-            bool r = false;
-            if (kk - id_lo <= id_span) {
-                r = (kk == node);
+            bool r = (kk == node);
 #pragma unroll
-                for (int mm = 0; mm < KP; mm++) r |= (kk == R.rc[mm]);
-            }
+            for (int mm = 0; mm < KP; mm++) r |= (kk == R.rc[mm]);
             return r;
         };
         const Philox4 A = philox4x32_10(neg_stream_key<HUB>(a, node), 0u, R.epoch, 1u, a.k0, a.k1);

@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed only carries the 128-byte NCCL id.
 
-The data path has ONE exchange step, inside the C library: an in-place ncclAllGather of the rows each rank owns
-after every mini-epoch (csrc/annembed_cuda.cu).  Nodes are partitioned in contiguous ranges of ceil(n/R).
+The data path has ONE exchange step, inside the C library (csrc/annembed_cuda.cu): an in-place ncclAllGather
+of the rows each rank owns every few sweeps, under the next launch; with peer memory (exchange_layout_handles) the moves
+of nodes owned elsewhere are reduced straight into the owner's replica over NVLink.
 """
 from __future__ import annotations
 
@@ -11,7 +12,8 @@ import numpy as np
 
 
 def shard_range(n: int, rank: int, nranks: int) -> tuple[int, int]:
-    """Owned node range of `rank` -- must match set_shard() in csrc/annembed_cuda.cu."""
+    """Owned node range of `rank` in the library's INTERNAL node order (set_shard() in csrc/annembed_cuda.cu; the internal
+    order is a relabelling, so this is not a range of the caller's ids)."""
     n_pad = ((n + nranks - 1) // nranks + 31) // 32 * 32          # whole warp tiles per shard
     return min(n, rank * n_pad), min(n, (rank + 1) * n_pad)
 
@@ -41,7 +43,7 @@ def broadcast_unique_id(make_id, rank: int, nranks: int) -> np.ndarray | None:
 
 
 def exchange_layout_handles(ctx, rank: int, nranks: int) -> None:
-    """Fused exchange set-up: all-gather the CUDA IPC handles of every rank's layout buffers (2 x 64 bytes each)
+    """Peer-memory set-up: all-gather the CUDA IPC handles of every rank's layout buffers (2 x 64 bytes each)
     through torch.distributed and open them in `ctx` (annembed_cuda_comm_import_layouts)."""
     if nranks == 1:
         return

@@ -285,7 +285,7 @@ class Embedder:
         self.cross_entropy = (None, None)
         self.device = device
         self.comm = comm                          # (rank, nranks, unique_id) or None
-        self.fused_exchange = fused_exchange      # peer-memory stores from the epoch kernel instead of an all-gather
+        self.fused_exchange = fused_exchange      # open the peers' layout buffers (asynchronous form on several ranks)
         self.context = context                    # optional long-lived device context (keeps its NCCL communicator and
                                                   # peer mappings across embeds); by default embed() creates and destroys one
         self.write_quality_csv = False            # the reference dumps first_dist.csv / continuity_ratio.csv (embedder.rs:729-743)

@@ -116,15 +116,18 @@ int annembed_cuda_destroy(annembed_cuda_ctx *ctx);
 const char *annembed_cuda_last_error(const annembed_cuda_ctx *ctx);
 
 /* ---- multi-GPU (one context per rank). No reference counterpart (single process, rayon). ----
- * Node range [rank*ceil(n/nranks), ...) is owned by `rank`; the n x d layout is replicated and
- * all-gathered once per mini-epoch.  unique_id is the 128-byte ncclUniqueId made by rank 0. */
+ * Every rank owns (fires, and holds the authoritative rows of) a part of the nodes; graph and n x d layout are replicated.
+ * unique_id is the 128-byte ncclUniqueId made by rank 0. */
 int annembed_cuda_comm_unique_id(uint8_t unique_id[128]);
 int annembed_cuda_comm_init(annembed_cuda_ctx *ctx, int rank, int nranks, const uint8_t unique_id[128]);
 
-/* Fused exchange (optional; after set_graph_csr on every rank): instead of the all-gather, the in-edge kernel stores
- * every owned row straight into all replicas over NVLink (peer memory opened through CUDA IPC) while the other tiles
- * are still computing, and a 4-byte all-reduce closes the mini-epoch.  export: 2 x 64-byte cudaIpcMemHandle_t of this
- * rank's two layout buffers; import: the handles of all ranks, rank-major (nranks x 128 bytes). */
+/* Peer memory (optional; after set_graph_csr on every rank): opens every rank's layout buffers on every rank (CUDA IPC).
+ * With it the asynchronous form runs on several ranks: moves of nodes owned elsewhere are reduced straight into the
+ * owner's replica over NVLink, the owners' rows are all-gathered every few sweeps under the next launch.
+ * (With ANNEMBED_FLAG_BULK_SYNCHRONOUS: the snapshot kernels store every owned row into all replicas, a 4-byte
+ * all-reduce closes the mini-epoch.)  Without it: bulk-synchronous form, NCCL broadcast of the owned rows per mini-epoch.
+ * export: 2 x 64-byte cudaIpcMemHandle_t of this rank's two layout buffers; import: the handles of all ranks, rank-major
+ * (nranks x 128 bytes). */
 int annembed_cuda_comm_export_layout(annembed_cuda_ctx *ctx, uint8_t handles[128]);
 int annembed_cuda_comm_import_layouts(annembed_cuda_ctx *ctx, const uint8_t *all_handles);
 
