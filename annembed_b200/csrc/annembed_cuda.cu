@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "sgd_core.cuh"
@@ -150,6 +151,8 @@ struct annembed_cuda_ctx {
     bool struct_async = false;     // the structures were built for the asynchronous form (no transposed index)
     uint64_t in_base = 0;
     DevBuf<uint2> neg_alias_old, neg_alias;   // alias table in the caller's / in the internal numbering
+    DevBuf<uint4> sec_alias;                  // sector-level alias table, internal numbering (2 x uint4 per sector of 4 nodes)
+    std::vector<float> neg_w_host;            // the caller's sampling weights (kept to build the sector table once the numbering is known)
     DevBuf<float> yapi, y0;        // current and initial layout in the caller's node order
     DevBuf<float> y[2];            // double-buffered layout of the epoch loop, internal node order (exported to the peers)
     int cur = 0;
@@ -905,6 +908,7 @@ k_epoch_out(EpochArgs a, unsigned long long *sample_counter)
 }
 
 #include "async_sweep.cuh"    // the asynchronous form of K4 (default on one rank)
+#include "sweep_events_cp.cuh" // ... its kappa <= 1 kernel for layouts of dimension <= 4, pipelined through cp.async groups
 
 #ifndef ANNEMBED_WARPS_IN
 #define ANNEMBED_WARPS_IN 4
@@ -1638,7 +1642,7 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
     REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_neg_weights: graph not set");
     CU(cudaSetDevice(ctx->device));
-    if (!w) { ctx->have_alias = false; ctx->neg_alias.release(); ctx->neg_alias_old.release(); return ANNEMBED_OK; }
+    if (!w) { ctx->have_alias = false; ctx->neg_alias.release(); ctx->neg_alias_old.release(); ctx->sec_alias.release(); ctx->neg_w_host.clear(); return ANNEMBED_OK; }
     const uint64_t n = ctx->n;
     double tot = 0.0;
     for (uint64_t i = 0; i < n; i++) {
@@ -1667,6 +1671,7 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
     CU(ctx->neg_alias_old.alloc(n));
     int rc;
     if ((rc = h2d(ctx, ctx->neg_alias_old.p, tab.data(), n * sizeof(uint2)))) return rc;
+    ctx->neg_w_host.assign(w, w + n);
     ctx->have_alias = true; ctx->alias_dirty = true;
     return ANNEMBED_OK;
 }
@@ -2002,6 +2007,57 @@ static int ensure_struct(annembed_cuda_ctx *ctx)
     return ANNEMBED_OK;
 }
 
+// Sector-level alias table of the hubness sampler (embedder.rs:909-931 NodeSampler, restated one level up): Vose's alias
+// method over the SECTORS of 4 consecutive nodes of the internal numbering (weight = the sum of the 4 node weights), plus the 3
+// cumulative thresholds that pick a node inside a sector.  P(node) = P(sector) * P(node | sector): exactly the node law.
+// The 4 lanes of a group share the sector draw and its accept / alias decision (ONE coalesced table sector, then ONE
+// coalesced row sector of the layout) and each picks its row from a rotation of one shared uniform
+// (tests/studies/sector_alias_study.py: chi-square per lane; tests/test_gpu_parity.py on the device).
+// Entry of sector s (32 bytes, one memory sector, so that the draw is ONE gather and branch-free):
+// uint4 {bits(prob), alias sector, bits(thr0), bits(thr1)}, uint4 {bits(thr2), bits(thr0), bits(thr1), bits(thr2) of the ALIAS sector}.
+static int build_sector_alias(annembed_cuda_ctx *ctx)
+{
+    const uint64_t n = ctx->n, nsec = (n + 3) / 4;
+    if (ctx->neg_w_host.size() != n) { ctx->sec_alias.release(); return ANNEMBED_OK; }
+    std::vector<uint32_t> old_of_new(n);
+    CU(cudaMemcpyAsync(old_of_new.data(), ctx->old_of_new.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc;
+    if ((rc = sync_stream(ctx))) return rc;
+    std::vector<double> q(nsec);
+    std::vector<uint4> tab(2 * nsec);
+    double tot = 0.0;
+    auto fbits = [](float f) { uint32_t b; memcpy(&b, &f, 4); return b; };
+    for (uint64_t s = 0; s < nsec; s++) {
+        double w4[4], W = 0.0;
+        for (int r = 0; r < 4; r++) { const uint64_t i = 4 * s + r; w4[r] = i < n ? (double)ctx->neg_w_host[old_of_new[i]] : 0.0; W += w4[r]; }
+        q[s] = W; tot += W;
+        // cumulative thresholds; a sector of zero weight is never drawn (prob 0 -> its alias), missing rows weigh 0
+        float t0 = 1.0f, t1 = 1.0f, t2 = 1.0f;
+        if (W > 0.0) { t0 = (float)(w4[0] / W); t1 = (float)((w4[0] + w4[1]) / W); t2 = (float)((w4[0] + w4[1] + w4[2]) / W); }
+        tab[2 * s] = make_uint4(0u, (uint32_t)s, fbits(t0), fbits(t1));
+        tab[2 * s + 1] = make_uint4(fbits(t2), 0u, 0u, 0u);
+    }
+    std::vector<uint32_t> small, large;
+    small.reserve(nsec); large.reserve(nsec);
+    for (uint64_t s = 0; s < nsec; s++) { q[s] = q[s] * (double)nsec / tot; (q[s] < 1.0 ? small : large).push_back((uint32_t)s); }
+    auto put = [&](uint32_t s, float prob, uint32_t alias) { tab[2 * (size_t)s].x = fbits(prob); tab[2 * (size_t)s].y = alias; };
+    while (!small.empty() && !large.empty()) {
+        const uint32_t sm = small.back(); small.pop_back();
+        const uint32_t lg = large.back(); large.pop_back();
+        put(sm, (float)q[sm], lg);
+        q[lg] = (q[lg] + q[sm]) - 1.0;
+        (q[lg] < 1.0 ? small : large).push_back(lg);
+    }
+    for (uint32_t lg : large) put(lg, 1.0f, lg);
+    for (uint32_t sm : small) put(sm, 1.0f, sm);
+    for (uint64_t s = 0; s < nsec; s++) {       // the alias sector's thresholds ride in the entry: no second table gather
+        const uint32_t al = tab[2 * s].y;
+        tab[2 * s + 1].y = tab[2 * (size_t)al].z; tab[2 * s + 1].z = tab[2 * (size_t)al].w; tab[2 * s + 1].w = tab[2 * (size_t)al + 1].x;
+    }
+    CU(ctx->sec_alias.alloc(2 * nsec));
+    return h2d(ctx, ctx->sec_alias.p, tab.data(), 2 * nsec * sizeof(uint4));
+}
+
 // device context build, weights part: K2 + cumulative row probabilities + rows + in-edge payloads
 // (≙ EntropyOptim::new, embedder.rs:964-1025)
 static int ensure_build(annembed_cuda_ctx *ctx)
@@ -2047,6 +2103,7 @@ alias:
         k_relabel_alias<<<nblocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->new_of_old.p, ctx->neg_alias_old.p, ctx->neg_alias.p);
         ctx->st.kernel_launches++;
         if ((rc = sync_stream(ctx))) return rc;
+        if ((rc = build_sector_alias(ctx))) return rc;
         ctx->alias_dirty = false;
     }
     return ANNEMBED_OK;
@@ -2576,6 +2633,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.row_ptr = ctx->row_ptr2.p; a.col = ctx->col2.p; a.p = nullptr; a.inv_s2 = ctx->inv_s2n.p;
     a.in_ptr = ctx->in_ptr_all.p ? ctx->in_ptr_all.p + ctx->lo : nullptr; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
     a.neg_alias = ctx->neg_alias.p;
+    a.sec_alias = (ctx->prm.flags & ANNEMBED_FLAG_NODE_ALIAS) ? nullptr : ctx->sec_alias.p;
     a.cum = ctx->cum.p;
     a.rowpack = ctx->rowpack.p; a.erank = ctx->erank.p;
     a.fired = (ctx->nranks == 1 && !(ctx->prm.flags & ANNEMBED_FLAG_REPLAY_IN_EDGES)) ? ctx->fired.p : nullptr;
@@ -2789,15 +2847,44 @@ static TileOrder tile_order(uint64_t tiles, uint64_t warps_total)
     o.step = tiles ? (uint32_t)((warps_total * (uint64_t)o.mul) % tiles) : 0u;
     return o;
 }
-template <int DP, bool HUB, int KP>
-static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a, uint32_t subs)
+// event kernels (kappa <= 1), uniform sampler: the nodes whose rows share a 128-byte line of the layout share their
+// negative streams (sgd_core.cuh neg_stream_key); ANNEMBED_FLAG_SECTOR_NEGATIVES keeps the 4-node groups (A/B)
+static uint32_t event_neg_group_shift(const annembed_cuda_ctx *ctx)
 {
+    if (ctx->prm.flags & ANNEMBED_FLAG_SECTOR_NEGATIVES) return 0u;
+    return ctx->DP == 2 ? 4u : (ctx->DP == 4 ? 3u : 0u);
+}
+template <int DP, bool HUB, int KP>
+static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a_in, uint32_t subs)
+{
+    EpochArgs a = a_in;
     const uint64_t owned = (uint64_t)(a.hi - a.lo);
 #ifndef ANNEMBED_ASYNC_POISSON
     if (a.kappa <= 1.0f) {
-        using TE = EventTile<DP, KP>;
+        a.neg_group_shift = event_neg_group_shift(ctx);
         // persistent warps: at most the resident blocks, the in-flight window, and ~8 firing tiles per warp and launch
         const uint64_t tiles = (owned + 31) / 32;
+        if constexpr (DP <= 4) {
+            if (ctx->prm.flags & ANNEMBED_FLAG_CP_ASYNC_PIPELINE) {         // A/B: the pipeline through cp.async groups
+                using TC = EventCp<DP, KP>;
+                static int resident_per_sm = 0;
+                if (!resident_per_sm) {
+                    cudaError_t e = cudaFuncSetAttribute(k_sweep_events_cp<DP, HUB, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::SMEM);
+                    if (e != cudaSuccess) return e;
+                    int nbsm = 0;
+                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_sweep_events_cp<DP, HUB, KP>, TC::THREADS, TC::SMEM);
+                    if (e != cudaSuccess) return e;
+                    resident_per_sm = std::max(1, nbsm);
+                }
+                const unsigned int resident = (unsigned int)(ctx->sm_count * resident_per_sm);
+                const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa * (double)subs / 8.0) / TC::WARPS);
+                const unsigned int nb = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(want, resident), async_blocks(ctx, tiles, TC::THREADS * TC::VISITS, DP));
+                k_sweep_events_cp<DP, HUB, KP><<<nb, TC::THREADS, TC::SMEM, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * TC::WARPS),
+                                                                                               subs, ctx->counter.p);
+                return cudaGetLastError();
+            }
+        }
+        using TE = EventTile<DP, KP>;
         const unsigned int resident = (unsigned int)(ctx->sm_count * TE::MINB);
         const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa * (double)subs / 8.0) / TE::WARPS);
         const unsigned int nb = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(want, resident), async_blocks(ctx, tiles, TE::WARPS * 32 * TE::VISITS, DP));
@@ -3293,6 +3380,8 @@ extern "C" int annembed_cuda_debug_draws(annembed_cuda_ctx *ctx, uint32_t epoch,
     if (neg_out) CU(dn.alloc(ctx->E * 5));
     if ((rc = ensure_build(ctx))) return rc;
     EpochArgs a = make_epoch_args(ctx, epoch, 0.0);
+    // the draws of the kernel that would run: the event kernels of the default schedule widen the uniform sampler's groups
+    if (use_async(ctx) && !ctx->prm.mini_epochs_per_batch && a.kappa <= 1.0f) a.neg_group_shift = event_neg_group_shift(ctx);
     if (hub) k_debug_draws<true><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);
     else k_debug_draws<false><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);
     ctx->st.kernel_launches++;

@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(128) k_sweep_async_generic(EpochArgs a, float 
 template <int DP, int KP>
 struct EventTile {
     static constexpr int WARPS = 4;
-    static constexpr int MINB = DP <= 2 ? (KP <= 8 ? ANNEMBED_EVENTS_MINB : 4) : (DP <= 4 ? 3 : (DP <= 8 ? 2 : 1));
+    static constexpr int MINB = DP <= 2 ? (KP <= 8 ? ANNEMBED_EVENTS_MINB : 4) : (DP <= 4 ? 3 : (DP <= 16 ? 2 : 1));
     static constexpr int VISITS = DP <= 4 ? 3 : 2;       // visits a warp has in flight (in-flight window of the launch)
 };
 

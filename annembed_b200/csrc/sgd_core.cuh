@@ -251,6 +251,8 @@ struct EpochArgs {
     const uint4 *__restrict__ in_rec;   // {src node, bits(P_lo), bits(P_hi), bits(inv_s2[src])}, entry q at in_rec[q - in_base]
     uint64_t in_base;
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
+    const uint4 *__restrict__ sec_alias; // sector-level alias table (2 x uint4 per sector of 4 nodes), null: node-level table only
+    uint32_t neg_group_shift;            // uniform sampler: 2^shift consecutive nodes share their negative streams (0 -> 2, see neg_stream_key)
     const float *__restrict__ cum;       // inclusive cumulative probability along each row (last entry exactly 1)
     // tiled kernels: rows padded to KP entries {col, bits(cum)} (pads: {NO_NODE, 1.0f}), 16-byte aligned per node
     const uint2 *__restrict__ rowpack;
@@ -270,7 +272,7 @@ struct EpochArgs {
 template <bool HUB>
 __host__ __device__ __forceinline__ uint32_t map_negative(const EpochArgs &a, uint32_t w_idx, uint32_t w_acc)
 {
-    uint32_t k = below32(w_idx, a.n);                                             // uniform, embedder.rs:1121
+    uint32_t k = below_auto(w_idx, w_acc, a.n);                                   // uniform, embedder.rs:1121 (w_acc: its top 24 bits are the accept word)
     if constexpr (HUB) {
         const uint2 t = a.neg_alias[k];
         if (!(u01_24(w_acc) < as_float(t.x))) k = t.y;                            // alias method, :919,929
@@ -354,11 +356,16 @@ struct GlobalRowRejector {          // nodeparam.rs:83-85 linear scan of the ori
 // correlated, which no statistic of the optimizer depends on.  The hubness (alias) sampler does the same one level up:
 // the group draws one random sector of the ALIAS TABLE, each lane reads a different entry of it and then accepts it or
 // follows its alias (embedder.rs:909-931): per sample, 5 independent draws from the hubness law.
+// The asynchronous event kernels widen the group of the uniform sampler from the rows of a 32-byte sector to the rows of a
+// 128-byte LINE (16 nodes in dimension 2, 8 in dimension 3-4: EpochArgs::neg_group_shift): per negative slot a warp then
+// asks the memory system for 2 (4) lines of 4 (2) sectors instead of 8 scattered sectors -- the same bytes in a quarter
+// (half) of the requests, and DRAM bursts of 128 bytes.  Every sample still draws 5 independent uniform negatives.
+__host__ __device__ __forceinline__ uint32_t neg_group_shift(const EpochArgs &a) { return a.neg_group_shift ? a.neg_group_shift : 2u; }
 template <bool HUB>
 __host__ __device__ __forceinline__ uint32_t neg_stream_key(const EpochArgs &a, uint32_t node)
 {
-    (void)a;
-    return node & ~3u;
+    if constexpr (HUB) return node & ~3u;
+    else return node & ~((1u << neg_group_shift(a)) - 1u);
 }
 
 // redraws of the rejected negatives (embedder.rs:1246-1252: the reference loops until accepted; bounded here)
@@ -391,17 +398,40 @@ __host__ __device__ __forceinline__ void draw_negatives_core(const EpochArgs &a,
     uint32_t wa[ANNEMBED_NB_NEG] = {0u, 0u, 0u, 0u, 0u};
     if constexpr (HUB) { wa[0] = C.x; wa[1] = C.y; wa[2] = C.z; wa[3] = C.w; wa[4] = fifth_word(C); }
     const uint32_t nsec = (a.n + 3u) >> 2;
+    const uint32_t gsh = neg_group_shift(a), gmask = (1u << gsh) - 1u, ngrp = (a.n + gmask) >> gsh;
+    (void)gsh; (void)gmask; (void)ngrp; (void)nsec;
     // branch-free; the redraws (probability ~ (deg+2)/n per negative) are a rare path
     bool any_rej = false;
     bool rej[ANNEMBED_NB_NEG];
 #pragma unroll
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
-        uint32_t k = (below32(wi[q], nsec) << 2) | ((rot + wi[q]) & 3u);       // random sector, row rotated by 2 random bits
-        bool out_of_range = k >= a.n;
-        if constexpr (HUB) {
-            if (!out_of_range) {                                               // alias method on the shared sector's entry
-                const uint2 t = a.neg_alias[k];
-                if (!(u01_24(wa[q]) < as_float(t.x))) k = t.y;
+        uint32_t k;
+        bool out_of_range;
+        if (HUB && a.sec_alias != nullptr) {
+            // sector-level alias method: the group shares the sector draw, its accept / alias decision and one uniform;
+            // lane `rot` picks its row inside the final sector from the rotation frac(u + rot / 4) of that uniform
+            // (the entry carries the thresholds of its alias sector too: one 32-byte gather, no branch)
+            const uint32_t s0 = below_auto(wi[q], wa[q], nsec);                // (the accept test reads the top 24 bits of wa)
+            const uint4 e0 = a.sec_alias[2 * (size_t)s0], e1 = a.sec_alias[2 * (size_t)s0 + 1];
+            const bool own = u01_24(wa[q]) < as_float(e0.x);
+            const uint32_t sct = own ? s0 : e0.y;
+            const float t0 = as_float(own ? e0.z : e1.y), t1 = as_float(own ? e0.w : e1.z), t2 = as_float(own ? e1.x : e1.w);
+            uint32_t h = wi[q] ^ ((wa[q] << 16) | (wa[q] >> 16));
+            h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;
+            float ul = u01_24(h) + 0.25f * (float)(rot & 3u);
+            ul = ul >= 1.0f ? ul - 1.0f : ul;
+            k = (sct << 2) + (ul >= t0 ? 1u : 0u) + (ul >= t1 ? 1u : 0u) + (ul >= t2 ? 1u : 0u);
+            out_of_range = k >= a.n;
+        } else {
+            // random sector / line, rotated row; the 8 extra bits of the wide draw come from the middle of the next word
+            if constexpr (HUB) k = (below_auto(wi[q], wa[q], nsec) << 2) | ((rot + wi[q]) & 3u);
+            else k = (below_auto(wi[q], wi[(q + 1) % ANNEMBED_NB_NEG] >> 4, ngrp) << gsh) | ((rot + wi[q]) & gmask);
+            out_of_range = k >= a.n;
+            if constexpr (HUB) {
+                if (!out_of_range) {                                           // node-level alias method on the shared sector's entries
+                    const uint2 t = a.neg_alias[k];
+                    if (!(u01_24(wa[q]) < as_float(t.x))) k = t.y;
+                }
             }
         }
         rej[q] = out_of_range || rejected(k);

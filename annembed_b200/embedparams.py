@@ -10,6 +10,9 @@ FLAG_NO_RELABEL = 4
 FLAG_REPLAY_IN_EDGES = 8
 FLAG_LEGACY_EPOCH_KERNELS = 16
 FLAG_BULK_SYNCHRONOUS = 32
+FLAG_NODE_ALIAS = 64
+FLAG_CP_ASYNC_PIPELINE = 128
+FLAG_SECTOR_NEGATIVES = 256
 
 
 @dataclass

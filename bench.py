@@ -64,6 +64,15 @@ def workload_name(a):
             f"{a.batches} batches x 10 samples/edge; scale_rho 0.75, grad_step 1")
 
 
+def config_for(a):
+    """`config` of the JSON line: the workload and nothing that depends on the arm, so that the two arms (--impl ours /
+    --impl reference) print the SAME object; everything measured or chosen by an arm goes to `details`."""
+    return {"workload": workload_name(a),
+            "l2": "inputs larger than L2 (graph 0.7 GB + layout 88 MB per pass over 11M nodes; L2 126 MB); no flush needed",
+            "cpu_arm": "the CPU arm (--impl reference and cpu_baseline) times a bounded sample of ONE gradient batch of the same "
+                       "graph per step (fraction stated in cpu_baseline.sample) and reports throughput; it is not a full embed"}
+
+
 def make_inputs(a, device):
     import workloads
     t = time.time()
@@ -145,7 +154,7 @@ def bulk(a, world):
 def kernel_name(a, world):
     if bulk(a, world):
         return "K4, bulk-synchronous form: k_cell_epochs / k_epoch_out + k_epoch_in per mini-epoch"
-    return "K4, asynchronous form: k_sweep_events (one launch = 4 thinned sub-sweeps, one sample per node in expectation)"
+    return "K4, asynchronous form: k_sweep_events (one launch = 16 thinned sub-sweeps of firing probability 1/4 = 4 samples per node in expectation)"
 
 
 def parallelism_name(a, world, st):
@@ -186,7 +195,10 @@ def cpu_arm(a, row_ptr, col, dist, y0, seconds, label):
     frac = min(1.0, rate * seconds / (10.0 * E))
     _, done, secs = oracle.optimize(row_ptr, col, p, es, y0[:, :a.dim], 1.0, 1.0, 10, a.batches, seed=2, first_batch=1,
                                     n_batches=1, sample_fraction=frac, timing=True, n_threads=cores)
+    batch_s = 10.0 * E / (done / secs)
     return {"value": 6.0 * done / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "k1_seconds": t_w, "sample_fraction_of_a_batch": frac,
+            "extrapolated_embed_s": t_w + a.batches * batch_s,
             "sample": f"{label}: {done} positive samples = {frac:.4f} of one batch (of {a.batches}) of the same graph, "
                       f"sampling loop only ({secs:.1f} s); K1 weights + scales took {t_w:.1f} s on the host and are not included",
             "positive_samples": int(done), "seconds": secs}
@@ -212,8 +224,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * tot_s / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 coordinates, f64 coefficients", "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": "CPU restatement of the reference (oracle/annembed_oracle.c, OpenMP "
-                   "Hogwild); the Rust reference cannot be built here (no cargo/rustc). Each step is a bounded sample."},
+        "config": config_for(a),
+        "details": {"note": "CPU restatement of the reference (oracle/annembed_oracle.c, OpenMP Hogwild); the Rust reference cannot "
+                            "be built here (no cargo/rustc, profiles/r02_cargo_probe_gpu_box.txt). Each step is a bounded sample."},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -343,12 +356,12 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * elapsed_max / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "mini_epochs_per_batch": int(mini), "flags": a.flags,
-                       "l2_persist_max_bytes": int(st["l2_persist_max_bytes"]), "l2_window_max_bytes": int(st["l2_window_max_bytes"]),
-                       "l2": "inputs larger than L2 (graph + transposed index > 2 GB per pass); no flush needed",
-                       "parallelism": parallelism_name(a, world, st),
-                       "positive_samples_per_step": samples / a.steps, "input_build_s": t_in,
-                       "cross_entropy_last_step": list(ce)},
+            "config": config_for(a),
+            "details": {"mini_epochs_per_batch": int(mini), "flags": a.flags,
+                        "l2_persist_max_bytes": int(st["l2_persist_max_bytes"]), "l2_window_max_bytes": int(st["l2_window_max_bytes"]),
+                        "parallelism": parallelism_name(a, world, st),
+                        "positive_samples_per_step": samples / a.steps, "input_build_s": t_in,
+                        "cross_entropy_last_step": list(ce)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "peak_source": peak_src, "kernel": kernel_name(a, world),

@@ -75,6 +75,13 @@ typedef struct annembed_cuda_params {
 #define ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS 16u  /* one launch of k_epoch_out + k_epoch_in per mini-epoch instead of the
                                                    cell-resident kernel (cross-check; also what dimensions > 4 use);
                                                    implies the bulk-synchronous form */
+#define ANNEMBED_FLAG_NODE_ALIAS 64u            /* hubness sampler: node-level alias table for every draw (cross-check of the
+                                                   sector-level table) */
+#define ANNEMBED_FLAG_CP_ASYNC_PIPELINE 128u    /* asynchronous form, dimension <= 4: k_sweep_events_cp (visits pipelined through
+                                                   cp.async groups in shared memory) instead of the register-staged
+                                                   k_sweep_events; measured slower, kept for the A/B */
+#define ANNEMBED_FLAG_SECTOR_NEGATIVES 256u     /* asynchronous event kernels, uniform sampler: negatives shared by the 4 nodes of a
+                                                   32-byte sector of the layout instead of the nodes of a 128-byte line (A/B) */
 #define ANNEMBED_FLAG_BULK_SYNCHRONOUS 32u      /* one rank: the deterministic snapshot kernels (bit-reproducible for a seed)
                                                    instead of the asynchronous sweep (async_sweep.cuh), which like the
                                                    reference's threaded loop depends on the interleaving of the threads */

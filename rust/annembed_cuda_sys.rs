@@ -27,6 +27,9 @@ pub const ANNEMBED_FLAG_NO_RELABEL: u32 = 4;
 pub const ANNEMBED_FLAG_REPLAY_IN_EDGES: u32 = 8;
 pub const ANNEMBED_FLAG_LEGACY_EPOCH_KERNELS: u32 = 16;
 pub const ANNEMBED_FLAG_BULK_SYNCHRONOUS: u32 = 32;
+pub const ANNEMBED_FLAG_NODE_ALIAS: u32 = 64;
+pub const ANNEMBED_FLAG_CP_ASYNC_PIPELINE: u32 = 128;
+pub const ANNEMBED_FLAG_SECTOR_NEGATIVES: u32 = 256;
 
 /// mirror of EmbedderParams (src/embedparams.rs:76-103) + the device-side knobs
 #[repr(C)]

@@ -33,6 +33,17 @@ extern "C" void hostsim_philox2(const uint32_t ctr[2], uint32_t key, uint32_t ou
 }
 
 // the per-node uniforms of one mini-epoch (systematic-sampling offsets), as the kernels compute them
+// multiply-shift maps of a random word to [0, n): the 32-bit one and the 40-bit one of large ranges (philox.cuh)
+extern "C" void hostsim_below(uint64_t count, const uint32_t *w, const uint32_t *low8, uint32_t n, uint32_t *out32, uint32_t *out40,
+                              uint32_t *out_auto)
+{
+    for (uint64_t i = 0; i < count; i++) {
+        out32[i] = below32(w[i], n);
+        out40[i] = below40(w[i], low8[i], n);
+        out_auto[i] = below_auto(w[i], low8[i], n);
+    }
+}
+
 extern "C" void hostsim_node_uniforms(uint32_t node0, uint32_t count, uint32_t epoch, uint64_t seed, float *out)
 {
     const uint32_t k2 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);

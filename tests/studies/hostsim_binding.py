@@ -29,6 +29,14 @@ def philox2(ctr, key):
     return out
 
 
+def below(w, low8, n):
+    w = np.ascontiguousarray(w, np.uint32); low8 = np.ascontiguousarray(low8, np.uint32)
+    o32, o40, oa = (np.zeros(len(w), np.uint32) for _ in range(3))
+    lib().hostsim_below(C.c_uint64(len(w)), _p(w, C.c_uint32), _p(low8, C.c_uint32), C.c_uint32(n), _p(o32, C.c_uint32),
+                        _p(o40, C.c_uint32), _p(oa, C.c_uint32))
+    return o32, o40, oa
+
+
 def node_uniforms(node0, count, epoch, seed):
     out = np.zeros(count, np.float32)
     lib().hostsim_node_uniforms(C.c_uint32(node0), C.c_uint32(count), C.c_uint32(epoch), C.c_uint64(seed), _p(out, C.c_float))

@@ -182,18 +182,85 @@ def test_device_draws_match_host_build_bit_for_bit():
         c_host, n_host = hs.draws(row_ptr, col, p, 10, 7, 1234567890123, epoch)
         np.testing.assert_array_equal(c_dev, c_host)
         np.testing.assert_array_equal(n_dev, n_host)
-    # hubness sampler: alias draws follow the weights
-    w = oracle.hubness_weights(row_ptr, col)
     np.testing.assert_array_equal(ctx.get_hubness_counts(), np.bincount(col, minlength=3000))
-    ctxh = ctx_for(row_ptr, col, dist, hubness_weighting=True, mini_epochs_per_batch=1, flags=4)
-    ctxh.edge_weights()
-    ctxh.set_neg_weights(w)
-    hist = np.zeros(3000)
-    for epoch in range(30):
-        c, negs = ctxh.debug_draws(epoch)
-        hist += np.bincount(negs[c > 0].reshape(-1), minlength=3000)
-    freq = hist / hist.sum()
-    assert np.corrcoef(freq, w / w.sum())[0, 1] > 0.9
+
+
+@pytest.mark.parametrize("flags", [4, 4 | 64])     # 4 = no relabelling (debug_draws reports the caller's ids), 64 = ANNEMBED_FLAG_NODE_ALIAS
+def test_hubness_negatives_follow_the_weights_chi_square(flags):
+    """Hubness sampler (embedder.rs:909-931): the accepted negatives follow clamp(in-degree, 1, n) / sum.  Chi-square of the
+    device draws against the law, for the sector-level alias table (the default: shared sector draw, per-lane row from a
+    rotated uniform) and for the node-level table (flag 64).  (With the internal relabelling the sector table is built over
+    the relabelled weights; tests/test_gpu_fidelity.py[c3s-True] covers that path end to end.)"""
+    from scipy import stats
+    n = 20000
+    row_ptr, col, dist = random_graph(n, 4, 12, seed=62)
+    rng = np.random.default_rng(3)
+    # heavy-tailed weights (a few hubs), like the in-degrees of a real kNN graph
+    w = np.clip(rng.zipf(1.7, n), 1, n).astype(np.float32)
+    ctx = ctx_for(row_ptr, col, dist, hubness_weighting=True, mini_epochs_per_batch=1, flags=flags, seed=99)
+    ctx.edge_weights(want_outputs=False)
+    ctx.set_neg_weights(w)
+    origin = np.repeat(np.arange(n), np.diff(row_ptr).astype(np.int64))
+    hist = np.zeros((4, n))          # one histogram per lane of the 4-node groups: the lanes of a group share the sector
+    for epoch in range(40):          # draw (sector table), so only the draws of ONE lane are independent of each other
+        c, negs = ctx.debug_draws(epoch)             # per edge: firing count and the negatives of its first firing
+        for r in range(4):
+            sel = np.nonzero((c > 0) & ((origin & 3) == r))[0]
+            hist[r] += np.bincount(negs[sel].reshape(-1), minlength=n)
+    ctx.close()
+    law = w.astype(np.float64) / w.sum()
+    hub = int(np.argmax(w))
+    order = np.argsort(law)
+    assert hist.sum() > 3e6
+    for r in range(4):
+        N = hist[r].sum()
+        e, c = law[order] * N, hist[r][order]
+        edges = np.nonzero(np.diff(np.floor(np.cumsum(e) / 50.0)))[0] + 1       # merge rare nodes: expected counts >= 50
+        ce, ee = np.add.reduceat(c, np.r_[0, edges]), np.add.reduceat(e, np.r_[0, edges])
+        chi = stats.chisquare(ce, ee * ce.sum() / ee.sum())
+        assert chi.pvalue > 1e-3, (r, chi.statistic, len(ce), chi.pvalue)
+    Nt = hist.sum()
+    assert abs(hist[:, hub].sum() / Nt / law[hub] - 1) < 0.02
+
+
+@pytest.mark.parametrize("flags,shift", [(4, 4), (4 | 256, 2)])   # 256 = ANNEMBED_FLAG_SECTOR_NEGATIVES (groups of 4 nodes)
+def test_uniform_negatives_of_the_event_kernels_chi_square(flags, shift):
+    """Uniform sampler of the asynchronous event kernels (embedder.rs:1121 restated per group): the 2^shift nodes whose rows
+    share a 128-byte line (32-byte sector) of the layout draw the SAME random line per negative slot and each takes a
+    different row of it.  Per lane the accepted negatives must be uniform over the nodes (chi-square); within a group the
+    first firings of an epoch share their lines and take distinct rows."""
+    from scipy import stats
+    n = 20000
+    row_ptr, col, dist = random_graph(n, 4, 12, seed=63)
+    ctx = ctx_for(row_ptr, col, dist, flags=flags, seed=7)       # default schedule, dimension 2
+    ctx.edge_weights(want_outputs=False)
+    origin = np.repeat(np.arange(n), np.diff(row_ptr).astype(np.int64))
+    G = 1 << shift
+    hist = np.zeros((G, n))
+    shared = distinct = pairs = 0
+    for epoch in range(120):
+        c, negs = ctx.debug_draws(epoch)
+        fire = np.nonzero(c > 0)[0]
+        for r in range(G):
+            sel = fire[(origin[fire] & (G - 1)) == r]
+            hist[r] += np.bincount(negs[sel].reshape(-1), minlength=n)
+        # first firing edge of every firing node (its firing index 0): group-mates share the stream (group, 0, epoch)
+        first = fire[np.r_[True, origin[fire][1:] != origin[fire][:-1]]]
+        grp = origin[first] >> shift
+        same = np.nonzero(grp[1:] == grp[:-1])[0]
+        a, b = negs[first[same]], negs[first[same + 1]]
+        ok = (a != 0xFFFFFFFF) & (b != 0xFFFFFFFF)
+        shared += int(((a >> shift) == (b >> shift))[ok].sum())
+        distinct += int((a != b)[ok].sum())
+        pairs += int(ok.sum())
+    ctx.close()
+    assert pairs > 10000
+    assert shared >= 0.99 * pairs            # the exceptions are the redraws after a rejection (own row / own node)
+    assert distinct >= 0.999 * pairs
+    for r in range(G):
+        N = hist[r].sum()
+        chi = stats.chisquare(hist[r])
+        assert N > 20 * n / G and chi.pvalue > 1e-4, (r, N, chi.statistic, chi.pvalue)
 
 
 BULK = 32    # ANNEMBED_FLAG_BULK_SYNCHRONOUS: the deterministic snapshot kernels (the default on one rank is the asynchronous sweep)
@@ -359,7 +426,8 @@ def _async_vs_snapshot(n, d, kmin, kmax, hub, M, flags_async, seed_graph=77):
     outs = []
     # flag 4 (no relabelling) on both sides: the draws are keyed by the internal node ids, and the two forms number the
     # nodes differently (random order / locality order)
-    for flags in (flags_async | 4, BULK | 1 | 4):
+    # flag 256 (ANNEMBED_FLAG_SECTOR_NEGATIVES): the event kernels share negatives by groups of 4 nodes like the snapshot kernels
+    for flags in (flags_async | 4 | 256, BULK | 1 | 4):
         ctx = ctx_for(row_ptr, col, dist, asked_dim=d, nb_grad_batch=2, grad_step=2e-5, seed=13, flags=flags,
                       hubness_weighting=hub, nb_sampling_by_edge=1, mini_epochs_per_batch=M)
         ctx.edge_weights(want_outputs=False)
@@ -374,9 +442,9 @@ def _async_vs_snapshot(n, d, kmin, kmax, hub, M, flags_async, seed_graph=77):
 
 
 # rows: (d, kmin, kmax, hub, M, flags).  kmin == kmax and M == k: kappa == 1 exactly, every node fires once per sweep (the
-# pipelined kernel k_sweep_events with full visits); M < k: several firings per visit (k_sweep_async); flags 1: thread per node
+# pipelined kernel k_sweep_events with full visits); M < k: several firings per visit (k_sweep_async); flags 1: thread per node; flags 128: k_sweep_events_cp
 @pytest.mark.parametrize("d,kmin,kmax,hub,M,flags", [(2, 6, 6, False, 6, 0), (3, 8, 8, True, 8, 0), (4, 16, 16, False, 16, 0), (15, 6, 6, False, 6, 0),
-                                                     (15, 10, 10, True, 10, 0),
+                                                     (15, 10, 10, True, 10, 0), (2, 6, 6, False, 6, 128), (3, 8, 8, True, 8, 128),
                                                      (2, 6, 6, False, 2, 0), (2, 3, 10, True, 3, 0), (15, 4, 10, True, 3, 0),
                                                      (2, 6, 6, False, 6, 1), (2, 17, 30, False, 30, 0), (5, 2, 7, True, 2, 1)])
 def test_async_sweeps_apply_the_same_samples_as_the_snapshot_kernels(d, kmin, kmax, hub, M, flags):

@@ -278,3 +278,27 @@ def test_embed_call_sequence_follows_one_step_embed():
     assert "dmap_init" not in ctx.calls and "set_embedding" in ctx.calls
     y_init = e.get_initial_embedding()
     assert y_init.shape == (60, 3) and np.abs(y_init).max() <= 0.5      # uniform in [-0.5, 0.5]^d
+
+
+def test_wide_multiply_shift_is_exact_and_unbiased_at_1e8():
+    """philox.cuh below40: floor(((w << 8 | b) * n) / 2^40) exactly (Python integers), and the bias the 32-bit map has at
+    n = 10^8 (bins of 42 or 43 words: 2.3 %) is gone: over ALL 2^40 inputs every bin of below40 holds
+    floor or ceil of 2^40 / n = 10995 or 10996 inputs (1e-4).  below_auto switches at 2^20."""
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 1 << 20, (1 << 20) + 1, 25_000_000, 100_000_000, (1 << 32) - 1):
+        w = rng.integers(0, 1 << 32, size=20000, dtype=np.uint64).astype(np.uint32)
+        w[:4] = [0, 1, 0xFFFFFFFF, 0xFFFFFFFE]
+        b = rng.integers(0, 1 << 32, size=20000, dtype=np.uint64).astype(np.uint32)
+        o32, o40, oa = hs.below(w, b, n)
+        ref32 = [(int(x) * n) >> 32 for x in w]
+        ref40 = [(((int(x) << 8) | (int(y) & 0xFF)) * n) >> 40 for x, y in zip(w, b)]
+        assert o32.tolist() == ref32 and o40.tolist() == ref40
+        assert oa.tolist() == (ref40 if n > (1 << 20) else ref32)
+        assert int(o40.max()) < n
+    # bin sizes: inputs x in [0, 2^40) map to floor(x n / 2^40); bin k holds ceil((k+1) 2^40 / n) - ceil(k 2^40 / n) inputs
+    n = 100_000_000
+    k = np.arange(0, n, 9973, dtype=object)
+    size40 = [(-(-(int(i) + 1) * (1 << 40) // n)) - (-(-int(i) * (1 << 40) // n)) for i in k]
+    size32 = [(-(-(int(i) + 1) * (1 << 32) // n)) - (-(-int(i) * (1 << 32) // n)) for i in k]
+    assert set(size40) <= {(1 << 40) // n, (1 << 40) // n + 1} and max(size40) / min(size40) - 1 < 1e-4
+    assert max(size32) / min(size32) - 1 > 0.02
