@@ -152,6 +152,8 @@ struct annembed_cuda_ctx {
     uint64_t in_base = 0;
     DevBuf<uint2> neg_alias_old, neg_alias;   // alias table in the caller's / in the internal numbering
     DevBuf<uint4> sec_alias;                  // sector-level alias table, internal numbering (2 x uint4 per sector of 4 nodes)
+    DevBuf<uint2> line_t1;                    // line-level alias table (event kernels, dimension <= 4): {bits(prob), alias line} per line
+    DevBuf<uint32_t> line_t2;                 // ... and the alias table INSIDE a line: (accept threshold of 2^24 << 4) | alias row, per row; per line its own and its alias line's
     std::vector<float> neg_w_host;            // the caller's sampling weights (kept to build the sector table once the numbering is known)
     DevBuf<float> yapi, y0;        // current and initial layout in the caller's node order
     DevBuf<float> y[2];            // double-buffered layout of the epoch loop, internal node order (exported to the peers)
@@ -1642,7 +1644,7 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
     if (!ctx) return ANNEMBED_ERR_INVALID_ARG;
     REQUIRE(ctx->have_graph, ANNEMBED_ERR_STATE, "set_neg_weights: graph not set");
     CU(cudaSetDevice(ctx->device));
-    if (!w) { ctx->have_alias = false; ctx->neg_alias.release(); ctx->neg_alias_old.release(); ctx->sec_alias.release(); ctx->neg_w_host.clear(); return ANNEMBED_OK; }
+    if (!w) { ctx->have_alias = false; ctx->neg_alias.release(); ctx->neg_alias_old.release(); ctx->sec_alias.release(); ctx->line_t1.release(); ctx->line_t2.release(); ctx->neg_w_host.clear(); return ANNEMBED_OK; }
     const uint64_t n = ctx->n;
     double tot = 0.0;
     for (uint64_t i = 0; i < n; i++) {
@@ -2055,7 +2057,59 @@ static int build_sector_alias(annembed_cuda_ctx *ctx)
         tab[2 * s + 1].y = tab[2 * (size_t)al].z; tab[2 * s + 1].z = tab[2 * (size_t)al].w; tab[2 * s + 1].w = tab[2 * (size_t)al + 1].x;
     }
     CU(ctx->sec_alias.alloc(2 * nsec));
-    return h2d(ctx, ctx->sec_alias.p, tab.data(), 2 * nsec * sizeof(uint4));
+    if ((rc = h2d(ctx, ctx->sec_alias.p, tab.data(), 2 * nsec * sizeof(uint4)))) return rc;
+
+    // Line-level tables of the event kernels (layouts of dimension <= 4): the G = 16 (dimension 2) or 8 (dimension 3-4)
+    // nodes whose rows fill a 128-byte line of the layout share the line draw.  Two alias methods, one inside the other:
+    // T1 over the LINES (weight = sum of the line's node weights): {prob, alias line};  T2 inside every line over its G
+    // rows (conditional law w_i / W_line): per row the accept threshold in units of 2^-24 and the alias row.  A lane reads
+    // T1[line] (8 bytes, the same for the whole group), then ITS column of T2 of the final line (the group's columns are
+    // distinct: one coalesced read), then its row of that line of the layout (one line request per group).  The T2 entry
+    // of a line carries the inner table of its ALIAS line behind its own (2 G words = one 128-byte line in dimension 2), so
+    // that T1 and both candidate columns are read at once: the draw is one round of table reads, then the row.
+    // P(node) = P(line) * P(row | line): exactly the node law (embedder.rs:909-931 restated two levels up).
+    if (ctx->DP > 4) { ctx->line_t1.release(); ctx->line_t2.release(); return ANNEMBED_OK; }
+    const uint32_t G = ctx->DP == 2 ? 16u : 8u;
+    const uint64_t nl = (n + G - 1) / G;
+    std::vector<uint2> t1(nl);
+    std::vector<uint32_t> t2(nl * 2 * G);          // [line][0..G): own inner table, [line][G..2G): the alias line's
+    std::vector<double> ql(nl);
+    double totl = 0.0;
+    for (uint64_t l = 0; l < nl; l++) {
+        double wr[16], W = 0.0;
+        for (uint32_t r = 0; r < G; r++) { const uint64_t i = l * G + r; wr[r] = i < n ? (double)ctx->neg_w_host[old_of_new[i]] : 0.0; W += wr[r]; }
+        ql[l] = W; totl += W;
+        // Vose inside the line (rows of weight 0 -- the padding of the last line -- get threshold 0: never accepted)
+        uint32_t sm[16], lg[16], nsm = 0, nlg = 0;
+        double qi[16];
+        for (uint32_t r = 0; r < G; r++) {
+            qi[r] = W > 0.0 ? wr[r] * (double)G / W : 1.0;
+            if (qi[r] < 1.0) sm[nsm++] = r; else lg[nlg++] = r;
+            t2[l * 2 * G + r] = (16777216u << 4) | r;
+        }
+        while (nsm && nlg) {
+            const uint32_t a = sm[--nsm], b = lg[--nlg];
+            t2[l * 2 * G + a] = ((uint32_t)std::min(16777216.0, std::floor(qi[a] * 16777216.0 + 0.5)) << 4) | b;
+            qi[b] = (qi[b] + qi[a]) - 1.0;
+            if (qi[b] < 1.0) sm[nsm++] = b; else lg[nlg++] = b;
+        }
+    }
+    small.clear(); large.clear();
+    for (uint64_t l = 0; l < nl; l++) { ql[l] = ql[l] * (double)nl / totl; (ql[l] < 1.0 ? small : large).push_back((uint32_t)l); t1[l] = make_uint2(fbits(1.0f), (uint32_t)l); }
+    while (!small.empty() && !large.empty()) {
+        const uint32_t sm = small.back(); small.pop_back();
+        const uint32_t lg = large.back(); large.pop_back();
+        t1[sm] = make_uint2(fbits((float)ql[sm]), lg);
+        ql[lg] = (ql[lg] + ql[sm]) - 1.0;
+        (ql[lg] < 1.0 ? small : large).push_back(lg);
+    }
+    for (uint64_t l = 0; l < nl; l++) {
+        const uint64_t al = t1[l].y;
+        for (uint32_t r = 0; r < G; r++) t2[l * 2 * G + G + r] = t2[al * 2 * G + r];
+    }
+    CU(ctx->line_t1.alloc(nl)); CU(ctx->line_t2.alloc(nl * 2 * G));
+    if ((rc = h2d(ctx, ctx->line_t1.p, t1.data(), nl * sizeof(uint2)))) return rc;
+    return h2d(ctx, ctx->line_t2.p, t2.data(), nl * 2 * G * sizeof(uint32_t));
 }
 
 // device context build, weights part: K2 + cumulative row probabilities + rows + in-edge payloads
@@ -2634,6 +2688,7 @@ static EpochArgs make_epoch_args(annembed_cuda_ctx *ctx, uint32_t epoch, double 
     a.in_ptr = ctx->in_ptr_all.p ? ctx->in_ptr_all.p + ctx->lo : nullptr; a.in_rec = ctx->in_rec.p; a.in_base = ctx->in_base;
     a.neg_alias = ctx->neg_alias.p;
     a.sec_alias = (ctx->prm.flags & ANNEMBED_FLAG_NODE_ALIAS) ? nullptr : ctx->sec_alias.p;
+    a.line_t1 = nullptr; a.line_t2 = nullptr;         // set by the event-kernel launches (set_event_negative_groups)
     a.cum = ctx->cum.p;
     a.rowpack = ctx->rowpack.p; a.erank = ctx->erank.p;
     a.fired = (ctx->nranks == 1 && !(ctx->prm.flags & ANNEMBED_FLAG_REPLAY_IN_EDGES)) ? ctx->fired.p : nullptr;
@@ -2854,6 +2909,11 @@ static uint32_t event_neg_group_shift(const annembed_cuda_ctx *ctx)
     if (ctx->prm.flags & ANNEMBED_FLAG_SECTOR_NEGATIVES) return 0u;
     return ctx->DP == 2 ? 4u : (ctx->DP == 4 ? 3u : 0u);
 }
+static void set_event_negative_groups(const annembed_cuda_ctx *ctx, EpochArgs &a)
+{
+    a.neg_group_shift = event_neg_group_shift(ctx);
+    if (a.neg_group_shift > 2 && a.sec_alias && ctx->line_t1.p && ctx->line_t2.p) { a.line_t1 = ctx->line_t1.p; a.line_t2 = ctx->line_t2.p; }
+}
 template <int DP, bool HUB, int KP>
 static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a_in, uint32_t subs)
 {
@@ -2861,11 +2921,15 @@ static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a_in
     const uint64_t owned = (uint64_t)(a.hi - a.lo);
 #ifndef ANNEMBED_ASYNC_POISSON
     if (a.kappa <= 1.0f) {
-        a.neg_group_shift = event_neg_group_shift(ctx);
+        set_event_negative_groups(ctx, a);
         // persistent warps: at most the resident blocks, the in-flight window, and ~8 firing tiles per warp and launch
         const uint64_t tiles = (owned + 31) / 32;
         if constexpr (DP <= 4) {
-            if (ctx->prm.flags & ANNEMBED_FLAG_CP_ASYNC_PIPELINE) {         // A/B: the pipeline through cp.async groups
+            // Hubness sampler: the pipeline through cp.async groups (the table reads are a third dependent round of memory
+            // accesses inside the gather stage, and the register pipeline exposes every round: 101 G against 82 G edge
+            // updates/s).  Uniform sampler: the two pipelines perform the same (199 / 200 G: the memory system is the bound);
+            // the register kernel is the default, ANNEMBED_FLAG_CP_ASYNC_PIPELINE selects the other one.
+            if (HUB || (ctx->prm.flags & ANNEMBED_FLAG_CP_ASYNC_PIPELINE)) {
                 using TC = EventCp<DP, KP>;
                 static int resident_per_sm = 0;
                 if (!resident_per_sm) {
@@ -2884,6 +2948,7 @@ static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a_in
                 return cudaGetLastError();
             }
         }
+      if constexpr (!(DP <= 4 && HUB)) {
         using TE = EventTile<DP, KP>;
         const unsigned int resident = (unsigned int)(ctx->sm_count * TE::MINB);
         const uint64_t want = std::max<uint64_t>(1, (uint64_t)((double)tiles * a.kappa * (double)subs / 8.0) / TE::WARPS);
@@ -2891,6 +2956,7 @@ static cudaError_t launch_async_kp(annembed_cuda_ctx *ctx, const EpochArgs &a_in
         k_sweep_events<DP, HUB, KP><<<nb, TE::WARPS * 32, 0, ctx->launch_stream>>>(a, ctx->y[0].p, peer_map(ctx), tile_order(tiles, (uint64_t)nb * TE::WARPS), subs,
                                                                                 ctx->counter.p);
         return cudaGetLastError();
+      }
     }
 #endif
     (void)subs;                                      // several firings per visit: one sweep per launch
@@ -3381,7 +3447,7 @@ extern "C" int annembed_cuda_debug_draws(annembed_cuda_ctx *ctx, uint32_t epoch,
     if ((rc = ensure_build(ctx))) return rc;
     EpochArgs a = make_epoch_args(ctx, epoch, 0.0);
     // the draws of the kernel that would run: the event kernels of the default schedule widen the uniform sampler's groups
-    if (use_async(ctx) && !ctx->prm.mini_epochs_per_batch && a.kappa <= 1.0f) a.neg_group_shift = event_neg_group_shift(ctx);
+    if (use_async(ctx) && !ctx->prm.mini_epochs_per_batch && a.kappa <= 1.0f) set_event_negative_groups(ctx, a);
     if (hub) k_debug_draws<true><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);
     else k_debug_draws<false><<<nblocks(ctx->n, 128), 128, 0, ctx->stream>>>(a, dc.p, dn.p);
     ctx->st.kernel_launches++;

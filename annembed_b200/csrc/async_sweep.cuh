@@ -75,13 +75,19 @@ struct PeerMap {
     float *y[8];                         // y[r]: rank r's replica (y[rank] = the local one)
     uint32_t lo[9];                      // shard boundaries
     uint32_t nranks;
+    // Select chain over the kernel parameters: NO dynamic index into y[] -- indexing the parameter array by a computed rank
+    // makes the compiler copy it to local memory and read it back with an LDL before every reduction, and that load was
+    // where 42 % of the stall samples of k_sweep_events sat (ncu source page, profiles/r02_k4_async_events_v4_ncu_full.json:
+    // the IMAD.WIDE after `LDL.64`), on one rank too, where the result is never used.
     __device__ __forceinline__ float *owner_replica(uint32_t j, float *local) const
     {
-        if (nranks <= 1) return local;
-        uint32_t r = 0;
+        float *p = local;
+        if (nranks > 1) {
+            p = y[0];
 #pragma unroll
-        for (uint32_t q = 1; q < 8; q++) r += (q < nranks && j >= lo[q]) ? 1u : 0u;
-        return y[r];
+            for (uint32_t q = 1; q < 8; q++) p = (q < nranks && j >= lo[q]) ? y[q] : p;
+        }
+        return p;
     }
 };
 

@@ -252,6 +252,8 @@ struct EpochArgs {
     uint64_t in_base;
     const uint2 *__restrict__ neg_alias; // {bits(prob), alias} per node, hubness sampler (embedder.rs:909-931)
     const uint4 *__restrict__ sec_alias; // sector-level alias table (2 x uint4 per sector of 4 nodes), null: node-level table only
+    const uint2 *__restrict__ line_t1;   // line-level alias tables of the event kernels (annembed_cuda.cu build_sector_alias), or null
+    const uint32_t *__restrict__ line_t2;
     uint32_t neg_group_shift;            // uniform sampler: 2^shift consecutive nodes share their negative streams (0 -> 2, see neg_stream_key)
     const float *__restrict__ cum;       // inclusive cumulative probability along each row (last entry exactly 1)
     // tiled kernels: rows padded to KP entries {col, bits(cum)} (pads: {NO_NODE, 1.0f}), 16-byte aligned per node
@@ -364,7 +366,7 @@ __host__ __device__ __forceinline__ uint32_t neg_group_shift(const EpochArgs &a)
 template <bool HUB>
 __host__ __device__ __forceinline__ uint32_t neg_stream_key(const EpochArgs &a, uint32_t node)
 {
-    if constexpr (HUB) return node & ~3u;
+    if constexpr (HUB) return a.line_t1 ? node & ~((1u << neg_group_shift(a)) - 1u) : node & ~3u;
     else return node & ~((1u << neg_group_shift(a)) - 1u);
 }
 
@@ -407,7 +409,23 @@ __host__ __device__ __forceinline__ void draw_negatives_core(const EpochArgs &a,
     for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
         uint32_t k;
         bool out_of_range;
-        if (HUB && a.sec_alias != nullptr) {
+        if (HUB && a.line_t1 != nullptr) {
+            // line-level alias method (event kernels): the group = the nodes of one 128-byte line of the layout shares the
+            // line draw and its accept / alias decision; lane `rot` then looks at ITS column of the final line's inner
+            // alias table (columns rotated by a shared random offset: distinct within the group, uniform per lane)
+            const uint32_t l0 = below_auto(wi[q], wa[q], ngrp);                 // (the accept test reads the top 24 bits of wa)
+            uint32_t h = wi[q] ^ ((wa[q] << 16) | (wa[q] >> 16));
+            h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;
+            const uint32_t c = (rot + (h >> 28)) & gmask;                       // top bits: the rotation; low 24 bits: the accept
+            // one round of reads: the line's {prob, alias line} and the lane's column of BOTH candidate lines' inner tables
+            const uint2 t1 = a.line_t1[l0];
+            const uint32_t *e2 = a.line_t2 + ((size_t)l0 << (gsh + 1)) + c;
+            const uint32_t c_own = e2[0], c_alias = e2[gmask + 1u];
+            const bool own = u01_24(wa[q]) < as_float(t1.x);
+            const uint32_t line = own ? l0 : t1.y, t2 = own ? c_own : c_alias;
+            k = (line << gsh) + ((h & 0xFFFFFFu) < (t2 >> 4) ? c : (t2 & 15u));
+            out_of_range = k >= a.n;
+        } else if (HUB && a.sec_alias != nullptr) {
             // sector-level alias method: the group shares the sector draw, its accept / alias decision and one uniform;
             // lane `rot` picks its row inside the final sector from the rotation frac(u + rot / 4) of that uniform
             // (the entry carries the thresholds of its alias sector too: one 32-byte gather, no branch)

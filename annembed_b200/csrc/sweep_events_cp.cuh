@@ -5,29 +5,38 @@
 // flight, visit v applied) in registers.  ptxas gives ALL the global loads of that loop ONE scoreboard (SB5: decoded from
 // the SASS control words of every LDG, profiles/r02_sweep_events_scoreboards.txt), and a scoreboard wait releases only
 // when every load counted on it has returned: the wait for the gathers of visit v also waits for the rows of visit v+2
-// issued a moment ago.  The pipeline therefore exposes a full memory latency twice per visit (ncu: 67 % of the stall
-// samples are long-scoreboard, issue slots 48 % busy, DRAM 24 %).  cp.async groups complete in order and
-// cp.async.wait_group N leaves the N newest groups in flight -- the partial wait the register pipeline cannot express.
+// issued a moment ago (ncu: 52-67 % of the stall samples are long-scoreboard).  cp.async groups complete in order and
+// cp.async.wait_group N leaves the N newest groups in flight -- the partial wait the register pipeline cannot express
+// (ncu of this kernel: long-scoreboard 16 % of the stall samples).
+// What it buys (A/B on one box, profiles/r02_ab_pipeline_and_negative_groups.txt): uniform negatives 199 vs 200 G edge
+// updates/s -- nothing: with either pipeline the memory system's rate of scattered requests is the bound; hubness
+// negatives 101 vs 82 G: the alias-table reads are a third dependent round of memory accesses inside the gather stage,
+// which the register pipeline exposes in full.  Default for the hubness sampler, ANNEMBED_FLAG_CP_ASYNC_PIPELINE otherwise.
 //
-// Per thread and visit: group L = the node's padded row (KP/2 16-byte copies, L2 evict-first: a row is read once per
-// sub-sweep) + its scale; group G = 7 layout rows (own, partner, 5 negatives; 16 bytes each -- in dimension 2 the aligned
-// PAIR of rows, .cg copies need 16 bytes and must bypass the L1: the rows are updated by the other SMs' reductions).
+// Per thread and visit: group L = the node's padded row (KP/2 16-byte copies) + its scale; group G = 7 layout rows (own,
+// partner, 5 negatives; 8 bytes each in dimension 2, 16 in dimension 3-4).  All copies are the .ca form, which goes
+// through the L1 like an ordinary load: the accesses of a warp to one line are ONE request to the L2.  (The .cg / BYPASS
+// form sends every thread's bytes on its own: measured, L2 throughput 81 % instead of 43 % and 25 % slower.  A row read
+// through the L1 can be stale by the few microseconds a line survives in the ~90 KB the shared memory leaves it -- less than
+// the samples in flight already allow; the layout statistics do not move, tests/test_gpu_fidelity.py.)
 // Iteration t of a warp:  issue L(t+2); wait_group 2 -> L(t+1) has landed: edge, negatives, issue G(t+1);
 // wait_group 2 -> G(t) has landed: attraction, 5 repulsions, the two reductions.  Every group has a whole iteration of
 // the warp (and of the other resident warps) to arrive.  The slots are private to the thread (no barrier), laid out
-// [slot][item][thread] so that all shared-memory accesses are conflict-free 16-byte accesses.
+// [slot][item][thread] so that all shared-memory accesses are conflict-free 8- or 16-byte accesses.
 // Sampling, draws, arithmetic and publication are those of k_sweep_events (same functions of sgd_core.cuh).
 #pragma once
 
 namespace cpa {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp16(void *dst, const void *src)
+// .ca copies go through the L1 like an ordinary load: the accesses of a warp to one line are ONE request to the L2
+// (the .cg / BYPASS form sends every thread's 16 bytes on its own: measured, L2 throughput 81 % instead of 43 %)
+__device__ __forceinline__ void cp16_ca(void *dst, const void *src)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp16_hint(void *dst, const void *src, uint64_t policy)
+__device__ __forceinline__ void cp8_ca(void *dst, const void *src)
 {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(policy) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp4(void *dst, const void *src)
 {
@@ -36,23 +45,16 @@ __device__ __forceinline__ void cp4(void *dst, const void *src)
 __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint64_t policy_evict_first()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 } // namespace cpa
 
 template <int DP, int KP>
 struct EventCp {
     static_assert(DP == 2 || DP == 4, "k_sweep_events_cp: layouts of dimension <= 4");
     static constexpr int WARPS = 4, THREADS = WARPS * 32;
-    static constexpr int RV = DP == 2 ? 1 : DP / 4;                 // 16-byte units of a gathered row slot
     static constexpr int ITEMS = 2 + ANNEMBED_NB_NEG;               // own row, partner's row, negatives
     static constexpr int H = KP / 2;                                // 16-byte units of a padded row
-    static constexpr int U4 = 2 * H + 2 * ITEMS * RV;               // per thread: 2 slots of tile rows, 2 slots of gathered rows
-    static constexpr size_t SMEM = (size_t)U4 * THREADS * 16 + 2 * THREADS * sizeof(float);
+    static constexpr int RB = DP * 4;                               // bytes of a gathered row slot (8 or 16)
+    static constexpr size_t SMEM = (size_t)2 * H * THREADS * 16 + (size_t)2 * ITEMS * THREADS * RB + 2 * THREADS * sizeof(float);
     static constexpr int FIT = (int)((227u * 1024u) / (SMEM + 1024u));
     static constexpr int MINB = FIT < 1 ? 1 : (FIT > (DP == 2 ? 5 : 4) ? (DP == 2 ? 5 : 4) : FIT);
     static constexpr int VISITS = 3;                                // visits a warp has in flight
@@ -110,13 +112,13 @@ k_sweep_events_cp(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t sub
 {
     static_assert(KP % 2 == 0, "rows are padded to an even number of entries (16-byte copies)");
     using TC = EventCp<DP, KP>;
-    constexpr int RV = TC::RV, ITEMS = TC::ITEMS, H = TC::H, NT = TC::THREADS;
+    constexpr int ITEMS = TC::ITEMS, H = TC::H, NT = TC::THREADS;
+    using GRow = typename std::conditional<DP == 2, uint2, uint4>::type;     // one gathered row
     extern __shared__ uint4 sm4[];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    uint4 *const sm_rows = sm4 + tid;                               // [slot][h]       -> sm_rows[(slot * H + h) * NT]
-    uint4 *const sm_g = sm4 + 2 * H * NT + tid;                     // [slot][item][v] -> sm_g[((slot * ITEMS + item) * RV + v) * NT]
-    float *const sm_inv = reinterpret_cast<float *>(sm4 + (size_t)TC::U4 * NT) + tid;   // [slot] -> sm_inv[slot * NT]
-    const uint64_t pol = cpa::policy_evict_first();
+    uint4 *const sm_rows = sm4 + tid;                               // [slot][h]    -> sm_rows[(slot * H + h) * NT]
+    GRow *const sm_g = reinterpret_cast<GRow *>(sm4 + 2 * H * NT) + tid;      // [slot][item] -> sm_g[(slot * ITEMS + item) * NT]
+    float *const sm_inv = reinterpret_cast<float *>(reinterpret_cast<GRow *>(sm4 + 2 * H * NT) + 2 * ITEMS * NT) + tid;   // [slot] -> sm_inv[slot * NT]
     unsigned int applied = 0;
 
     FiringTiles ft;
@@ -125,19 +127,18 @@ k_sweep_events_cp(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t sub
 
     // per slot: stage `load` (Rn: node or NO_NODE for a lane beyond the end; Rv: warp-uniform, the slot holds a visit) and
     // stage `gather` (Gn: node or NO_NODE for an idle lane)
-    uint32_t Rn[2], Re[2], Ru[2], Gn[2], Gj[2], Ghalf[2];
+    uint32_t Rn[2], Re[2], Ru[2], Gn[2], Gj[2];
     float Gpe[2], Ginv[2];
     unsigned Guse[2];
     bool Rv[2] = {false, false}, Gv[2] = {false, false};
     Rn[0] = Rn[1] = Gn[0] = Gn[1] = ANNEMBED_NO_NODE;
-    Re[0] = Re[1] = Ru[0] = Ru[1] = Gj[0] = Gj[1] = Ghalf[0] = Ghalf[1] = 0u;
+    Re[0] = Re[1] = Ru[0] = Ru[1] = Gj[0] = Gj[1] = 0u;
     Gpe[0] = Gpe[1] = Ginv[0] = Ginv[1] = 0.0f;
     Guse[0] = Guse[1] = 0u;
 
-    // address of the 16-byte unit(s) that hold row idx of the layout
-    auto row_src = [&](uint32_t idx) -> const uint4 * {
-        if constexpr (DP == 2) return reinterpret_cast<const uint4 *>(Y) + (idx >> 1);
-        else return reinterpret_cast<const uint4 *>(Y + (size_t)idx * DP);
+    auto copy_row = [&](GRow *dst, uint32_t idx) {                  // row idx of the layout -> the thread's slot
+        if constexpr (DP == 2) cpa::cp8_ca(dst, Y + (size_t)idx * DP);
+        else cpa::cp16_ca(dst, Y + (size_t)idx * DP);
     };
 
     auto load = [&](auto SLOT) {                                    // group L of the next visit (an empty group when there is none)
@@ -152,7 +153,7 @@ k_sweep_events_cp(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t sub
             const uint32_t node = (uint32_t)n0 + (valid ? lane : 0);
             const uint4 *rp = async_row_ptr<KP>(a.rowpack, node);
 #pragma unroll
-            for (int h = 0; h < H; h++) cpa::cp16_hint(sm_rows + (S * H + h) * NT, rp + h, pol);
+            for (int h = 0; h < H; h++) cpa::cp16_ca(sm_rows + (S * H + h) * NT, rp + h);
             cpa::cp4(sm_inv + S * NT, a.inv_s2 + node);
             Rn[S] = valid ? node : ANNEMBED_NO_NODE;
             Re[S] = ft.epoch; Ru[S] = ft.ukey;
@@ -197,28 +198,20 @@ k_sweep_events_cp(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t sub
             uint32_t negs[ANNEMBED_NB_NEG];
             draw_negatives_v2<HUB>(a, Re[S], node, 0u, A, rejected, negs);
             unsigned use = 0;
-            uint32_t half = (node & 1u) | ((j & 1u) << 1);
-            uint4 *const g0 = sm_g + (S * ITEMS) * RV * NT;
-#pragma unroll
-            for (int v = 0; v < RV; v++) {
-                cpa::cp16(g0 + (0 * RV + v) * NT, row_src(node) + v);
-                cpa::cp16(g0 + (1 * RV + v) * NT, row_src(j) + v);
-            }
+            GRow *const g0 = sm_g + (S * ITEMS) * NT;
+            copy_row(g0, node);
+            copy_row(g0 + NT, j);
 #pragma unroll
             for (int q = 0; q < ANNEMBED_NB_NEG; q++) {
                 const bool okq = negs[q] != ANNEMBED_NO_NODE;
-                const uint32_t k = okq ? negs[q] : node;
                 use |= okq ? (1u << q) : 0u;
-                half |= (k & 1u) << (2 + q);
-#pragma unroll
-                for (int v = 0; v < RV; v++) cpa::cp16(g0 + ((2 + q) * RV + v) * NT, row_src(k) + v);
+                copy_row(g0 + (2 + q) * NT, okq ? negs[q] : node);
             }
             Gn[S] = fires ? node : ANNEMBED_NO_NODE;
             Gj[S] = j;
             Gpe[S] = F_SUB(P_hi, P_lo);
             Ginv[S] = sm_inv[S * NT];
             Guse[S] = use;
-            Ghalf[S] = half;
         }
         cpa::commit();
     };
@@ -226,20 +219,11 @@ k_sweep_events_cp(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t sub
     auto apply = [&](auto SLOT) {                                   // gathered rows of slot S have landed
         constexpr int S = decltype(SLOT)::value;
         if (!Gv[S] || Gn[S] == ANNEMBED_NO_NODE) return;
-        const uint4 *const g0 = sm_g + (S * ITEMS) * RV * NT;
+        const GRow *const g0 = sm_g + (S * ITEMS) * NT;
         auto row = [&](int item, float (&v)[DP]) {
-            if constexpr (DP == 2) {
-                const uint4 t = g0[item * NT];
-                const bool hi = (Ghalf[S] >> item) & 1u;
-                v[0] = __uint_as_float(hi ? t.z : t.x); v[1] = __uint_as_float(hi ? t.w : t.y);
-            } else {
-#pragma unroll
-                for (int w = 0; w < RV; w++) {
-                    const uint4 t = g0[(item * RV + w) * NT];
-                    v[4 * w] = __uint_as_float(t.x); v[4 * w + 1] = __uint_as_float(t.y);
-                    v[4 * w + 2] = __uint_as_float(t.z); v[4 * w + 3] = __uint_as_float(t.w);
-                }
-            }
+            const GRow t = g0[item * NT];
+            v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y);
+            if constexpr (DP == 4) { v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w); }
         };
         float y[DP], y0[DP], yj[DP], g[DP];
         row(0, y);

@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c5"],
+                    help="c3 (default): BASELINE.json configs[2], 11M x 28, k=6; c5: configs[4], 100M x 64, k=15 (sets --nodes/--data-dim/--knn)")
+    ap.add_argument("--data-dim", type=int, default=28)
     ap.add_argument("--nodes", type=int, default=11_000_000)
     ap.add_argument("--knn", type=int, default=6)
     ap.add_argument("--dim", type=int, default=2)
@@ -55,11 +58,14 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="(kept for command-line compatibility; no variants are measured)")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-gather instead of the fused peer-store exchange")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == "c5":
+        a.nodes, a.data_dim, a.knn = 100_000_000, 64, 15
+    return a
 
 
 def workload_name(a):
-    return (f"synthetic {a.nodes}x28 Higgs-shape mixture, cluster-blocked exact kNN k={a.knn}, shuffled node ids, "
+    return (f"synthetic {a.nodes}x{a.data_dim} {'Higgs-shape ' if a.data_dim == 28 else ''}mixture, cluster-blocked exact kNN k={a.knn}, shuffled node ids, "
             f"0.5% duplicate rows (disconnected 4096-node blocks: no long-range edges, no hubs); embed dim {a.dim}; "
             f"{a.batches} batches x 10 samples/edge; scale_rho 0.75, grad_step 1")
 
@@ -68,7 +74,8 @@ def config_for(a):
     """`config` of the JSON line: the workload and nothing that depends on the arm, so that the two arms (--impl ours /
     --impl reference) print the SAME object; everything measured or chosen by an arm goes to `details`."""
     return {"workload": workload_name(a),
-            "l2": "inputs larger than L2 (graph 0.7 GB + layout 88 MB per pass over 11M nodes; L2 126 MB); no flush needed",
+            "l2": f"inputs larger than L2 (padded rows {a.nodes * (a.knn + a.knn % 2) * 8 / 1e9:.2f} GB + layout {a.nodes * 8 * ((a.dim + 1) // 2) / 1e6:.0f} MB "
+                  f"per pass over the nodes; L2 126 MB); no flush needed",
             "cpu_arm": "the CPU arm (--impl reference and cpu_baseline) times a bounded sample of ONE gradient batch of the same "
                        "graph per step (fraction stated in cpu_baseline.sample) and reports throughput; it is not a full embed"}
 
@@ -76,7 +83,7 @@ def config_for(a):
 def make_inputs(a, device):
     import workloads
     t = time.time()
-    row_ptr, col, dist = workloads.blocked_knn_graph(a.nodes, 28, a.knn, seed=0, device=device)
+    row_ptr, col, dist = workloads.blocked_knn_graph(a.nodes, a.data_dim, a.knn, seed=0, device=device)
     y0 = workloads.random_init(a.nodes, a.dim, seed=0)
     # keep the host copies in pinned memory (the e2e arm copies from them every step)
     def pin(arr):

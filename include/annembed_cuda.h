@@ -77,9 +77,10 @@ typedef struct annembed_cuda_params {
                                                    implies the bulk-synchronous form */
 #define ANNEMBED_FLAG_NODE_ALIAS 64u            /* hubness sampler: node-level alias table for every draw (cross-check of the
                                                    sector-level table) */
-#define ANNEMBED_FLAG_CP_ASYNC_PIPELINE 128u    /* asynchronous form, dimension <= 4: k_sweep_events_cp (visits pipelined through
-                                                   cp.async groups in shared memory) instead of the register-staged
-                                                   k_sweep_events; measured slower, kept for the A/B */
+#define ANNEMBED_FLAG_CP_ASYNC_PIPELINE 128u    /* asynchronous form, dimension <= 4, uniform negatives: k_sweep_events_cp (visits
+                                                   pipelined through cp.async groups in shared memory) instead of the
+                                                   register-staged k_sweep_events; same speed, kept for the A/B.
+                                                   The hubness sampler always runs k_sweep_events_cp in these dimensions. */
 #define ANNEMBED_FLAG_SECTOR_NEGATIVES 256u     /* asynchronous event kernels, uniform sampler: negatives shared by the 4 nodes of a
                                                    32-byte sector of the layout instead of the nodes of a 128-byte line (A/B) */
 #define ANNEMBED_FLAG_BULK_SYNCHRONOUS 32u      /* one rank: the deterministic snapshot kernels (bit-reproducible for a seed)

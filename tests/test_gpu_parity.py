@@ -185,34 +185,38 @@ def test_device_draws_match_host_build_bit_for_bit():
     np.testing.assert_array_equal(ctx.get_hubness_counts(), np.bincount(col, minlength=3000))
 
 
-@pytest.mark.parametrize("flags", [4, 4 | 64])     # 4 = no relabelling (debug_draws reports the caller's ids), 64 = ANNEMBED_FLAG_NODE_ALIAS
-def test_hubness_negatives_follow_the_weights_chi_square(flags):
+# flags 4 = no relabelling (debug_draws reports the caller's ids), 64 = ANNEMBED_FLAG_NODE_ALIAS; M = mini_epochs_per_batch
+# (0: the default schedule, whose event kernels draw through the line-level tables); G = nodes that share a negative stream
+@pytest.mark.parametrize("flags,M,G", [(4, 1, 4), (4 | 64, 1, 4), (4, 0, 16)])
+def test_hubness_negatives_follow_the_weights_chi_square(flags, M, G):
     """Hubness sampler (embedder.rs:909-931): the accepted negatives follow clamp(in-degree, 1, n) / sum.  Chi-square of the
-    device draws against the law, for the sector-level alias table (the default: shared sector draw, per-lane row from a
-    rotated uniform) and for the node-level table (flag 64).  (With the internal relabelling the sector table is built over
-    the relabelled weights; tests/test_gpu_fidelity.py[c3s-True] covers that path end to end.)"""
+    device draws against the law, per lane of a group (the lanes of a group share the sector / line draw, so only the
+    draws of ONE lane are independent of each other), for the sector-level alias table (shared sector draw, per-lane row
+    from a rotated uniform), the node-level table (flag 64) and the line-level tables of the event kernels (alias method
+    over the 16-node lines, alias method inside the line).  (With the internal relabelling the tables are built over the
+    relabelled weights; tests/test_gpu_fidelity.py[c3s-True] covers that path end to end.)"""
     from scipy import stats
     n = 20000
     row_ptr, col, dist = random_graph(n, 4, 12, seed=62)
     rng = np.random.default_rng(3)
     # heavy-tailed weights (a few hubs), like the in-degrees of a real kNN graph
     w = np.clip(rng.zipf(1.7, n), 1, n).astype(np.float32)
-    ctx = ctx_for(row_ptr, col, dist, hubness_weighting=True, mini_epochs_per_batch=1, flags=flags, seed=99)
+    ctx = ctx_for(row_ptr, col, dist, hubness_weighting=True, mini_epochs_per_batch=M, flags=flags, seed=99)
     ctx.edge_weights(want_outputs=False)
     ctx.set_neg_weights(w)
     origin = np.repeat(np.arange(n), np.diff(row_ptr).astype(np.int64))
-    hist = np.zeros((4, n))          # one histogram per lane of the 4-node groups: the lanes of a group share the sector
-    for epoch in range(40):          # draw (sector table), so only the draws of ONE lane are independent of each other
+    hist = np.zeros((G, n))          # one histogram per lane of the groups
+    for epoch in range(40 if M else 160):
         c, negs = ctx.debug_draws(epoch)             # per edge: firing count and the negatives of its first firing
-        for r in range(4):
-            sel = np.nonzero((c > 0) & ((origin & 3) == r))[0]
+        for r in range(G):
+            sel = np.nonzero((c > 0) & ((origin & (G - 1)) == r))[0]
             hist[r] += np.bincount(negs[sel].reshape(-1), minlength=n)
     ctx.close()
     law = w.astype(np.float64) / w.sum()
     hub = int(np.argmax(w))
     order = np.argsort(law)
     assert hist.sum() > 3e6
-    for r in range(4):
+    for r in range(G):
         N = hist[r].sum()
         e, c = law[order] * N, hist[r][order]
         edges = np.nonzero(np.diff(np.floor(np.cumsum(e) / 50.0)))[0] + 1       # merge rare nodes: expected counts >= 50
