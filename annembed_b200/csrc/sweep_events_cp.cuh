@@ -153,7 +153,7 @@ k_sweep_events_cp(EpochArgs a, float *Y, PeerMap pm, TileOrder ord, uint32_t sub
             const uint32_t node = (uint32_t)n0 + (valid ? lane : 0);
             const uint4 *rp = async_row_ptr<KP>(a.rowpack, node);
 #pragma unroll
-            for (int h = 0; h < H; h++) cpa::cp16_ca(sm_rows + (S * H + h) * NT, rp + h);
+            for (int h = 0; h < H; h++) cpa::cp16_ca(sm_rows + (S * H + h) * NT, rp + 32 * h);
             cpa::cp4(sm_inv + S * NT, a.inv_s2 + node);
             Rn[S] = valid ? node : ANNEMBED_NO_NODE;
             Re[S] = ft.epoch; Ru[S] = ft.ukey;

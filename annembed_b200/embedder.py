@@ -207,7 +207,7 @@ class CudaContext:
 
     def get_embedding(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
-            out = np.empty((self.n, self.params.asked_dim), np.float32)
+            out = _result_buffer((self.n, self.params.asked_dim))
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.n * self.params.asked_dim
         self._ck(self.lib.annembed_cuda_get_embedding(self.h, ptr(out, C.c_float)))
         return out
@@ -240,6 +240,19 @@ class CudaContext:
         negs = np.empty((self.E, 5), np.uint32) if want_negs else None
         self._ck(self.lib.annembed_cuda_debug_draws(self.h, epoch, ptr(counts, C.c_uint32), ptr(negs, C.c_uint32)))
         return counts, negs
+
+
+def _result_buffer(shape) -> np.ndarray:
+    """Host array for a layout read back from the device: page-locked when torch can provide it (its caching host
+    allocator recycles the block once the array is dropped), so that the copy runs at PCIe speed -- a pageable 88 MB
+    destination took 21 ms at 11M nodes, 2 ms pinned.  Plain numpy otherwise."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True).numpy()
+    except Exception:
+        pass
+    return np.empty(shape, np.float32)
 
 
 class KGraphProjection:

@@ -140,7 +140,9 @@ int annembed_cuda_comm_export_layout(annembed_cuda_ctx *ctx, uint8_t handles[128
 int annembed_cuda_comm_import_layouts(annembed_cuda_ctx *ctx, const uint8_t *all_handles);
 
 /* ≙ the KGraph hand-off, kgraph.rs:108-120 + get_neighbours :157.  Rows sorted ascending by distance
- * (kgraph.rs:508-509), no self edges, every row non-empty.  row_ptr has n+1 entries. */
+ * (kgraph.rs:508-509), no self edges, every row non-empty.  row_ptr has n+1 entries.
+ * After comm_init with several ranks the call is COLLECTIVE: every rank passes the same graph, uploads one nranks-th of
+ * each array from its host and receives the other parts over NVLink (grouped ncclBroadcast). */
 int annembed_cuda_set_graph_csr(annembed_cuda_ctx *ctx, uint64_t n, const uint64_t *row_ptr,
                                 const uint32_t *col, const float *dist);
 
