@@ -355,6 +355,7 @@ def run_ours(a):
                 e2e_dev = {k: emb.stats[k] for k in ("edge_weights_ms", "build_ms", "optimize_ms", "cross_entropy_ms")}
                 e2e_dev["wall_ms"] = 1e3 * (time.perf_counter() - t1)
                 e2e_dev["host_phases_ms"] = {k: round(v, 2) for k, v in emb.host_timings_ms.items()}
+            del out, emb                              # the result's page-locked block goes back to torch's host cache
         e2e = (e2e_t, e2e_samples, h2d, d2h, e2e_dev)
 
     # ---- reduce over ranks: time = max, work = sum
