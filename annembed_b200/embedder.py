@@ -368,7 +368,16 @@ class Embedder:
         if getattr(self, "hkgraph", None) is not None:
             return self.h_embed()                                                   # embedder.rs:186-190
         device_dmap = self.initial_embedding is None and p.dmap_init    # embedder.rs:308-345 on the device
-        if self.initial_embedding is None and not p.dmap_init:
+        if device_dmap and self.get_nb_nodes() < 80:
+            # the device range finder is the reference's rank-20 one (graphlaplace.rs:113): it needs 4 x 20 nodes.  The
+            # reference switches to a full SVD below 500 nodes (graphlaplace.rs:100-108), which the device path does not
+            # have: tiny graphs (the upper layers of a small hierarchy) start from the random layout of the
+            # dmap_init = false branch instead.  (asked_dim > 19 stays an error: EmbedError / ANNEMBED_ERR_UNSUPPORTED.)
+            import warnings
+            warnings.warn("dmap_init needs >= 80 nodes on the device: using the random initial layout (embedder.rs:348)",
+                          RuntimeWarning, stacklevel=2)
+            device_dmap = False
+        if self.initial_embedding is None and not device_dmap:
             self.initial_embedding = self._get_random_init(1.0)       # embedder.rs:348
         ctx = self.context
         own_ctx = ctx is None

@@ -255,14 +255,22 @@ def test_embed_call_sequence_follows_one_step_embed():
     """one_step_embed (embedder.rs:298-371): dmap_init without a layout -> device diffusion-map layout (:308-345);
     explicit layout -> set_embedding; dmap_init=false -> get_random_init(1.) (:348); hubness weights = clamp(count, 1, n)
     (:826-833).  Host logic only: the device context is a recording stand-in."""
-    row_ptr, col, dist = random_graph(60, 3, 5, seed=2)
-    g = A.KGraph(row_ptr, col, dist)
-    ctx = _RecordingContext(60, 2)
-    e = A.Embedder(g, A.EmbedderParams(dmap_init=True), context=ctx)
+    rp100, c100, d100 = random_graph(100, 3, 5, seed=2)
+    ctx = _RecordingContext(100, 2)
+    e = A.Embedder(A.KGraph(rp100, c100, d100), A.EmbedderParams(dmap_init=True), context=ctx)
     assert e.embed() == 1
     assert ctx.calls == ["set_graph_csr", "edge_weights", "dmap_init", "optimize", "get_embedding"]
-    assert e.get_initial_embedding().shape == (60, 2) and e.cross_entropy == (2.0, 1.0)
+    assert e.get_initial_embedding().shape == (100, 2) and e.cross_entropy == (2.0, 1.0)
     assert "dmap_init" in e.host_timings_ms and "set_embedding" not in e.host_timings_ms
+
+    row_ptr, col, dist = random_graph(60, 3, 5, seed=2)
+    g = A.KGraph(row_ptr, col, dist)
+    # below 80 nodes the device range finder does not apply: random layout, with a warning
+    ctx = _RecordingContext(60, 2)
+    e = A.Embedder(g, A.EmbedderParams(dmap_init=True), context=ctx)
+    with pytest.warns(RuntimeWarning, match="dmap_init"):
+        assert e.embed() == 1
+    assert "dmap_init" not in ctx.calls and "set_embedding" in ctx.calls
 
     ctx = _RecordingContext(60, 2)
     y0 = np.zeros((60, 2), np.float32)
