@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "sgd_core.cuh"
+#include "alias_tables.hpp"
 #include "quality.cuh"
 #include "dmap.cuh"
 
@@ -2053,37 +2054,9 @@ static int build_sector_alias(annembed_cuda_ctx *ctx)
     CU(cudaMemcpyAsync(old_of_new.data(), ctx->old_of_new.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     int rc;
     if ((rc = sync_stream(ctx))) return rc;
-    std::vector<double> q(nsec);
-    std::vector<uint4> tab(2 * nsec);
-    double tot = 0.0;
-    auto fbits = [](float f) { uint32_t b; memcpy(&b, &f, 4); return b; };
-    for (uint64_t s = 0; s < nsec; s++) {
-        double w4[4], W = 0.0;
-        for (int r = 0; r < 4; r++) { const uint64_t i = 4 * s + r; w4[r] = i < n ? (double)ctx->neg_w_host[old_of_new[i]] : 0.0; W += w4[r]; }
-        q[s] = W; tot += W;
-        // cumulative thresholds; a sector of zero weight is never drawn (prob 0 -> its alias), missing rows weigh 0
-        float t0 = 1.0f, t1 = 1.0f, t2 = 1.0f;
-        if (W > 0.0) { t0 = (float)(w4[0] / W); t1 = (float)((w4[0] + w4[1]) / W); t2 = (float)((w4[0] + w4[1] + w4[2]) / W); }
-        tab[2 * s] = make_uint4(0u, (uint32_t)s, fbits(t0), fbits(t1));
-        tab[2 * s + 1] = make_uint4(fbits(t2), 0u, 0u, 0u);
-    }
-    std::vector<uint32_t> small, large;
-    small.reserve(nsec); large.reserve(nsec);
-    for (uint64_t s = 0; s < nsec; s++) { q[s] = q[s] * (double)nsec / tot; (q[s] < 1.0 ? small : large).push_back((uint32_t)s); }
-    auto put = [&](uint32_t s, float prob, uint32_t alias) { tab[2 * (size_t)s].x = fbits(prob); tab[2 * (size_t)s].y = alias; };
-    while (!small.empty() && !large.empty()) {
-        const uint32_t sm = small.back(); small.pop_back();
-        const uint32_t lg = large.back(); large.pop_back();
-        put(sm, (float)q[sm], lg);
-        q[lg] = (q[lg] + q[sm]) - 1.0;
-        (q[lg] < 1.0 ? small : large).push_back(lg);
-    }
-    for (uint32_t lg : large) put(lg, 1.0f, lg);
-    for (uint32_t sm : small) put(sm, 1.0f, sm);
-    for (uint64_t s = 0; s < nsec; s++) {       // the alias sector's thresholds ride in the entry: no second table gather
-        const uint32_t al = tab[2 * s].y;
-        tab[2 * s + 1].y = tab[2 * (size_t)al].z; tab[2 * s + 1].z = tab[2 * (size_t)al].w; tab[2 * s + 1].w = tab[2 * (size_t)al + 1].x;
-    }
+    std::vector<uint4> tab;
+    auto weight = [&](uint64_t i) { return (double)ctx->neg_w_host[old_of_new[i]]; };
+    annembed_host::build_sector_alias_table(n, weight, tab);
     CU(ctx->sec_alias.alloc(2 * nsec));
     if ((rc = h2d(ctx, ctx->sec_alias.p, tab.data(), 2 * nsec * sizeof(uint4)))) return rc;
 
@@ -2099,42 +2072,9 @@ static int build_sector_alias(annembed_cuda_ctx *ctx)
     if (ctx->DP > 4) { ctx->line_t1.release(); ctx->line_t2.release(); return ANNEMBED_OK; }
     const uint32_t G = ctx->DP == 2 ? 16u : 8u;
     const uint64_t nl = (n + G - 1) / G;
-    std::vector<uint2> t1(nl);
-    std::vector<uint32_t> t2(nl * 2 * G);          // [line][0..G): own inner table, [line][G..2G): the alias line's
-    std::vector<double> ql(nl);
-    double totl = 0.0;
-    for (uint64_t l = 0; l < nl; l++) {
-        double wr[16], W = 0.0;
-        for (uint32_t r = 0; r < G; r++) { const uint64_t i = l * G + r; wr[r] = i < n ? (double)ctx->neg_w_host[old_of_new[i]] : 0.0; W += wr[r]; }
-        ql[l] = W; totl += W;
-        // Vose inside the line (rows of weight 0 -- the padding of the last line -- get threshold 0: never accepted)
-        uint32_t sm[16], lg[16], nsm = 0, nlg = 0;
-        double qi[16];
-        for (uint32_t r = 0; r < G; r++) {
-            qi[r] = W > 0.0 ? wr[r] * (double)G / W : 1.0;
-            if (qi[r] < 1.0) sm[nsm++] = r; else lg[nlg++] = r;
-            t2[l * 2 * G + r] = (16777216u << 4) | r;
-        }
-        while (nsm && nlg) {
-            const uint32_t a = sm[--nsm], b = lg[--nlg];
-            t2[l * 2 * G + a] = ((uint32_t)std::min(16777216.0, std::floor(qi[a] * 16777216.0 + 0.5)) << 4) | b;
-            qi[b] = (qi[b] + qi[a]) - 1.0;
-            if (qi[b] < 1.0) sm[nsm++] = b; else lg[nlg++] = b;
-        }
-    }
-    small.clear(); large.clear();
-    for (uint64_t l = 0; l < nl; l++) { ql[l] = ql[l] * (double)nl / totl; (ql[l] < 1.0 ? small : large).push_back((uint32_t)l); t1[l] = make_uint2(fbits(1.0f), (uint32_t)l); }
-    while (!small.empty() && !large.empty()) {
-        const uint32_t sm = small.back(); small.pop_back();
-        const uint32_t lg = large.back(); large.pop_back();
-        t1[sm] = make_uint2(fbits((float)ql[sm]), lg);
-        ql[lg] = (ql[lg] + ql[sm]) - 1.0;
-        (ql[lg] < 1.0 ? small : large).push_back(lg);
-    }
-    for (uint64_t l = 0; l < nl; l++) {
-        const uint64_t al = t1[l].y;
-        for (uint32_t r = 0; r < G; r++) t2[l * 2 * G + G + r] = t2[al * 2 * G + r];
-    }
+    std::vector<uint2> t1;
+    std::vector<uint32_t> t2;
+    annembed_host::build_line_alias_tables(n, G, weight, t1, t2);
     CU(ctx->line_t1.alloc(nl)); CU(ctx->line_t2.alloc(nl * 2 * G));
     if ((rc = h2d(ctx, ctx->line_t1.p, t1.data(), nl * sizeof(uint2)))) return rc;
     return h2d(ctx, ctx->line_t2.p, t2.data(), nl * 2 * G * sizeof(uint32_t));

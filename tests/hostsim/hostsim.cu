@@ -11,6 +11,7 @@
 #include <omp.h>
 #endif
 #include "../../annembed_b200/csrc/sgd_core.cuh"
+#include "../../annembed_b200/csrc/alias_tables.hpp"
 
 using namespace annembed;
 
@@ -33,6 +34,21 @@ extern "C" void hostsim_philox2(const uint32_t ctr[2], uint32_t key, uint32_t ou
 }
 
 // the per-node uniforms of one mini-epoch (systematic-sampling offsets), as the kernels compute them
+// the grouped alias tables of the hubness sampler (annembed_b200/csrc/alias_tables.hpp), identity numbering
+extern "C" void hostsim_alias_tables(uint64_t n, uint32_t G, const float *w, uint32_t *sector_tab /*[8 * ceil(n/4)]*/,
+                                     uint32_t *t1_out /*[2 * ceil(n/G)]*/, uint32_t *t2_out /*[2 G * ceil(n/G)]*/)
+{
+    auto weight = [&](uint64_t i) { return (double)w[i]; };
+    std::vector<uint4> tab;
+    annembed_host::build_sector_alias_table(n, weight, tab);
+    memcpy(sector_tab, tab.data(), tab.size() * sizeof(uint4));
+    std::vector<uint2> t1;
+    std::vector<uint32_t> t2;
+    annembed_host::build_line_alias_tables(n, G, weight, t1, t2);
+    memcpy(t1_out, t1.data(), t1.size() * sizeof(uint2));
+    memcpy(t2_out, t2.data(), t2.size() * sizeof(uint32_t));
+}
+
 // multiply-shift maps of a random word to [0, n): the 32-bit one and the 40-bit one of large ranges (philox.cuh)
 extern "C" void hostsim_below(uint64_t count, const uint32_t *w, const uint32_t *low8, uint32_t n, uint32_t *out32, uint32_t *out40,
                               uint32_t *out_auto)

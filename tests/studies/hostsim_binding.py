@@ -29,6 +29,16 @@ def philox2(ctr, key):
     return out
 
 
+def alias_tables(w, G):
+    """(sector table [nsec, 8] u32, T1 [nl, 2] u32, T2 [nl, 2 G] u32) of annembed_b200/csrc/alias_tables.hpp, identity numbering."""
+    w = np.ascontiguousarray(w, np.float32)
+    n = len(w)
+    nsec, nl = (n + 3) // 4, (n + G - 1) // G
+    sec = np.zeros((nsec, 8), np.uint32); t1 = np.zeros((nl, 2), np.uint32); t2 = np.zeros((nl, 2 * G), np.uint32)
+    lib().hostsim_alias_tables(C.c_uint64(n), C.c_uint32(G), _p(w, C.c_float), _p(sec, C.c_uint32), _p(t1, C.c_uint32), _p(t2, C.c_uint32))
+    return sec, t1, t2
+
+
 def below(w, low8, n):
     w = np.ascontiguousarray(w, np.uint32); low8 = np.ascontiguousarray(low8, np.uint32)
     o32, o40, oa = (np.zeros(len(w), np.uint32) for _ in range(3))

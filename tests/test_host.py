@@ -310,3 +310,57 @@ def test_wide_multiply_shift_is_exact_and_unbiased_at_1e8():
     size32 = [(-(-(int(i) + 1) * (1 << 32) // n)) - (-(-int(i) * (1 << 32) // n)) for i in k]
     assert set(size40) <= {(1 << 40) // n, (1 << 40) // n + 1} and max(size40) / min(size40) - 1 < 1e-4
     assert max(size32) / min(size32) - 1 > 0.02
+
+
+@pytest.mark.parametrize("n,G", [(20003, 16), (20003, 8), (37, 16), (16, 16), (5, 8)])
+def test_grouped_alias_tables_encode_the_node_law(n, G):
+    """annembed_b200/csrc/alias_tables.hpp (hubness sampler, embedder.rs:909-931 restated per sector / per line): the node
+    law the tables encode, computed EXACTLY from their entries, is w / sum(w).
+    Sector table: P(i) = 1/nsec * sum_s [prob_s * cond_s(i) + (1 - prob_s) * cond_alias(s)(i)], cond from the thresholds.
+    Line tables : P(i) = 1/nl * sum_l [prob_l * inner_l(i) + (1 - prob_l) * inner_alias(l)(i)], inner_L(r) = 1/G * sum_c
+    [thr_c * (c == r) + (1 - thr_c) * (alias_c == r)].  Also: the alias sector's / line's data embedded in an entry are that
+    sector's / line's own, padding nodes have probability 0."""
+    rng = np.random.default_rng(n + G)
+    w = np.clip(rng.zipf(1.7, n), 1, n).astype(np.float32)          # heavy-tailed, like in-degrees
+    w[rng.integers(0, n, size=max(1, n // 50))] = 0.0                # a few nodes that must never be drawn
+    if n == 37:
+        w[16:32] = 0.0                                               # a whole line of weight zero
+    law = w.astype(np.float64) / w.astype(np.float64).sum()
+    sec, t1, t2 = hs.alias_tables(w, G)
+    f = lambda a: a.view(np.float32).astype(np.float64)
+    # ---- sector level
+    nsec = len(sec)
+    prob, alias = f(sec[:, 0].copy()), sec[:, 1].astype(np.int64)
+    thr_own = np.stack([f(sec[:, 2].copy()), f(sec[:, 3].copy()), f(sec[:, 4].copy())], 1)
+    thr_al = np.stack([f(sec[:, 5].copy()), f(sec[:, 6].copy()), f(sec[:, 7].copy())], 1)
+    np.testing.assert_array_equal(thr_al, thr_own[alias])
+    cond = np.diff(np.concatenate([np.zeros((nsec, 1)), thr_own, np.ones((nsec, 1))], 1), axis=1)     # [nsec, 4]
+    assert (cond >= 0).all()
+    P = np.zeros(nsec * 4)
+    np.add.at(P, (np.arange(nsec)[:, None] * 4 + np.arange(4)).ravel(), (prob[:, None] * cond).ravel() / nsec)
+    np.add.at(P, (alias[:, None] * 4 + np.arange(4)).ravel(), ((1 - prob)[:, None] * cond[alias]).ravel() / nsec)
+    assert np.abs(P[n:]).max(initial=0.0) == 0.0
+    # resolution: the thresholds are fp32 numbers in [0, 1] (2^-24 of the SECTOR's mass per row: a weight-1 node behind a
+    # weight-10^4 hub of its sector is off by up to 10^-3 of its own tiny probability, everything else by 10^-6)
+    mass4 = np.pad(law, (0, nsec * 4 - n)).reshape(nsec, 4).sum(1).repeat(4)[:n]
+    assert (np.abs(P[:n] - law) <= 2e-6 * law + 2.5e-7 * mass4).all()
+    assert np.quantile(np.abs(P[:n] - law) / np.maximum(law, 1e-300), 0.99) < 2e-5
+    # ---- line level
+    nl = len(t1)
+    probl, al = f(t1[:, 0].copy()), t1[:, 1].astype(np.int64)
+    np.testing.assert_array_equal(t2[:, G:], t2[al][:, :G])
+    thr = (t2[:, :G] >> 4).astype(np.float64) / 2.0 ** 24
+    ali = (t2[:, :G] & 15).astype(np.int64)
+    assert thr.max() <= 1.0 and ali.max() < G
+    inner = np.zeros((nl, G))
+    np.add.at(inner, (np.arange(nl)[:, None].repeat(G, 1), np.arange(G)[None, :].repeat(nl, 0)), thr / G)
+    np.add.at(inner, (np.arange(nl)[:, None].repeat(G, 1), ali), (1 - thr) / G)
+    np.testing.assert_allclose(inner.sum(1), 1.0, rtol=1e-12)
+    P = np.zeros(nl * G)
+    np.add.at(P, (np.arange(nl)[:, None] * G + np.arange(G)).ravel(), (probl[:, None] * inner).ravel() / nl)
+    np.add.at(P, (al[:, None] * G + np.arange(G)).ravel(), ((1 - probl)[:, None] * inner[al]).ravel() / nl)
+    assert np.abs(P[n:]).max(initial=0.0) == 0.0
+    assert (P[:n][w == 0] == 0).all()
+    massG = np.pad(law, (0, nl * G - n)).reshape(nl, G).sum(1).repeat(G)[:n]        # accept thresholds: 2^-24 of qi = G w_i / W_line
+    assert (np.abs(P[:n] - law) <= 2e-6 * law + 2.5e-7 * massG).all()
+    assert np.quantile(np.abs(P[:n] - law) / np.maximum(law, 1e-300), 0.99) < 2e-5
