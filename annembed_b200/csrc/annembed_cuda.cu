@@ -469,9 +469,10 @@ __global__ void k_relabel_rows(uint64_t n, const uint32_t *__restrict__ old_of_n
     for (uint64_t m = 0; m < k; m++) col2[w0 + m] = new_of_old[col[r0 + m]];
 }
 // rows of the tiled kernels: KP entries {neighbour, bits(cumulative probability)} per node, pads {NO_NODE, 1.0f}
-// Rows padded to KP {neighbour, cumulative probability} pairs: [node][KP].  `interleave` (per tile of 32 nodes
-// [pair h = m / 2][lane][m & 1]: the h-th 16-byte load of a warp reads 512 contiguous bytes) was measured and is not used:
-// the L1 already merges the three loads of a lane, +0.5 % (profiles/r02_ab_row_layout.txt).
+// Rows padded to KP {neighbour, cumulative probability} pairs.  interleave = 0: [node][KP] (bulk-synchronous kernels; the
+// cell kernel copies whole tiles).  interleave = 1 (asynchronous form, async_sweep.cuh async_row_ptr): per tile of 32 nodes
+// [pair h = m / 2][lane][m & 1], so that the h-th 16-byte load of a warp reads 512 contiguous bytes (no effect at KP = 6,
+// where the L1 merged the three loads of a lane -- profiles/r02_ab_build_flags.txt; kept for the wide rows).
 __global__ void k_rowpack(uint64_t n, int KP, int interleave, const uint64_t *__restrict__ row_ptr2, const uint32_t *__restrict__ col2,
                           const float *__restrict__ cum, uint2 *__restrict__ rowpack)
 {
@@ -1681,24 +1682,8 @@ extern "C" int annembed_cuda_set_neg_weights(annembed_cuda_ctx *ctx, const float
         tot += w[i];
     }
     REQUIRE(tot > 0.0, ANNEMBED_ERR_INVALID_ARG, "all sampling weights are zero");
-    std::vector<double> q(n);
-    std::vector<uint32_t> small, large;
-    small.reserve(n); large.reserve(n);
-    std::vector<uint2> tab(n);
-    for (uint64_t i = 0; i < n; i++) {
-        q[i] = (double)w[i] * (double)n / tot;
-        (q[i] < 1.0 ? small : large).push_back((uint32_t)i);
-    }
-    auto put = [&](uint32_t i, float prob, uint32_t alias) { uint32_t bits; memcpy(&bits, &prob, 4); tab[i] = make_uint2(bits, alias); };
-    while (!small.empty() && !large.empty()) {
-        const uint32_t s = small.back(); small.pop_back();
-        const uint32_t l = large.back(); large.pop_back();
-        put(s, (float)q[s], l);
-        q[l] = (q[l] + q[s]) - 1.0;
-        (q[l] < 1.0 ? small : large).push_back(l);
-    }
-    for (uint32_t l : large) put(l, 1.0f, l);
-    for (uint32_t s : small) put(s, 1.0f, s);
+    std::vector<uint2> tab;
+    annembed_host::build_node_alias_table(n, [&](uint64_t i) { return (double)w[i]; }, tot, tab);
     CU(ctx->neg_alias_old.alloc(n));
     int rc;
     if ((rc = h2d(ctx, ctx->neg_alias_old.p, tab.data(), n * sizeof(uint2)))) return rc;
@@ -2056,10 +2041,6 @@ static int build_sector_alias(annembed_cuda_ctx *ctx)
     if ((rc = sync_stream(ctx))) return rc;
     std::vector<uint4> tab;
     auto weight = [&](uint64_t i) { return (double)ctx->neg_w_host[old_of_new[i]]; };
-    annembed_host::build_sector_alias_table(n, weight, tab);
-    CU(ctx->sec_alias.alloc(2 * nsec));
-    if ((rc = h2d(ctx, ctx->sec_alias.p, tab.data(), 2 * nsec * sizeof(uint4)))) return rc;
-
     // Line-level tables of the event kernels (layouts of dimension <= 4): the G = 16 (dimension 2) or 8 (dimension 3-4)
     // nodes whose rows fill a 128-byte line of the layout share the line draw.  Two alias methods, one inside the other:
     // T1 over the LINES (weight = sum of the line's node weights): {prob, alias line};  T2 inside every line over its G
@@ -2069,12 +2050,20 @@ static int build_sector_alias(annembed_cuda_ctx *ctx)
     // of a line carries the inner table of its ALIAS line behind its own (2 G words = one 128-byte line in dimension 2), so
     // that T1 and both candidate columns are read at once: the draw is one round of table reads, then the row.
     // P(node) = P(line) * P(row | line): exactly the node law (embedder.rs:909-931 restated two levels up).
-    if (ctx->DP > 4) { ctx->line_t1.release(); ctx->line_t2.release(); return ANNEMBED_OK; }
+    // Built on a second host thread while this one builds and uploads the sector table (both are host work, 0.2-0.3 s each
+    // at 11M nodes).
+    const bool want_lines = ctx->DP <= 4;
     const uint32_t G = ctx->DP == 2 ? 16u : 8u;
     const uint64_t nl = (n + G - 1) / G;
     std::vector<uint2> t1;
     std::vector<uint32_t> t2;
-    annembed_host::build_line_alias_tables(n, G, weight, t1, t2);
+    struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } lines;   // joined on every return path
+    if (want_lines) lines.t = std::thread([&]() { annembed_host::build_line_alias_tables(n, G, weight, t1, t2); });
+    annembed_host::build_sector_alias_table(n, weight, tab);
+    CU(ctx->sec_alias.alloc(2 * nsec));
+    if ((rc = h2d(ctx, ctx->sec_alias.p, tab.data(), 2 * nsec * sizeof(uint4)))) return rc;
+    if (!want_lines) { ctx->line_t1.release(); ctx->line_t2.release(); return ANNEMBED_OK; }
+    lines.t.join();
     CU(ctx->line_t1.alloc(nl)); CU(ctx->line_t2.alloc(nl * 2 * G));
     if ((rc = h2d(ctx, ctx->line_t1.p, t1.data(), nl * sizeof(uint2)))) return rc;
     return h2d(ctx, ctx->line_t2.p, t2.data(), nl * 2 * G * sizeof(uint32_t));

@@ -15,6 +15,7 @@
 // get_quality_estimate_from_edge_length.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -89,7 +90,8 @@ public:
     Embedder(const KGraph &kgraph, EmbedderParams parameters, int device = 0)
         : kgraph_(kgraph), parameters_(parameters), device_(device) {}
 
-    // the initial layout (n x asked_dim, row-major, node-index order); required when dmap_init is true
+    // the initial layout (n x asked_dim, row-major, node-index order); optional: without it embed() computes the
+    // diffusion-map layout on the device (dmap_init = true, >= 80 nodes) or draws the random one (embedder.rs:348)
     void set_initial_embedding(std::vector<float> y) { initial_embedding_ = std::move(y); }
 
     size_t get_asked_dimension() const { return parameters_.asked_dim; }          // embedder.rs:135-153
@@ -107,8 +109,15 @@ public:
     int embed()
     {
         const size_t n = get_nb_nodes(), d = parameters_.asked_dim;
-        const bool device_dmap = initial_embedding_.empty() && parameters_.dmap_init;   // embedder.rs:308-345 on the device
-        if (initial_embedding_.empty() && !parameters_.dmap_init) {
+        bool device_dmap = initial_embedding_.empty() && parameters_.dmap_init;         // embedder.rs:308-345 on the device
+        if (device_dmap && n < 80) {
+            // the device range finder is the reference's rank-20 one (graphlaplace.rs:113) and needs 4 x 20 nodes; the
+            // reference switches to a full SVD below 500 nodes (graphlaplace.rs:100-108), which the device path does not
+            // have: tiny graphs start from the random layout of the dmap_init = false branch (same rule as embedder.py)
+            fprintf(stderr, "annembed: dmap_init needs >= 80 nodes on the device: using the random initial layout (embedder.rs:348)\n");
+            device_dmap = false;
+        }
+        if (initial_embedding_.empty() && !device_dmap) {
             // ≙ get_random_init(1.) (embedder.rs:348,456-470): uniform in [-0.5, 0.5]^d
             std::mt19937_64 rng(parameters_.seed);
             std::uniform_real_distribution<float> u(-0.5f, 0.5f);

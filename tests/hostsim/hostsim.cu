@@ -48,6 +48,15 @@ extern "C" void hostsim_alias_tables(uint64_t n, uint32_t G, const float *w, uin
     memcpy(t1_out, t1.data(), t1.size() * sizeof(uint2));
     memcpy(t2_out, t2.data(), t2.size() * sizeof(uint32_t));
 }
+// the node-level table (annembed_cuda_set_neg_weights builds it with the same function and the same sequential sum)
+extern "C" void hostsim_node_alias_table(uint64_t n, const float *w, uint32_t *tab_out /*[2 n]*/)
+{
+    double tot = 0.0;
+    for (uint64_t i = 0; i < n; i++) tot += w[i];
+    std::vector<uint2> tab;
+    annembed_host::build_node_alias_table(n, [&](uint64_t i) { return (double)w[i]; }, tot, tab);
+    memcpy(tab_out, tab.data(), tab.size() * sizeof(uint2));
+}
 
 // multiply-shift maps of a random word to [0, n): the 32-bit one and the 40-bit one of large ranges (philox.cuh)
 extern "C" void hostsim_below(uint64_t count, const uint32_t *w, const uint32_t *low8, uint32_t n, uint32_t *out32, uint32_t *out40,

@@ -39,6 +39,14 @@ def alias_tables(w, G):
     return sec, t1, t2
 
 
+def node_alias_table(w):
+    """Node-level alias table [n, 2] u32 = {bits(prob), alias} (annembed_b200/csrc/alias_tables.hpp)."""
+    w = np.ascontiguousarray(w, np.float32)
+    tab = np.zeros((len(w), 2), np.uint32)
+    lib().hostsim_node_alias_table(C.c_uint64(len(w)), _p(w, C.c_float), _p(tab, C.c_uint32))
+    return tab
+
+
 def below(w, low8, n):
     w = np.ascontiguousarray(w, np.uint32); low8 = np.ascontiguousarray(low8, np.uint32)
     o32, o40, oa = (np.zeros(len(w), np.uint32) for _ in range(3))

@@ -364,3 +364,26 @@ def test_grouped_alias_tables_encode_the_node_law(n, G):
     massG = np.pad(law, (0, nl * G - n)).reshape(nl, G).sum(1).repeat(G)[:n]        # accept thresholds: 2^-24 of qi = G w_i / W_line
     assert (np.abs(P[:n] - law) <= 2e-6 * law + 2.5e-7 * massG).all()
     assert np.quantile(np.abs(P[:n] - law) / np.maximum(law, 1e-300), 0.99) < 2e-5
+
+
+@pytest.mark.parametrize("n", [1, 7, 20003, 200001])
+def test_node_alias_table_encodes_the_node_law(n):
+    """Node-level table of annembed_cuda_set_neg_weights (≙ WeightedAliasIndex over clamp(in_degree, 1, N), embedder.rs:916-919):
+    P(i) = 1/n * [prob_i + sum_{s: alias(s) = i} (1 - prob_s)] computed from the entries is w / sum(w) to fp32 resolution of
+    the accept probabilities; zero-weight nodes are never drawn.  n = 200001 takes the multi-threaded path of the builder."""
+    rng = np.random.default_rng(n)
+    w = np.clip(rng.zipf(1.7, n), 1, n).astype(np.float32)
+    if n > 7:
+        w[rng.integers(0, n, size=n // 50)] = 0.0
+    law = w.astype(np.float64) / w.astype(np.float64).sum()
+    tab = hs.node_alias_table(w)
+    prob = tab[:, 0].copy().view(np.float32).astype(np.float64)
+    alias = tab[:, 1].astype(np.int64)
+    assert prob.min() >= 0.0 and prob.max() <= 1.0 and alias.max() < n
+    P = prob / n
+    np.add.at(P, alias, (1.0 - prob) / n)
+    assert (P[w == 0] == 0).all()
+    assert np.abs(P.sum() - 1.0) < 1e-9
+    # an accept probability is an fp32 number in [0, 1]: 2^-24 / n absolute per entry that points at a node
+    cnt = np.bincount(alias, minlength=n) + 1
+    assert (np.abs(P - law) <= 1e-7 * cnt / n + 1e-12).all()
