@@ -399,7 +399,10 @@ def run_ours(a):
                         "l2_persist_max_bytes": int(st["l2_persist_max_bytes"]), "l2_window_max_bytes": int(st["l2_window_max_bytes"]),
                         "parallelism": parallelism_name(a, world, st),
                         "positive_samples_per_step": samples / a.steps, "input_build_s": t_in,
-                        "cross_entropy_last_step": list(ce)},
+                        "cross_entropy_last_step": list(ce),
+                        "timing": "value / ms_per_step: host clock between device synchronisations + barriers on both sides of the K steps "
+                                  "(every library call ends with a synchronisation of its stream), max over ranks; roofline and "
+                                  "breakdown_ms_per_step: CUDA events on the library's stream around every launch"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "peak_source": peak_src, "kernel": kernel_name(a, world),
