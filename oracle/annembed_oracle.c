@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#include <stdatomic.h>
+#include <sched.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -415,6 +417,223 @@ int64_t oracle_optimize(uint64_t n, uint32_t d, const uint64_t *row_ptr, const u
     alias_free(&pos);
     if (have_neg) alias_free(&negt);
     free(src);
+    return done;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The same loop on the reference's DATA LAYOUT: the timing twin SURVEY.md 8(d) asks for beside the
+ * plain-array loop above ("per-node heap rows + reader/writer locks").  Same arithmetic and the
+ * same random draws as oracle_optimize (single-threaded the two produce bit-identical layouts:
+ * tests/test_oracle.py), but every memory operation of ce_optim_edge_shannon is performed the
+ * way the Rust code performs it:
+ *   - embedded: Vec<Arc<RwLock<Array1<F>>>> (embedder.rs:941,994-998): one heap block per node
+ *     holding the Arc counters, the lock word and the Array1 header, whose data is another heap
+ *     block;  get_embedded_data = Arc::clone (:1071-1073): one atomic increment + one decrement
+ *     of the row's strong count per access;
+ *   - .read().to_owned() (:1186-1187): shared lock (one compare-and-swap), a fresh heap copy of
+ *     the row, unlock;  *(...write()) = y (:1239,1301): exclusive lock, the copy BECOMES the row's
+ *     storage, the old block is freed;  negatives: try_read (:1257), a failed lock redraws;
+ *   - gradient: Array1::zeros(dim) (:1200), each `gradient = (&y - &y_i) * c` (:1230,1290)
+ *     allocates the difference, scales it in place and drops the previous gradient;
+ *   - edges: Vec<(NodeIdx, OutEdge<f32>)>, 24 bytes per edge (:939,975-984);  the rejection scan
+ *     get_edge (nodeparam.rs:83-85) walks the node's own Vec<OutEdge<f32>> (16 bytes per edge, one
+ *     heap block per node, kdumap.rs:63-87).
+ * The lock is parking_lot's word lock restated (uncontended paths only: one CAS to lock, one
+ * atomic to unlock; contention spins with sched_yield).  The generator stays xoshiro256++ (the
+ * reference's thread-local ChaCha12 costs more per draw): the twin is still an optimistic
+ * stand-in for the Rust loop, by less than the plain-array loop is.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t node; float weight; } rl_outedge_t;              /* OutEdge<f32> */
+typedef struct { uint64_t src; rl_outedge_t e; } rl_edge_t;                /* (NodeIdx, OutEdge<f32>) */
+typedef struct { rl_outedge_t *edges; uint64_t len, cap; float scale; } rl_nodeparam_t;   /* NodeParam, nodeparam.rs:72-76 */
+typedef struct {
+    atomic_long strong, weak;             /* ArcInner */
+    atomic_ulong lock;                    /* RawRwLock state */
+    float *data; uint64_t len, cap;       /* Array1<F>: OwnedRepr<F> ... */
+    float *ptr; uint64_t dim; int64_t stride; /* ... + view pointer, shape, stride */
+} rl_row_t;
+#define RL_WRITER 8ul
+#define RL_READER 16ul
+
+static inline int rl_try_read(rl_row_t *r)
+{
+    unsigned long st = atomic_load_explicit(&r->lock, memory_order_relaxed);
+    while (!(st & RL_WRITER))
+        if (atomic_compare_exchange_weak_explicit(&r->lock, &st, st + RL_READER, memory_order_acquire, memory_order_relaxed)) return 1;
+    return 0;
+}
+static inline void rl_read_unlock(rl_row_t *r) { atomic_fetch_sub_explicit(&r->lock, RL_READER, memory_order_release); }
+static inline void rl_write_lock(rl_row_t *r)
+{
+    for (;;) {
+        unsigned long zero = 0ul;
+        if (atomic_compare_exchange_weak_explicit(&r->lock, &zero, RL_WRITER, memory_order_acquire, memory_order_relaxed)) return;
+        if (zero != 0ul) sched_yield();
+    }
+}
+static inline void rl_write_unlock(rl_row_t *r) { atomic_store_explicit(&r->lock, 0ul, memory_order_release); }
+static inline rl_row_t *rl_get_embedded_data(rl_row_t **rows, uint64_t node)          /* :1071-1073 */
+{
+    rl_row_t *r = rows[node];
+    atomic_fetch_add_explicit(&r->strong, 1, memory_order_relaxed);
+    return r;
+}
+static inline void rl_drop(rl_row_t *r) { atomic_fetch_sub_explicit(&r->strong, 1, memory_order_release); }
+static inline float *rl_to_owned(const rl_row_t *r, uint32_t d)
+{
+    float *c = (float *)malloc(d * sizeof(float));
+    memcpy(c, r->ptr, d * sizeof(float));
+    return c;
+}
+static inline float *rl_read_owned(rl_row_t **rows, uint64_t node, uint32_t d)        /* get(..).read().to_owned() */
+{
+    rl_row_t *r = rl_get_embedded_data(rows, node);
+    while (!rl_try_read(r)) sched_yield();
+    float *c = rl_to_owned(r, d);
+    rl_read_unlock(r);
+    rl_drop(r);
+    return c;
+}
+static inline void rl_write_move(rl_row_t **rows, uint64_t node, float *y)            /* *(get(..).write()) = y */
+{
+    rl_row_t *r = rl_get_embedded_data(rows, node);
+    rl_write_lock(r);
+    float *old = r->data;
+    r->data = y; r->ptr = y;
+    rl_write_unlock(r);
+    rl_drop(r);
+    free(old);
+}
+static inline int rl_get_edge(const rl_nodeparam_t *np, uint64_t k)                   /* nodeparam.rs:83-85 */
+{
+    for (uint64_t m = 0; m < np->len; m++) if (np->edges[m].node == k) return 1;
+    return 0;
+}
+
+int64_t oracle_optimize_reference_layout(uint64_t n, uint32_t d, const uint64_t *row_ptr, const uint32_t *col,
+                                         const float *p, const float *emb_scale, float *y, double b,
+                                         double grad_step_init, uint32_t nb_sampling_by_edge, uint32_t nb_grad_batch,
+                                         const float *neg_w, uint64_t seed, uint32_t first_batch,
+                                         uint32_t n_batches_to_run, double sample_fraction, int n_threads,
+                                         double *loop_seconds)
+{
+    if (d > 64) return -1;
+    const uint64_t E = row_ptr[n];
+    rl_edge_t *edges = (rl_edge_t *)malloc(E * sizeof(rl_edge_t));                    /* :975-984 */
+    rl_nodeparam_t *node_params = (rl_nodeparam_t *)malloc(n * sizeof(rl_nodeparam_t));
+    rl_row_t **rows = (rl_row_t **)malloc(n * sizeof(rl_row_t *));
+    if (!edges || !node_params || !rows) return -2;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t k = row_ptr[i + 1] - row_ptr[i];
+        node_params[i].edges = (rl_outedge_t *)malloc((k ? k : 1) * sizeof(rl_outedge_t));
+        node_params[i].len = node_params[i].cap = k; node_params[i].scale = 0.0f;
+        rl_row_t *r = (rl_row_t *)malloc(sizeof(rl_row_t));
+        float *data = (float *)malloc(d * sizeof(float));
+        if (!node_params[i].edges || !r || !data) return -2;
+        for (uint64_t m = 0; m < k; m++) {
+            const uint64_t e = row_ptr[i] + m;
+            node_params[i].edges[m].node = col[e]; node_params[i].edges[m].weight = p[e];
+            edges[e].src = i; edges[e].e = node_params[i].edges[m];
+        }
+        atomic_init(&r->strong, 1); atomic_init(&r->weak, 1); atomic_init(&r->lock, 0ul);
+        memcpy(data, y + i * d, d * sizeof(float));
+        r->data = r->ptr = data; r->len = r->cap = r->dim = d; r->stride = 1;
+        rows[i] = r;
+    }
+    alias_t pos, negt;
+    if (alias_build(&pos, p, E)) return -2;                 /* :987 */
+    const int have_neg = neg_w != NULL;
+    if (have_neg && alias_build(&negt, neg_w, n)) return -2;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#else
+    (void)n_threads;
+#endif
+    const uint64_t nb_sample = (uint64_t)((double)nb_sampling_by_edge * (double)E * sample_fraction); /* :858 */
+    int64_t done = 0;
+    double t_loop = 0.0;
+    for (uint32_t iter = first_batch; iter < first_batch + n_batches_to_run && iter <= nb_grad_batch; iter++) {
+        const double grad_step = grad_step_init * (1.0 - (double)iter / (double)nb_grad_batch); /* :875 */
+        const double t0 = wall_seconds();
+#pragma omp parallel
+        {
+            rng_t rng;
+#ifdef _OPENMP
+            int tid = omp_get_thread_num();
+#else
+            int tid = 0;
+#endif
+            rng_seed(&rng, seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)iter << 20) + (uint64_t)tid);
+#pragma omp for schedule(static)
+            for (int64_t s = 0; s < (int64_t)nb_sample; s++) {
+                const uint64_t e = alias_draw(&pos, &rng);                           /* :1182 */
+                const uint64_t node_i = edges[e].src, node_j = edges[e].e.node;
+                float *y_i = rl_read_owned(rows, node_i, d);                         /* :1186 */
+                float *y_j = rl_read_owned(rows, node_j, d);                         /* :1187 */
+                float *gradient = (float *)calloc(d, sizeof(float));                 /* :1200 */
+                const double weight = (double)edges[e].e.weight;
+                const double scale = (double)emb_scale[node_i];
+                const double s2 = scale * scale;
+                float dsum = 0.0f;
+                for (uint32_t c = 0; c < d; c++) dsum += (y_i[c] - y_j[c]) * (y_i[c] - y_j[c]);
+                const double u = (double)dsum / s2;
+                const double coeff = common_coeff(u, s2, b);
+                if (u > 0.0) {
+                    const double alfa = (double)(1.0f / PROBA_MIN);
+                    const double rep = 1.0 / fmax(u * u, alfa);
+                    double cij = grad_step * coeff * (-weight + (1.0 - weight) * rep);
+                    cij = fmax(cij, -0.49);
+                    const float cf = (float)cij;
+                    float *t = (float *)malloc(d * sizeof(float));                   /* &y_j - &y_i */
+                    for (uint32_t c = 0; c < d; c++) t[c] = y_j[c] - y_i[c];
+                    for (uint32_t c = 0; c < d; c++) t[c] = t[c] * cf;               /* * coeff, in place */
+                    free(gradient); gradient = t;
+                }
+                for (uint32_t c = 0; c < d; c++) y_i[c] -= gradient[c];              /* :1237 */
+                for (uint32_t c = 0; c < d; c++) y_j[c] += gradient[c];              /* :1238 */
+                rl_write_move(rows, node_j, y_j);                                    /* :1239 */
+                int got = 0;
+                while (got < 5) {                                                    /* :1241-1299 */
+                    const uint64_t k = have_neg ? alias_draw(&negt, &rng) : rng_below(&rng, n);
+                    if (k == node_i || k == node_j || rl_get_edge(&node_params[node_i], k)) continue;
+                    rl_row_t *r = rl_get_embedded_data(rows, k);
+                    if (!rl_try_read(r)) { rl_drop(r); continue; }                   /* :1257-1265 */
+                    float *y_k = rl_to_owned(r, d);
+                    rl_read_unlock(r);
+                    rl_drop(r);
+                    got++;
+                    float dk = 0.0f;
+                    for (uint32_t c = 0; c < d; c++) dk += (y_i[c] - y_k[c]) * (y_i[c] - y_k[c]);
+                    const double dik = (double)dk;
+                    const double uk = dik / s2;
+                    const double ck = common_coeff(uk, s2, b);
+                    if (dik > 0.0) {
+                        const double rep = 1.0 / fmax(uk * uk, 1.0 / 16.0);
+                        const double cik = fmin(grad_step * ck * rep, 2.0);
+                        const float cf = (float)cik;
+                        float *t = (float *)malloc(d * sizeof(float));
+                        for (uint32_t c = 0; c < d; c++) t[c] = y_k[c] - y_i[c];
+                        for (uint32_t c = 0; c < d; c++) t[c] = t[c] * cf;
+                        free(gradient); gradient = t;
+                    }
+                    for (uint32_t c = 0; c < d; c++) y_i[c] -= gradient[c];          /* :1297 */
+                    free(y_k);
+                }
+                rl_write_move(rows, node_i, y_i);                                    /* :1301 */
+                free(gradient);
+            }
+        }
+        t_loop += wall_seconds() - t0;
+        done += (int64_t)nb_sample;
+    }
+    if (loop_seconds) *loop_seconds = t_loop;
+    for (uint64_t i = 0; i < n; i++) {                                               /* :888-899 copy-out */
+        memcpy(y + i * d, rows[i]->ptr, d * sizeof(float));
+        free(rows[i]->data); free(rows[i]); free(node_params[i].edges);
+    }
+    alias_free(&pos);
+    if (have_neg) alias_free(&negt);
+    free(rows); free(node_params); free(edges);
     return done;
 }
 

@@ -36,6 +36,7 @@ def lib() -> C.CDLL:
         _LIB = C.CDLL(build())
         _LIB.oracle_cross_entropy.restype = C.c_double
         _LIB.oracle_optimize.restype = C.c_int64
+        _LIB.oracle_optimize_reference_layout.restype = C.c_int64
     return _LIB
 
 
@@ -121,8 +122,11 @@ def hubness_weights(row_ptr, col):
 
 
 def optimize(row_ptr, col, p, emb_scale, y0, b=1.0, grad_step=2.0, nb_sampling_by_edge=10, nb_grad_batch=20,
-             neg_w=None, seed=0, first_batch=1, n_batches=None, sample_fraction=1.0, n_threads=0, timing=False):
-    """embedder.rs:794-904 Hogwild loop.  Returns (y, positive_samples_processed[, loop_seconds])."""
+             neg_w=None, seed=0, first_batch=1, n_batches=None, sample_fraction=1.0, n_threads=0, timing=False,
+             reference_layout=False):
+    """embedder.rs:794-904 Hogwild loop.  Returns (y, positive_samples_processed[, loop_seconds]).
+    reference_layout=True runs the same loop on the reference's data layout (per-node heap rows behind Arc + RwLock,
+    heap copies per access: oracle_optimize_reference_layout) -- the timing twin of SURVEY.md 8(d)."""
     row_ptr, col = _graph(row_ptr, col)
     p = np.ascontiguousarray(p, np.float32)
     emb_scale = np.ascontiguousarray(emb_scale, np.float32)
@@ -135,11 +139,12 @@ def optimize(row_ptr, col, p, emb_scale, y0, b=1.0, grad_step=2.0, nb_sampling_b
     if neg_w is not None:
         neg_w = np.ascontiguousarray(neg_w, np.float32)
         negp = _p(neg_w, C.c_float)
-    done = lib().oracle_optimize(C.c_uint64(n), C.c_uint32(d), _p(row_ptr, C.c_uint64), _p(col, C.c_uint32),
-                                 _p(p, C.c_float), _p(emb_scale, C.c_float), _p(y, C.c_float), C.c_double(b),
-                                 C.c_double(grad_step), C.c_uint32(nb_sampling_by_edge), C.c_uint32(nb_grad_batch),
-                                 negp, C.c_uint64(seed), C.c_uint32(first_batch), C.c_uint32(n_batches),
-                                 C.c_double(sample_fraction), C.c_int(n_threads), C.byref(secs))
+    fn = lib().oracle_optimize_reference_layout if reference_layout else lib().oracle_optimize
+    done = fn(C.c_uint64(n), C.c_uint32(d), _p(row_ptr, C.c_uint64), _p(col, C.c_uint32),
+              _p(p, C.c_float), _p(emb_scale, C.c_float), _p(y, C.c_float), C.c_double(b),
+              C.c_double(grad_step), C.c_uint32(nb_sampling_by_edge), C.c_uint32(nb_grad_batch),
+              negp, C.c_uint64(seed), C.c_uint32(first_batch), C.c_uint32(n_batches),
+              C.c_double(sample_fraction), C.c_int(n_threads), C.byref(secs))
     if done < 0:
         raise RuntimeError(f"oracle_optimize failed: {done}")
     if timing:

@@ -222,6 +222,31 @@ def test_hogwild_loop_improves_layout_and_counts_samples(small_graph):
     np.testing.assert_array_equal(w, np.clip(np.bincount(col, minlength=n), 1, n).astype(F))
 
 
+@pytest.mark.parametrize("d,b,hub", [(2, 1.0, False), (5, 0.5, True), (15, 1.0, False)])
+def test_reference_layout_twin_is_the_same_loop(d, b, hub):
+    """oracle_optimize_reference_layout (the CPU arm's timing twin: per-node heap rows behind Arc + RwLock, heap copies
+    per access, embedder.rs:939-941,1071-1073,1186-1301) applies the same samples with the same arithmetic as the
+    plain-array loop: on one thread the two layouts are bit-identical; on several threads both are Hogwild runs of the
+    same optimisation (finite, same sample count, cross entropy within the run-to-run spread)."""
+    row_ptr, col, dist = random_graph(1500, 3, 9, seed=21, zero_frac=0.05)
+    n = len(row_ptr) - 1
+    scale, p = oracle.edge_weights(row_ptr, col, dist)
+    es = oracle.embedded_scales(scale)
+    y0 = np.random.default_rng(2).uniform(-.5, .5, size=(n, d)).astype(F)
+    w = oracle.hubness_weights(row_ptr, col) if hub else None
+    ya, da = oracle.optimize(row_ptr, col, p, es, y0, b, 1.0, 10, 4, neg_w=w, seed=5, n_threads=1)
+    yb, db = oracle.optimize(row_ptr, col, p, es, y0, b, 1.0, 10, 4, neg_w=w, seed=5, n_threads=1, reference_layout=True)
+    assert da == db == 4 * 10 * len(col)
+    assert np.abs(ya - y0).max() > 0.1
+    np.testing.assert_array_equal(ya, yb)
+    ces = []
+    for rl in (False, True):
+        y, done = oracle.optimize(row_ptr, col, p, es, y0, b, 1.0, 10, 4, neg_w=w, seed=6, n_threads=4, reference_layout=rl)
+        assert done == da and np.isfinite(y).all()
+        ces.append(oracle.cross_entropy(row_ptr, col, p, es, y, b))
+    assert abs(ces[0] - ces[1]) < 0.15 * min(ces)
+
+
 def test_transformed_kgraph_running_minimum():
     row_ptr = np.array([0, 3, 4, 5, 6], np.uint64)
     col = np.array([1, 2, 3, 0, 0, 0], np.uint32)
