@@ -216,6 +216,9 @@ def cpu_arm(a, row_ptr, col, dist, y0, seconds, label, twin=False):
     scale, p = oracle.edge_weights(row_ptr, col, dist, 0.75, 1.0)
     es = oracle.embedded_scales(scale)
     t_w = time.time() - t0
+    t0 = time.time()
+    oracle.cross_entropy(row_ptr, col, p, es, y0[:, :a.dim], 1.0)          # K5: the reference evaluates it twice per embed (:846,885)
+    t_ce = time.time() - t0
     # all host cores (torchrun exports OMP_NUM_THREADS=1; the oracle sets its own thread count)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     E = len(col)
@@ -235,16 +238,17 @@ def cpu_arm(a, row_ptr, col, dist, y0, seconds, label, twin=False):
                                               reference_layout=True)
         extra["reference_layout"] = {
             "value": 6.0 * done_rl / secs_rl, "unit": UNIT, "positive_samples": int(done_rl), "seconds": secs_rl,
-            "extrapolated_embed_s": t_w + a.batches * 10.0 * E / (done_rl / secs_rl),
+            "extrapolated_embed_s": t_w + 2.0 * t_ce + a.batches * 10.0 * E / (done_rl / secs_rl),
             "note": "same loop, same arithmetic, on the reference's data layout: Vec<Arc<RwLock<Array1>>> rows (heap block per "
                     "node, Arc::clone + lock + heap copy per row access, the copy becomes the row on write), 24-byte edge "
                     "records, per-node edge vectors for the rejection scan (embedder.rs:939-941,1071-1073,1186-1301); "
                     "reported beside `value`, not used for any ratio"}
     return {**extra, "value": 6.0 * done / secs, "unit": UNIT, "cores": cores, "kind": "port",
-            "k1_seconds": t_w, "sample_fraction_of_a_batch": frac,
-            "extrapolated_embed_s": t_w + a.batches * batch_s,
+            "k1_seconds": t_w, "ce_seconds": t_ce, "sample_fraction_of_a_batch": frac,
+            "extrapolated_embed_s": t_w + 2.0 * t_ce + a.batches * batch_s,
             "sample": f"{label}: {done} positive samples = {frac:.4f} of one batch (of {a.batches}) of the same graph, "
-                      f"sampling loop only ({secs:.1f} s); K1 weights + scales took {t_w:.1f} s on the host and are not included",
+                      f"sampling loop only ({secs:.1f} s); K1 weights + scales took {t_w:.1f} s and one cross-entropy evaluation {t_ce:.1f} s on the host: "
+                      f"not in `value`, included in extrapolated_embed_s (K1 + 2 CE + {a.batches} batches)",
             "positive_samples": int(done), "seconds": secs}
 
 
