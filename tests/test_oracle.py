@@ -247,6 +247,37 @@ def test_reference_layout_twin_is_the_same_loop(d, b, hub):
     assert abs(ces[0] - ces[1]) < 0.15 * min(ces)
 
 
+def test_mini_embed_full_on_the_oracle():
+    """The reference's only end-to-end test of the path, embedder.rs:1435-1467 (mini_embed_full), run on the oracle: 500
+    points of gen_rand_data_f32 (:1419-1433: v = 2 i U * U per coordinate, dimension 20), L1 kNN graph with knbn = 10
+    (exact here, HNSW there), EmbedderParams::default() with asked_dim = 5 -- the reference asserts embed().is_ok(); here:
+    every weight row is a probability row, the loop finishes with finite coordinates, and graph neighbours end up closer
+    than random pairs (the cross entropy is NOT a monotone witness: from a random layout it rises, here as in the bench).
+    (tests/cpp/test_embedder.cpp runs the same case through the CUDA path.)"""
+    rng = np.random.default_rng(0)
+    n, dim, knbn = 500, 20, 10
+    val = 2.0 * np.arange(n, dtype=np.float32) * rng.random(n, dtype=np.float32)
+    data = val[:, None] * rng.random((n, dim), dtype=np.float32)
+    l1 = np.abs(data[:, None, :] - data[None, :, :]).sum(-1)
+    np.fill_diagonal(l1, np.inf)
+    idx = np.argsort(l1, axis=1, kind="stable")[:, :knbn]
+    dist = np.take_along_axis(l1, idx, 1).astype(F)
+    row_ptr = (np.arange(n + 1) * knbn).astype(np.uint64)
+    col = idx.astype(np.uint32).ravel()
+    scale, p = oracle.edge_weights(row_ptr, col, dist.ravel())            # scale_rho 1, beta 1: embedparams.rs:107-132
+    np.testing.assert_allclose(p.reshape(n, knbn).sum(1), 1.0, rtol=1e-5)
+    assert (p > 0).all() and (scale > 0).all()
+    es = oracle.embedded_scales(scale)
+    y0 = rng.uniform(-.5, .5, size=(n, 5)).astype(F)                      # get_random_init(1.), embedder.rs:456-470
+    y, done = oracle.optimize(row_ptr, col, p, es, y0, 1.0, 2.0, 10, 20, seed=1, n_threads=2)   # defaults: grad_step 2, 20 batches
+    assert done == 20 * 10 * len(col) and np.isfinite(y).all()
+    assert np.isfinite(oracle.cross_entropy(row_ptr, col, p, es, y, 1.0))
+    src = np.repeat(np.arange(n), knbn)
+    d_edges = np.linalg.norm(y[src] - y[col], axis=1)
+    d_rand = np.linalg.norm(y[rng.integers(0, n, 5000)] - y[rng.integers(0, n, 5000)], axis=1)
+    assert np.median(d_edges) < 0.5 * np.median(d_rand), (np.median(d_edges), np.median(d_rand))
+
+
 def test_transformed_kgraph_running_minimum():
     row_ptr = np.array([0, 3, 4, 5, 6], np.uint64)
     col = np.array([1, 2, 3, 0, 0, 0], np.uint32)
