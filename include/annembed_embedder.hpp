@@ -78,6 +78,53 @@ struct KGraph {
     uint64_t get_data_id_from_idx(size_t idx) const { return data_id.empty() ? idx : data_id[idx]; }   // :335
 };
 
+// The ANNKGCSR interchange file (the same bytes as annembed_b200/kgraph.py write_csr / read_csr and rust/kgraph_csr.rs;
+// the reference's KGraph has no serialisation).  Little endian (the only byte order this library runs on):
+//   magic 8 bytes "ANNKGCSR"; u32 version = 1, u32 flags = 0; u64 n, u64 E, u64 max_nbng;
+//   u64 row_ptr[n+1]; u32 col[E]; f32 dist[E]; u64 data_id[n]
+inline void write_csr(const std::string &path, const KGraph &g)
+{
+    const uint64_t n = g.get_nb_nodes(), E = g.col.size();
+    if (g.row_ptr.size() != n + 1 || g.dist.size() != E || g.row_ptr.back() != E || (!g.data_id.empty() && g.data_id.size() != n))
+        throw std::invalid_argument("write_csr: inconsistent CSR arrays");
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("write_csr: cannot open " + path);
+    const uint32_t head[2] = {1u, 0u};
+    const uint64_t sizes[3] = {n, E, (uint64_t)g.max_nbng};
+    bool ok = std::fwrite("ANNKGCSR", 1, 8, f) == 8 && std::fwrite(head, 4, 2, f) == 2 && std::fwrite(sizes, 8, 3, f) == 3 &&
+              std::fwrite(g.row_ptr.data(), 8, n + 1, f) == n + 1 && std::fwrite(g.col.data(), 4, E, f) == E &&
+              std::fwrite(g.dist.data(), 4, E, f) == E;
+    if (ok) {
+        if (g.data_id.empty()) { for (uint64_t i = 0; i < n && ok; i++) ok = std::fwrite(&i, 8, 1, f) == 1; }   // identity DataIds
+        else ok = std::fwrite(g.data_id.data(), 8, n, f) == n;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) throw std::runtime_error("write_csr: short write to " + path);
+}
+
+inline KGraph read_csr(const std::string &path)
+{
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("read_csr: cannot open " + path);
+    struct Closer { FILE *f; ~Closer() { std::fclose(f); } } closer{f};
+    char magic[8];
+    uint32_t head[2];
+    uint64_t sizes[3];
+    if (std::fread(magic, 1, 8, f) != 8 || std::string(magic, 8) != "ANNKGCSR") throw std::runtime_error("not an ANNKGCSR file");
+    if (std::fread(head, 4, 2, f) != 2 || head[0] != 1u) throw std::runtime_error("unsupported ANNKGCSR version");
+    if (std::fread(sizes, 8, 3, f) != 3) throw std::runtime_error("truncated ANNKGCSR file");
+    const uint64_t n = sizes[0], E = sizes[1];
+    if (n >= 0xFFFFFFFFull || E >= 0xFFFFFFFFull) throw std::runtime_error("ANNKGCSR: n and E must be below 2^32 - 1");   // the library's limits
+    KGraph g;
+    g.max_nbng = (size_t)sizes[2];
+    g.row_ptr.resize(n + 1); g.col.resize(E); g.dist.resize(E); g.data_id.resize(n);
+    if (std::fread(g.row_ptr.data(), 8, n + 1, f) != n + 1 || std::fread(g.col.data(), 4, E, f) != E ||
+        std::fread(g.dist.data(), 4, E, f) != E || std::fread(g.data_id.data(), 8, n, f) != n)
+        throw std::runtime_error("truncated ANNKGCSR file");
+    if (g.row_ptr[0] != 0 || g.row_ptr[n] != E) throw std::runtime_error("ANNKGCSR: row_ptr[n] != E");
+    return g;
+}
+
 // ≙ Err(1) of Embedder::embed (embedder.rs:183,366-369)
 struct EmbedError : std::runtime_error {
     int status;

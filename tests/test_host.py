@@ -387,3 +387,33 @@ def test_node_alias_table_encodes_the_node_law(n):
     # an accept probability is an fp32 number in [0, 1]: 2^-24 / n absolute per entry that points at a node
     cnt = np.bincount(alias, minlength=n) + 1
     assert (np.abs(P - law) <= 1e-7 * cnt / n + 1e-12).all()
+
+
+def test_cpp_mirror_reads_and_writes_the_csr_file(tmp_path):
+    """N4: the ANNKGCSR file through the C++ mirror (include/annembed_embedder.hpp read_csr / write_csr; CPU-only driver
+    tests/cpp/test_kgraph_io.cpp): a file written by annembed_b200/kgraph.py is read, checked (rows ascending,
+    kgraph.rs:508-509) and written back byte for byte; truncated files, a wrong magic and row_ptr[n] != E are refused."""
+    import os
+    import subprocess
+    from annembed_b200.kgraph import KGraph, read_csr, write_csr
+    here = os.path.join(os.path.dirname(__file__), "cpp")
+    subprocess.run(["make", "-C", here, "-s", "test_kgraph_io"], check=True)
+    exe = os.path.join(here, "test_kgraph_io")
+    row_ptr, col, dist = random_graph(300, 1, 9, seed=5, zero_frac=0.1)
+    ids = np.random.default_rng(1).permutation(300).astype(np.uint64) + 1000
+    g = KGraph(row_ptr, col, dist, ids, max_nbng=9)
+    a, b = str(tmp_path / "a.csr"), str(tmp_path / "b.csr")
+    write_csr(a, g)
+    out = subprocess.run([exe, a, b], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip() == f"n=300 E={len(col)} max_nbng=9 first_id={int(ids[0])}"
+    assert open(a, "rb").read() == open(b, "rb").read()
+    g2 = read_csr(b)
+    np.testing.assert_array_equal(g2.col, col); np.testing.assert_array_equal(g2.data_id, ids)
+    raw = open(a, "rb").read()
+    bad = str(tmp_path / "bad.csr")
+    broken_row_ptr = bytearray(raw); broken_row_ptr[40 + 8 * 300] ^= 1          # low byte of row_ptr[n]
+    for blob in (raw[:-5], b"ANNKGCSX" + raw[8:], raw[:8] + (2).to_bytes(4, "little") + raw[12:], bytes(broken_row_ptr)):
+        open(bad, "wb").write(blob)
+        out = subprocess.run([exe, bad, "bad"], capture_output=True, text=True)
+        assert out.returncode == 0 and out.stdout.startswith("error:"), out.stdout
