@@ -41,3 +41,26 @@ def test_unique_id_broadcast_and_shards(tmp_path):
     np.testing.assert_array_equal(r0[:128], (np.arange(128) * 7 % 251))
     np.testing.assert_array_equal(r0[:128], r1[:128])
     assert r0[128] == 0 and r0[129] == r1[128] == 512 and r1[129] == n
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone runs the CPU arm and prints
+    ONE JSON line (same metric / unit / config object as the GPU arm's), the other rank exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--nodes", "20000", "--steps", "1", "--warmup", "0", "--cpu-seconds", "0.2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "edge_updates_per_s" and d["unit"] == "edge updates/s" and d["n_gpus"] == 2
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["reference_layout"]["value"] > 0 and set(d["config"]) == {"workload", "l2", "cpu_arm"}
