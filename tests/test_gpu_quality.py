@@ -2,7 +2,7 @@
 
 Same graph, same initial layout, same parameters (examples/mnist_digits.rs:92-100: 30 batches, grad_step 1,
 10 samples/edge).  The reference is unseeded and asynchronous, so parity is distributional:
-means over 5 independent runs of the quality statistics of embedder.rs:620-753 (+ kNN preservation) within 1 %
+means over 20 independent runs of the quality statistics of embedder.rs:620-753 (+ kNN preservation) within 1 %
 (the two ratio statistics, noisier, within 1.5 % / 2 %)."""
 import numpy as np
 import pytest
@@ -13,7 +13,10 @@ from oracle import oracle, quality
 
 pytestmark = pytest.mark.gpu
 
-N, NBNG, RUNS = 20000, 50, 5
+# 20 runs per side: at 20 000 nodes a single run's median edge ratio moves by 1.2 % (oracle, 8 runs: 0.409 +- 0.0047), so the
+# difference of two 5-run means has a standard error of 0.7 % -- the 1.5 % gate below would be a two-sigma test of the noise.
+# With 20 runs it is four sigma (0.37 %); the other statistics are far inside their gates either way.
+N, NBNG, RUNS = 20000, 50, 20
 
 
 @pytest.fixture(scope="module")
@@ -56,7 +59,7 @@ def test_quality_statistics_within_one_percent_of_oracle(data, k, scale_rho, nb_
     print("oracle", r, "\ncuda  ", o)
     for k in ("mean_nbmatch", "knn_preservation"):
         assert abs(o[k] - r[k]) <= 0.01 * abs(r[k]), (k, o[k], r[k])
-    # the ratio statistics of the oracle itself move by +-0.5 % between sets of 5 runs
+    # the ratio statistics of the oracle itself move by +-0.5 % between sets of 5 runs (+-0.25 % between sets of 20)
     assert abs(o["median_ratio"] - r["median_ratio"]) <= 0.015 * r["median_ratio"], (o["median_ratio"], r["median_ratio"])
     assert abs(o["mean_ratio"] - r["mean_ratio"]) <= 0.02 * r["mean_ratio"]
     # a count of rare events: within 1 % of the node count
